@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py - depth-maps/s of the MVSFormer++ depth-inference hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA library behind the reference seams)
+  python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the reference's algorithm on the host cores
+
+A step = one pass of the hot path (FMT -> 4-stage cascade: warp + group-correlation + visibility aggregation ->
+cost regularisation -> soft-argmax) over one batch of synthetic reference views; the workload is BASELINE.json
+configs[1] (DTU test config: V=5, numdepth 192, 1152x1536, ndepths 32/16/8/4), one depth map per GPU per step
+(weak scaling: reference views shard embarrassingly; NCCL only gathers the depth maps).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "dtu": dict(name="DTU test config: V=5 views, numdepth=192 (425..931mm), 1152x1536, ndepths [32,16,8,4], "
+                     "feature pyramids C=[64,32,16,8] (BASELINE.json configs[1])", V=5, H=1152, W=1536, numdepth=192),
+    "small": dict(name="plumbing: V=3, numdepth=48, 128x192", V=3, H=128, W=192, numdepth=48),
+}
+TMP = [5.0, 5.0, 5.0, 1.0]
+
+
+def algorithmic_bytes(V, H, W, feat_chs=(64, 32, 16, 8), ndepths=(32, 16, 8, 4), G=8):
+    """4*[V*C*HW + D*HW + G*D*HW] per stage (features once, hypotheses once, volume once)."""
+    out = []
+    for c, d, sc in zip(feat_chs, ndepths, (8, 4, 2, 1)):
+        hw = (H // sc) * (W // sc)
+        out.append(4 * (V * c * hw + d * hw + G * d * hw))
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(o[0]))
+                self.max_mhz = float(o[1])
+                for n, v in zip(names, o[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_inputs(wl, seed, jitter=0.0):
+    from mvsformerplusplus_b200 import synth
+    feats = synth.make_features(wl["V"], wl["H"], wl["W"], seed=seed, smooth=False)
+    proj = synth.make_proj_matrices(wl["V"], wl["H"], wl["W"], jitter=jitter)
+    dv = synth.make_depth_values(wl["numdepth"], 425.0, 2.65 * 192 / wl["numdepth"])
+    return feats, proj, dv
+
+
+def make_net(seed=7):
+    import torch
+    from mvsformerplusplus_b200 import synth
+    from mvsformerplusplus_b200.config import default_args
+    from mvsformerplusplus_b200.hotpath import HotPathNet
+    torch.manual_seed(0)
+    net = HotPathNet(default_args()).eval()
+    sd = synth.randomize_state_dict(net, seed=seed)
+    return net, sd
+
+
+# ======================================================================================================
+def cpu_reference_pass(wl, threads, seed=1234):
+    """One pass of the reference's algorithm on the host (oracle port with the reference's own ATen kernels:
+    F.grid_sample + SDPA, fp32).  Returns seconds."""
+    import torch
+    from mvsformerplusplus_b200.config import default_args
+    from oracle import hotpath as O  # bench.py's cpu_baseline leg is one of the three allowed oracle users
+    O.USE_ATEN_KERNELS = True
+    torch.set_num_threads(threads)
+    net, sd = make_net()
+    feats, proj, dv = make_inputs(wl, seed)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.hotpath_forward(feats, proj, dv, sd, default_args(), tmp=TMP)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(a, wl, rank, world):
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    threads = os.cpu_count() or 1
+    times = []
+    for i in range(a.warmup + a.steps):
+        dt = cpu_reference_pass(wl, threads)
+        if i >= a.warmup:
+            times.append(dt)
+    ms = 1000.0 * sum(times) / len(times)
+    val = 1000.0 / ms
+    sample = "1 full depth map (whole workload, fp32, oracle port calling the reference's ATen kernels) per step"
+    line = {"impl": "reference", "metric": "depth-maps/sec (hot path: FMT + 4-stage cascade)", "value": val, "unit": "depth-maps/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "host_threads": threads},
+            "cpu_baseline": {"value": val, "unit": "depth-maps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "depth-maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================================
+def run_ours(a, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from mvsformerplusplus_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device - the B200 hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    net, _ = make_net()
+    net = net.to(dev)
+    B = a.batch
+    # per-rank shard of reference views: distinct seeds / jittered cameras
+    host_inputs = []
+    for b in range(B):
+        feats, proj, dv = make_inputs(wl, 1234 + rank * B + b, jitter=0.02 * ((rank * B + b) % 5))
+        host_inputs.append(({k: v.pin_memory() for k, v in feats.items()}, {k: v.pin_memory() for k, v in proj.items()},
+                            dv.pin_memory()))
+    dev_inputs = [({k: v.to(dev) for k, v in f.items()}, {k: v.to(dev) for k, v in p.items()}, d.to(dev))
+                  for f, p, d in host_inputs]
+    h2d = sum(sum(v.numel() * 4 for v in f.values()) + sum(v.numel() * 4 for v in p.values()) + d.numel() * 4
+              for f, p, d in host_inputs)
+    H, W = wl["H"], wl["W"]
+    gather_buf = torch.empty((world, B, 2, H, W), device=dev) if world > 1 else None
+    local_buf = torch.empty((B, 2, H, W), device=dev)
+    host_out = torch.empty((B, 2, H, W)).pin_memory()
+
+    def step_resident():
+        for b, (f, p, d) in enumerate(dev_inputs):
+            out = net.forward_features(f, p, d, TMP)
+            local_buf[b, 0].copy_(out["refined_depth"][0])
+            local_buf[b, 1].copy_(out["photometric_confidence"][0])
+        if world > 1:  # the only collective on the path: gather of the depth maps
+            dist.all_gather_into_tensor(gather_buf.view(-1), local_buf.view(-1))
+
+    def step_e2e():
+        for b, (f, p, d) in enumerate(host_inputs):
+            fd = {k: v.to(dev, non_blocking=True) for k, v in f.items()}
+            pd = {k: v.to(dev, non_blocking=True) for k, v in p.items()}
+            out = net.forward_features(fd, pd, d.to(dev, non_blocking=True), TMP)
+            local_buf[b, 0].copy_(out["refined_depth"][0])
+            local_buf[b, 1].copy_(out["photometric_confidence"][0])
+        host_out.copy_(local_buf, non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gather_buf.view(-1), local_buf.view(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.launch_count(reset=True)
+    ms_step = timed(step_resident, a.steps, max(a.warmup, 3))
+    launches = _lib.launch_count(reset=True) // (a.steps + max(a.warmup, 3))
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, a.steps, max(a.warmup, 3))
+    d2h = host_out.numel() * 4
+
+    # ---- per-entry-point device time (CUDA events on the launching stream) for the roofline of the fused
+    #      warp + group-correlation kernels (pass A entropy + pass B aggregation, all 4 stages)
+    line_extra = {}
+    if rank == 0:
+        f, p, d = dev_inputs[0]
+        reps = 3
+        with _lib.profile_calls() as prof:
+            for _ in range(reps):
+                net.forward_features(f, p, d, TMP)
+        summ = prof.summary()
+        per_map = {k: v["ms"] / reps for k, v in summ.items()}
+        t_wc = per_map.get("mvsf_warp_corr_entropy", 0.0) + per_map.get("mvsf_warp_corr_aggregate", 0.0)
+        alg = algorithmic_bytes(wl["V"], H, W)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, which = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, which = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        achieved = sum(alg) / 1e9 / (t_wc / 1e3) if t_wc > 0 else 0.0
+        line_extra["roofline"] = {"bound": "hbm", "kernel": "warp_corr_entropy + warp_corr_aggregate (8 launches / depth map)",
+                                  "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                  "traffic": None, "peak_source": which, "algorithmic_bytes_per_depth_map": sum(alg),
+                                  "kernel_ms_per_depth_map": t_wc}
+        line_extra["kernel_ms_per_depth_map"] = {k.replace("mvsf_", ""): round(v, 4) for k, v in sorted(per_map.items())}
+
+    if rank == 0:
+        cpu = None
+        if not a.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            dt = cpu_reference_pass(wl, threads)
+            cpu = {"value": 1.0 / dt, "unit": "depth-maps/s", "cores": threads, "kind": "port",
+                   "sample": "1 full depth map of the same workload (cold, fp32, oracle port calling the reference's ATen "
+                             "kernels F.grid_sample + SDPA)"}
+        maps = B * world
+        line = {"metric": "depth-maps/sec (hot path: FMT + 4-stage cascade)", "value": maps * 1000.0 / ms_step,
+                "unit": "depth-maps/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "ref_views_per_gpu_per_step": B, "parallelism": f"shard{world}",
+                           "l2": "inputs_larger_than_l2 (531 MB feature pyramids per depth map)",
+                           "precision": "fp32 parity mode (all kernels fp32 SIMT)"},
+                "e2e": {"value": maps * 1000.0 / ms_e2e, "unit": "depth-maps/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches, "clocks": clocks,
+                "cpu_baseline": cpu}
+        line.update(line_extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="dtu", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=1, help="reference views per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[a.workload]
+    if a.impl == "reference":
+        if a.steps > 3:
+            a.steps = 3  # each step is ~15-60 s of host work; keep the arm within minutes
+        a.warmup = min(a.warmup, 1)
+        run_reference_arm(a, wl, rank, world)
+        return
+    run_ours(a, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+/*
+ * libmvsf_b200 - C ABI of the B200-native MVSFormer++ depth-inference hot path.
+ *
+ * The reference (maybeLx/MVSFormerPlusPlus) has no FFI layer: its seams are Python callables
+ * (SURVEY.md §8b).  Each entry point below states the reference callable (file:line, relative to the
+ * reference repo root) whose arithmetic it replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer to fp32 data unless marked "host"; buffers are owned by the
+ *     caller and borrowed for the duration of the call (the reference's torch tensors play this role);
+ *   - one sample per call (the reference's eval path is batch-1: DINOv2_mvsformer_model.py:88);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls never synchronise;
+ *   - return 0 on success, a negative mvsf_status otherwise; mvsf_last_error() gives the message
+ *     (the Python host raises RuntimeError, mirroring the reference's Python exceptions);
+ *   - there is no CPU fallback and no dispatch: a missing/failed CUDA path is an error.
+ *
+ * Layouts (HBM):  feature maps are channels-last  [V][H][W][C];  hypothesis / probability volumes are
+ * depth-major [D][H][W] (the reference's [B,D,H,W] with B=1);  cost volumes are [D][H][W][G] (NDHWC);
+ * tokens are [L][C].  Packed-weight layouts are documented per function and produced by
+ * mvsformerplusplus_b200/packing.py from a reference state_dict (BatchNorm folded, eval mode).
+ */
+#ifndef MVSF_B200_H
+#define MVSF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mvsf_stream_t; /* cudaStream_t */
+
+enum mvsf_status {
+  MVSF_OK = 0,
+  MVSF_ERR_INVALID = -1,     /* bad argument / unsupported shape (reference: AssertionError / NotImplementedError) */
+  MVSF_ERR_CUDA = -2,        /* CUDA launch or runtime error */
+  MVSF_ERR_WORKSPACE = -3    /* workspace too small */
+};
+
+const char* mvsf_last_error(void);
+int mvsf_abi_version(void);
+/* number of kernel launches issued by this library on the calling thread since the last reset (bench.py's gpu_launches) */
+long long mvsf_launch_count(int reset);
+
+/* ---- layout helpers at the boundary (reference tensors are NCHW: DINOv2_mvsformer_model.py:95-98) */
+int mvsf_nchw_to_nhwc(const float* src, float* dst, int N, int C, int HW, mvsf_stream_t stream);
+int mvsf_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, mvsf_stream_t stream);
+
+/* ---- W1: projection prep.  models/cost_volume.py:68-71 + models/warping.py:80-82 (src@inv(ref), rot/trans)
+ *      and torch.inverse(K) of models/position_encoding.py:146.
+ * proj [V][2][4][4] (slot 0 extrinsic, slot 1[:3,:3] intrinsic; view 0 = reference view).
+ * homs [(V-1)][12]: rot row-major (9) then trans (3) of  P_src * P_ref^-1.   kinv_ref [9] row-major. */
+int mvsf_compose_geometry(const float* proj, int V, float* homs, float* kinv_ref, mvsf_stream_t stream);
+
+/* ---- F5: models/module.py:692-704 init_inverse_range.  depth_values [Dn] -> out [D][H][W] */
+int mvsf_init_inverse_range(const float* depth_values, int Dn, float* out, int D, int H, int W, mvsf_stream_t stream);
+/* ---- F6: models/module.py:707-724 schedule_inverse_range (shift=False).
+ * prev_depth [H/2][W/2], prev_hypo [Dp][H/2][W/2] (only planes 1 and 2 are read) -> out [D][H][W] */
+int mvsf_schedule_inverse_range(const float* prev_depth, const float* prev_hypo, int Dp, float split_itv, float* out,
+                                int D, int H, int W, mvsf_stream_t stream);
+/* ---- F7: models/position_encoding.py:138-161 get_position_3d(normalize=True).
+ * stats [6] = {width_min,width_max,height_min,height_max,depth_min,depth_max}; when compute_minmax != 0 the
+ * first four are computed from this call's positions (stage 1) else reused.  pos [3][D][H][W]. */
+int mvsf_position3d(const float* kinv_ref, const float* depth, const float* depth_values, int Dn, float* stats,
+                    int compute_minmax, float* pos, int D, int H, int W, mvsf_stream_t stream);
+
+/* ---- W2 (finest seam): models/warping.py:69-109 homo_warping_3D_with_mask.
+ * src [H][W][C], hom [12], depth [D][H][W] -> warped [C][D][H][W] (reference layout), mask [D][H][W] u8 or NULL */
+int mvsf_homo_warp(const float* src_nhwc, const float* hom, const float* depth, float* warped, uint8_t* mask, int C,
+                   int D, int H, int W, mvsf_stream_t stream);
+
+/* ---- W2+W3+W4 pass A: warp + group correlation summed over groups + softmax-entropy over D.
+ * models/cost_volume.py:72-92.  feat [V][H][W][C] (view 0 = reference), homs [(V-1)][12], depth [D][H][W]
+ * -> entropy [(V-1)][H][W].   The (V-1,C,D,H,W) warped volume is never written. */
+int mvsf_warp_corr_entropy(const float* feat, const float* homs, const float* depth, float* entropy, int V, int C,
+                           int G, int D, int H, int W, mvsf_stream_t stream);
+/* ---- W4 visibility CNN: models/cost_volume.py:37,93.  entropy [N][H][W] -> vis [N][H][W].
+ * wts: packed, BN folded: w1[9][16] b1[16] w2[16 ic][9][16 oc] b2[16] w3[16 ic][9][8 oc] b3[8] w4[8] b4[1] (=3649 floats) */
+int mvsf_vis_cnn(const float* entropy, const float* wts, float* vis, int N, int H, int W, mvsf_stream_t stream);
+/* ---- W2+W3+W4 pass B: recompute warp + group correlation, weight by vis, reduce over views.
+ * models/cost_volume.py:72-101 -> volume [D][H][W][G] = sum_v w_v*inprod_v / (sum_v w_v + 1e-6) */
+int mvsf_warp_corr_aggregate(const float* feat, const float* homs, const float* depth, const float* vis,
+                             float* volume, int V, int C, int G, int D, int H, int W, mvsf_stream_t stream);
+
+/* ---- R2-R4: models/module.py:367-408 (kind 0: CostRegNet, stride 2, 3^3 prob no bias) and
+ *      :453-504 (kind 1: CostRegNet3D, stride (1,2,2), 1^3 prob + bias).  volume [D][H][W][C] -> logits [D][H][W].
+ * wts: packed by packing.pack_costreg_unet (per layer [27][Cin][Cout] with BN scale folded, then bias[Cout]). */
+int mvsf_costreg_unet_workspace_bytes(int kind, int C, int D, int H, int W, size_t* bytes);
+int mvsf_costreg_unet_forward(int kind, const float* volume, const float* wts, float* logits, void* workspace,
+                              size_t workspace_bytes, int C, int D, int H, int W, mvsf_stream_t stream);
+
+/* ---- R1: models/module.py:602-646 PureTransformerCostReg (+ position_encoding.py:164-189 PositionEncoding3D).
+ * volume [D][H][W][C] is modified in place by the PE add; pos [3][D][H][W] or NULL.
+ * Fixed by the shipped config: down_rate (2,4,4), mid 64, heads 4, mlp 256.  softmax_scale = hd^-0.5*log_tal(N). */
+int mvsf_costreg_tr_workspace_bytes(int C, int D, int H, int W, size_t* bytes);
+int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, float* logits, void* workspace,
+                            size_t workspace_bytes, int C, int D, int H, int W, int layers, float softmax_scale,
+                            mvsf_stream_t stream);
+
+/* ---- S1: models/cost_volume.py:105-117 + models/module.py:649-655 (eval, depth_type 'ce').
+ * logits [D][H][W], depth hypotheses [D][H][W] -> prob [D][H][W], depth [H][W], conf [H][W] */
+int mvsf_softargmax(const float* logits, const float* depth_hypo, float tmp, float* prob, float* depth, float* conf,
+                    int D, int H, int W, mvsf_stream_t stream);
+/* ---- S2: DINOv2_mvsformer_model.py:167-177: acc (+)= scale * nearest_upsample(conf) ; init!=0 overwrites */
+int mvsf_conf_accumulate(const float* conf, int h, int w, float* acc, int H, int W, float scale, int init,
+                         mvsf_stream_t stream);
+
+/* ---- F1-F4: models/FMT.py:164-206 FMT_with_pathway.forward.
+ * Inputs are the reference's NCHW pyramids: f1 [V][64][H1][W1], f2 [V][32][2H1][2W1], f3 [V][16][4H1][4W1],
+ * f4 [V][8][8H1][8W1]; pe [H1*W1][64] is the PositionEncodingSineNorm table (position_encoding.py:61-74).
+ * Outputs are channels-last: o1 [V][H1][W1][64] ... o4 [V][8H1][8W1][8].  wts: packing.pack_fmt. */
+int mvsf_fmt_workspace_bytes(int V, int H1, int W1, size_t* bytes);
+int mvsf_fmt_forward(const float* f1, const float* f2, const float* f3, const float* f4, const float* pe,
+                     const float* wts, float* o1, float* o2, float* o3, float* o4, void* workspace,
+                     size_t workspace_bytes, int V, int H1, int W1, mvsf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSF_B200_H */

@@ -1,0 +1,104 @@
+"""ctypes binding of libmvsf_b200.so (include/mvsf_b200.h).  There is no fallback: if the library is missing or a
+call fails, a RuntimeError is raised (the reference's seams raise Python exceptions: SURVEY.md §8b)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmvsf_b200.so")
+_lib = None
+
+P, I, F, Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+SIGNATURES = {
+    "mvsf_abi_version": ([], I),
+    "mvsf_launch_count": ([I], ctypes.c_longlong),
+    "mvsf_nchw_to_nhwc": ([P, P, I, I, I, P], I),
+    "mvsf_nhwc_to_nchw": ([P, P, I, I, I, P], I),
+    "mvsf_compose_geometry": ([P, I, P, P, P], I),
+    "mvsf_init_inverse_range": ([P, I, P, I, I, I, P], I),
+    "mvsf_schedule_inverse_range": ([P, P, I, F, P, I, I, I, P], I),
+    "mvsf_position3d": ([P, P, P, I, P, I, P, I, I, I, P], I),
+    "mvsf_homo_warp": ([P, P, P, P, P, I, I, I, I, P], I),
+    "mvsf_warp_corr_entropy": ([P, P, P, P, I, I, I, I, I, I, P], I),
+    "mvsf_vis_cnn": ([P, P, P, I, I, I, P], I),
+    "mvsf_warp_corr_aggregate": ([P, P, P, P, P, I, I, I, I, I, I, P], I),
+    "mvsf_costreg_unet_workspace_bytes": ([I, I, I, I, I, ctypes.POINTER(Z)], I),
+    "mvsf_costreg_unet_forward": ([I, P, P, P, P, Z, I, I, I, I, P], I),
+    "mvsf_costreg_tr_workspace_bytes": ([I, I, I, I, ctypes.POINTER(Z)], I),
+    "mvsf_costreg_tr_forward": ([P, P, P, P, P, Z, I, I, I, I, I, F, P], I),
+    "mvsf_softargmax": ([P, P, F, P, P, P, I, I, I, P], I),
+    "mvsf_conf_accumulate": ([P, I, I, P, I, I, F, I, P], I),
+    "mvsf_fmt_workspace_bytes": ([I, I, I, ctypes.POINTER(Z)], I),
+    "mvsf_fmt_forward": ([P] * 11 + [Z, I, I, I, P], I),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m mvsformerplusplus_b200.build` "
+                               "(the B200 hot path has no CPU/PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.mvsf_last_error.restype = ctypes.c_char_p
+        L.mvsf_last_error.argtypes = []
+        for name, (argt, rest) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported
+            fn.argtypes = argt
+            fn.restype = rest
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().mvsf_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (status {rc}): {msg}")
+
+
+def launch_count(reset=False):
+    return int(lib().mvsf_launch_count(1 if reset else 0))
+
+
+class profile_calls:
+    """Context manager: brackets every library call with CUDA events on the current stream and reports device
+    milliseconds per entry point (used by bench.py for the roofline of the warp+correlation kernels).
+    Timing-only instrumentation; it does not change what is launched."""
+
+    def __init__(self):
+        self.records = []  # (name, start_event, end_event)
+
+    def __enter__(self):
+        import torch
+        L = lib()
+        self._orig = {}
+        for name in SIGNATURES:
+            if name.endswith("_workspace_bytes") or name in ("mvsf_abi_version", "mvsf_launch_count"):
+                continue
+            fn = getattr(L, name)
+            self._orig[name] = fn
+
+            def wrapped(*a, _fn=fn, _name=name):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                rc = _fn(*a)
+                e.record()
+                self.records.append((_name, s, e))
+                return rc
+            setattr(L, name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        L = lib()
+        for name, fn in self._orig.items():
+            setattr(L, name, fn)
+        return False
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0})
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+        return out

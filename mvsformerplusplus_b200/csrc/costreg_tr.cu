@@ -1,0 +1,270 @@
+// R1: stage-1 transformer cost regulariser, models/module.py:602-646 (PureTransformerCostReg) with
+// FlashAttnBlock post-norm blocks (:569-582), LayerNorm3D (:586-599), PositionEncoding3D
+// (models/position_encoding.py:164-189) and the entropy-invariance softmax scale (attention.py:158-161).
+//
+// volume [D][H][W][8] --(+pe_proj(PE3D))--> patchify (2,4,4) GEMM K=256 + LN3D --> tokens [N][64]
+//   6 x { qkv GEMM -> softmax attention (4 heads x 16) -> proj GEMM + gamma1/residual/LN -> FFN GEMMs + gamma2/residual/LN }
+//   --> un-patchify GEMM (64 -> 2*4*4*8) --> per-voxel LN3D(8) + 1x1x1 prob --> logits [D][H][W]
+// Softmax attention is order-free over tokens, so tokens are kept in (d', h', w') raster order instead of the
+// reference's "(h w d)" (module.py:573) - the result is identical.
+#include <float.h>
+
+#include "linear.cuh"
+
+namespace mvsf {
+
+// packed weights (floats), produced by packing.pack_costreg_tr:
+//   pe_w[8][24] | down_w[64][256] (k = ((kd*4+kh)*4+kw)*8+ci) | down_b[64] | down_ln_w[64] | down_ln_b[64]
+//   per layer: qkv_w[192][64] | proj_w[64][64] | proj_b[64] | gamma1[64] | n1_w[64] | n1_b[64]
+//              | f1_w[256][64] | f1_b[256] | f2_w[64][256] | f2_b[64] | gamma2[64] | n2_w[64] | n2_b[64]
+//   up_w[256][64] (n = ((kd*4+kh)*4+kw)*8+co) | up_b[256] | up_ln_w[8] | up_ln_b[8] | prob_w[8] | prob_b[1] (+3 pad)
+constexpr int TR_PE = 0, TR_DOWN_W = 192, TR_DOWN_B = TR_DOWN_W + 64 * 256, TR_DOWN_LNW = TR_DOWN_B + 64,
+              TR_DOWN_LNB = TR_DOWN_LNW + 64, TR_LAYER0 = TR_DOWN_LNB + 64;
+constexpr int L_QKV = 0, L_PROJ_W = 192 * 64, L_PROJ_B = L_PROJ_W + 64 * 64, L_G1 = L_PROJ_B + 64, L_N1W = L_G1 + 64,
+              L_N1B = L_N1W + 64, L_F1W = L_N1B + 64, L_F1B = L_F1W + 256 * 64, L_F2W = L_F1B + 256,
+              L_F2B = L_F2W + 64 * 256, L_G2 = L_F2B + 64, L_N2W = L_G2 + 64, L_N2B = L_N2W + 64, TR_LAYER = L_N2B + 64;
+constexpr int U_W = 0, U_B = 256 * 64, U_LNW = U_B + 256, U_LNB = U_LNW + 8, U_PW = U_LNB + 8, U_PB = U_PW + 8;
+
+// volume[d,y,x,:] += pe_w (8x24) * PE3D(pos[:,d,y,x])
+__global__ void pe3d_add_kernel(float* __restrict__ vol, const float* __restrict__ pos, const float* __restrict__ pe_w,
+                                size_t nvox) {
+  __shared__ float w[8 * 24];
+  for (int i = threadIdx.x; i < 192; i += blockDim.x) w[i] = __ldg(pe_w + i);
+  __syncthreads();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvox) return;
+  // div_term = exp(arange(0,8,2) * (-ln(1e4)/8))  (position_encoding.py:169)
+  const float div[4] = {1.0f, 0.1f, 0.01f, 0.001f};
+  float pe[24];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float p = __ldg(pos + a * nvox + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float arg = __fmul_rn(__fmul_rn(p, 4.0f), div[k]);
+      pe[a * 8 + 2 * k] = sinf(arg);
+      pe[a * 8 + 2 * k + 1] = cosf(arg);
+    }
+  }
+  float4* v = reinterpret_cast<float4*>(vol + i * 8);
+  float4 v0 = v[0], v1 = v[1];
+  float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 24; ++k) s = fmaf(w[c * 24 + k], pe[k], s);
+    o[c] += s;
+  }
+  v[0] = make_float4(o[0], o[1], o[2], o[3]);
+  v[1] = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+// im2col for the (2,4,4)/(2,4,4) patchify conv: patches[t][((kd*4+kh)*4+kw)*8 + ci]
+__global__ void patch_gather_kernel(const float* __restrict__ vol, float* __restrict__ patches, int D, int H, int W) {
+  const int Hp = H / 4, Wp = W / 4;
+  size_t total = (size_t)(D / 2) * Hp * Wp * 32 * 2;  // float4 elements: token x 32 voxels x 2 halves
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int half = (int)(i & 1);
+  int vox = (int)((i >> 1) & 31);
+  size_t t = i >> 6;
+  int wp = (int)(t % Wp), hp = (int)((t / Wp) % Hp), dp = (int)(t / ((size_t)Wp * Hp));
+  int kw = vox & 3, kh = (vox >> 2) & 3, kd = vox >> 4;
+  size_t src = (((size_t)(dp * 2 + kd) * H + hp * 4 + kh) * W + wp * 4 + kw) * 8 + half * 4;
+  reinterpret_cast<float4*>(patches)[i] = ldg4(vol + src);
+}
+
+// fp32 softmax attention, one thread per query, K/V tiles broadcast from shared memory, online softmax in
+// blocks of 8 keys.  qkv [N][3][4][16] (attention.py:77), out [N][4][16].
+constexpr int ATT_KT = 128;
+__global__ void __launch_bounds__(128)
+attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int N, float scale_log2e) {
+  __shared__ __align__(16) float Ks[ATT_KT][16];
+  __shared__ __align__(16) float Vs[ATT_KT][16];
+  const int h = blockIdx.y;
+  const int qi = blockIdx.x * 128 + threadIdx.x;
+  const bool qvalid = qi < N;
+  float q[16];
+  {
+    const float* qp = qkv + (size_t)(qvalid ? qi : 0) * 192 + h * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 t = ldg4(qp + c * 4);
+      q[c * 4 + 0] = t.x * scale_log2e; q[c * 4 + 1] = t.y * scale_log2e;
+      q[c * 4 + 2] = t.z * scale_log2e; q[c * 4 + 3] = t.w * scale_log2e;
+    }
+  }
+  float m = -1e30f, l = 0.f, o[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+
+  for (int k0 = 0; k0 < N; k0 += ATT_KT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < ATT_KT * 4; i += 128) {
+      int kk = i >> 2, c = i & 3;
+      int key = k0 + kk;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (key < N) {
+        kv = ldg4(qkv + (size_t)key * 192 + 64 + h * 16 + c * 4);
+        vv = ldg4(qkv + (size_t)key * 192 + 128 + h * 16 + c * 4);
+      }
+      *reinterpret_cast<float4*>(&Ks[kk][c * 4]) = kv;
+      *reinterpret_cast<float4*>(&Vs[kk][c * 4]) = vv;
+    }
+    __syncthreads();
+    const int kmax = min(ATT_KT, N - k0);
+    for (int j = 0; j < ATT_KT; j += 8) {
+      if (j >= kmax) break;
+      float s[8];
+      float mb = m;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4* kp = reinterpret_cast<const float4*>(&Ks[j + i][0]);
+        float4 k0v = kp[0], k1v = kp[1], k2v = kp[2], k3v = kp[3];
+        float a = q[0] * k0v.x;
+        a = fmaf(q[1], k0v.y, a); a = fmaf(q[2], k0v.z, a); a = fmaf(q[3], k0v.w, a);
+        a = fmaf(q[4], k1v.x, a); a = fmaf(q[5], k1v.y, a); a = fmaf(q[6], k1v.z, a); a = fmaf(q[7], k1v.w, a);
+        a = fmaf(q[8], k2v.x, a); a = fmaf(q[9], k2v.y, a); a = fmaf(q[10], k2v.z, a); a = fmaf(q[11], k2v.w, a);
+        a = fmaf(q[12], k3v.x, a); a = fmaf(q[13], k3v.y, a); a = fmaf(q[14], k3v.z, a); a = fmaf(q[15], k3v.w, a);
+        s[i] = (j + i < kmax) ? a : -1e30f;
+        mb = fmaxf(mb, s[i]);
+      }
+      const float corr = exp2f(m - mb);
+      m = mb;
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) o[d] *= corr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float p = exp2f(s[i] - mb);
+        l += p;
+        const float4* vp = reinterpret_cast<const float4*>(&Vs[j + i][0]);
+        float4 v0 = vp[0], v1 = vp[1], v2 = vp[2], v3 = vp[3];
+        o[0] = fmaf(p, v0.x, o[0]); o[1] = fmaf(p, v0.y, o[1]); o[2] = fmaf(p, v0.z, o[2]); o[3] = fmaf(p, v0.w, o[3]);
+        o[4] = fmaf(p, v1.x, o[4]); o[5] = fmaf(p, v1.y, o[5]); o[6] = fmaf(p, v1.z, o[6]); o[7] = fmaf(p, v1.w, o[7]);
+        o[8] = fmaf(p, v2.x, o[8]); o[9] = fmaf(p, v2.y, o[9]); o[10] = fmaf(p, v2.z, o[10]); o[11] = fmaf(p, v2.w, o[11]);
+        o[12] = fmaf(p, v3.x, o[12]); o[13] = fmaf(p, v3.y, o[13]); o[14] = fmaf(p, v3.z, o[14]); o[15] = fmaf(p, v3.w, o[15]);
+      }
+    }
+  }
+  if (qvalid) {
+    const float inv = __fdiv_rn(1.0f, l);
+    float* op = out + (size_t)qi * 64 + h * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(op + c * 4) =
+          make_float4(o[c * 4 + 0] * inv, o[c * 4 + 1] * inv, o[c * 4 + 2] * inv, o[c * 4 + 3] * inv);
+  }
+}
+
+// un-patchify epilogue: u [N][256] (n = vox*8+co) -> LayerNorm3D over the 8 channels of each voxel (eps 1e-6)
+// -> prob 1x1x1 (8 -> 1) + bias -> logits [D][H][W]
+__global__ void unpatch_ln_prob_kernel(const float* __restrict__ u, const float* __restrict__ tail,
+                                       float* __restrict__ logits, int D, int H, int W) {
+  const int Hp = H / 4, Wp = W / 4;
+  size_t total = (size_t)D * H * W;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // thread order follows u's memory order (token-major, voxel-minor) so the 32-byte reads are coalesced
+  int vox = (int)(i & 31);
+  size_t t = i >> 5;
+  int wp = (int)(t % Wp), hp = (int)((t / Wp) % Hp), dp = (int)(t / ((size_t)Wp * Hp));
+  int kw = vox & 3, kh = (vox >> 2) & 3, kd = vox >> 4;
+  float4 a = ldg4(u + i * 8), b = ldg4(u + i * 8 + 4);
+  float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float mean = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) mean += x[c];
+  mean *= 0.125f;
+  float var = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { float dd = x[c] - mean; var = fmaf(dd, dd, var); }
+  var *= 0.125f;
+  const float sd = sqrtf(var + 1e-6f);
+  float s = __ldg(tail + (U_PB - U_LNW));
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float y = __ldg(tail + c) * __fdiv_rn(x[c] - mean, sd) + __ldg(tail + 8 + c);
+    s = fmaf(y, __ldg(tail + 16 + c), s);
+  }
+  logits[((size_t)(dp * 2 + kd) * H + hp * 4 + kh) * W + wp * 4 + kw] = s;
+}
+
+}  // namespace mvsf
+
+using namespace mvsf;
+
+extern "C" {
+
+int mvsf_costreg_tr_workspace_bytes(int C, int D, int H, int W, size_t* bytes) {
+  MVSF_REQUIRE(bytes && C == 8, "costreg_tr: base channel must be 8");
+  MVSF_REQUIRE(D % 2 == 0 && H % 4 == 0 && W % 4 == 0 && D > 0 && H > 0 && W > 0,
+               "costreg_tr: D %% 2, H %% 4, W %% 4 must be 0 (down_rate (2,4,4))");
+  size_t N = (size_t)(D / 2) * (H / 4) * (W / 4);
+  // patches/u/h [N][256], x [N][64], y [N][64], o [N][64], qkv [N][192]
+  *bytes = N * (256 + 64 + 64 + 64 + 192) * sizeof(float);
+  return MVSF_OK;
+}
+
+int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, float* logits, void* workspace,
+                            size_t workspace_bytes, int C, int D, int H, int W, int layers, float softmax_scale,
+                            mvsf_stream_t stream) {
+  MVSF_REQUIRE(volume && wts && logits && workspace && layers >= 0, "costreg_tr: bad arguments");
+  size_t need = 0;
+  int rc = mvsf_costreg_tr_workspace_bytes(C, D, H, W, &need);
+  if (rc) return rc;
+  if (workspace_bytes < need) return fail(MVSF_ERR_WORKSPACE, "costreg_tr: workspace %zu < %zu bytes", workspace_bytes, need);
+  MVSF_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)wts & 15) == 0 && ((uintptr_t)volume & 15) == 0,
+               "costreg_tr: pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nvox = (size_t)D * H * W;
+  const int N = (int)((size_t)(D / 2) * (H / 4) * (W / 4));
+  float* big = (float*)workspace;          // [N][256]: patches, then FFN hidden, then un-patchify output
+  float* x = big + (size_t)N * 256;        // [N][64]
+  float* y = x + (size_t)N * 64;           // [N][64]
+  float* o = y + (size_t)N * 64;           // [N][64]
+  float* qkv = o + (size_t)N * 64;         // [N][192]
+
+  if (pos) {
+    pe3d_add_kernel<<<cdiv((long long)nvox, 256), 256, 0, s>>>(volume, pos, wts + TR_PE, nvox);
+    MVSF_LAUNCH_CHECK("pe3d_add");
+  }
+  patch_gather_kernel<<<cdiv((long long)N * 64, 256), 256, 0, s>>>(volume, big, D, H, W);
+  MVSF_LAUNCH_CHECK("patch_gather");
+
+  LinArgs a{};
+  a.A = big; a.lda = 256; a.W = wts + TR_DOWN_W; a.bias = wts + TR_DOWN_B; a.C = x; a.ldc = 64;
+  a.M = N; a.N = 64; a.K = 256; a.ln_w = wts + TR_DOWN_LNW; a.ln_b = wts + TR_DOWN_LNB; a.ln_eps = 1e-6f;
+  if ((rc = launch_linear(a, LIN_LN, s))) return rc;
+
+  const float scale_log2e = softmax_scale * 1.4426950408889634f;
+  for (int l = 0; l < layers; ++l) {
+    const float* lw = wts + TR_LAYER0 + (size_t)l * TR_LAYER;
+    LinArgs q{};
+    q.A = x; q.lda = 64; q.W = lw + L_QKV; q.bias = nullptr; q.C = qkv; q.ldc = 192; q.M = N; q.N = 192; q.K = 64;
+    if ((rc = launch_linear(q, LIN_BIAS, s))) return rc;
+    dim3 agrid(cdiv(N, 128), 4);
+    attention_f32_kernel<<<agrid, 128, 0, s>>>(qkv, o, N, scale_log2e);
+    MVSF_LAUNCH_CHECK("attention_f32");
+    LinArgs p{};
+    p.A = o; p.lda = 64; p.W = lw + L_PROJ_W; p.bias = lw + L_PROJ_B; p.C = y; p.ldc = 64; p.M = N; p.N = 64; p.K = 64;
+    p.res = x; p.ldres = 64; p.gamma = lw + L_G1; p.ln_w = lw + L_N1W; p.ln_b = lw + L_N1B; p.ln_eps = 1e-5f;
+    if ((rc = launch_linear(p, LIN_RES_LN, s))) return rc;
+    LinArgs f1{};
+    f1.A = y; f1.lda = 64; f1.W = lw + L_F1W; f1.bias = lw + L_F1B; f1.C = big; f1.ldc = 256; f1.M = N; f1.N = 256; f1.K = 64;
+    if ((rc = launch_linear(f1, LIN_GELU, s))) return rc;
+    LinArgs f2{};
+    f2.A = big; f2.lda = 256; f2.W = lw + L_F2W; f2.bias = lw + L_F2B; f2.C = x; f2.ldc = 64; f2.M = N; f2.N = 64; f2.K = 256;
+    f2.res = y; f2.ldres = 64; f2.gamma = lw + L_G2; f2.ln_w = lw + L_N2W; f2.ln_b = lw + L_N2B; f2.ln_eps = 1e-5f;
+    if ((rc = launch_linear(f2, LIN_RES_LN, s))) return rc;
+  }
+  const float* uw = wts + TR_LAYER0 + (size_t)layers * TR_LAYER;
+  LinArgs u{};
+  u.A = x; u.lda = 64; u.W = uw + U_W; u.bias = uw + U_B; u.C = big; u.ldc = 256; u.M = N; u.N = 256; u.K = 64;
+  if ((rc = launch_linear(u, LIN_BIAS, s))) return rc;
+  unpatch_ln_prob_kernel<<<cdiv((long long)nvox, 256), 256, 0, s>>>(big, uw + U_LNW, logits, D, H, W);
+  MVSF_LAUNCH_CHECK("unpatch_ln_prob");
+  return MVSF_OK;
+}
+}

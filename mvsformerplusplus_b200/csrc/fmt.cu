@@ -1,0 +1,398 @@
+// F1-F4: FMT_with_pathway.forward (models/FMT.py:164-206): cross-view feature transformer on the 1/8-resolution
+// features (FMT.forward :81-137, CrossBlock block.py:336-346 pre-norm with pre_norm_query=False, linear attention
+// attention.py:261-291, LayerScale, Mlp) followed by the top-down pathway
+//   stage_{k+1} = smooth_k( bilinear_up(dim_reduction_k(stage_k)) + lateral_{k+1} )      (FMT.py:154-162,195-197).
+// Tokens "(h w) c" of the reference are exactly channels-last pixels, so the stage-1 output is produced directly in
+// the [V][H][W][64] layout the warp kernels consume.  All source views are processed as one batch; the K/V
+// summaries of the two cross layers depend only on the reference view and are computed once.
+#include "linear.cuh"
+
+namespace mvsf {
+
+// packed weights per CrossBlock (floats): n1_w[64] n1_b[64] qkv_w[192][64] proj_w[64][64] proj_b[64] g1[64]
+//                                          n2_w[64] n2_b[64] f1_w[256][64] f1_b[256] f2_w[64][256] f2_b[64] g2[64]
+constexpr int B_N1W = 0, B_N1B = 64, B_QKV = 128, B_PW = B_QKV + 192 * 64, B_PB = B_PW + 64 * 64, B_G1 = B_PB + 64,
+              B_N2W = B_G1 + 64, B_N2B = B_N2W + 64, B_F1W = B_N2B + 64, B_F1B = B_F1W + 256 * 64,
+              B_F2W = B_F1B + 256, B_F2B = B_F2W + 64 * 256, B_G2 = B_F2B + 64, B_SIZE = B_G2 + 64;
+// after 4 blocks: dr1[32][64] dr2[16][32] dr3[8][16] sm1[9][32][32] sm2[9][16][16] sm3[9][8][8]   ([tap][ci][co])
+constexpr int P_DR1 = 4 * B_SIZE, P_DR2 = P_DR1 + 32 * 64, P_DR3 = P_DR2 + 16 * 32, P_SM1 = P_DR3 + 8 * 16,
+              P_SM2 = P_SM1 + 9 * 32 * 32, P_SM3 = P_SM2 + 9 * 16 * 16, FMT_WTS = P_SM3 + 9 * 8 * 8;
+constexpr int KVSZ = 4 * 16 * 16 + 64;  // KV[h][m][d] + ksum[h][d]
+
+// f [V][64][L] (NCHW) + pe [L][64] -> tok [V][L][64]
+__global__ void tokens_add_pe_kernel(const float* __restrict__ f, const float* __restrict__ pe, float* __restrict__ tok,
+                                     int L) {
+  __shared__ float tile[32][33];
+  const int v = blockIdx.z;
+  const float* s = f + (size_t)v * 64 * L;
+  float* d = tok + (size_t)v * 64 * L;
+  int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, p = p0 + threadIdx.x;
+    if (p < L) tile[i][threadIdx.x] = s[(size_t)c * L + p];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < L) d[(size_t)p * 64 + c] = tile[threadIdx.x][i] + __ldg(pe + (size_t)p * 64 + c);
+  }
+}
+
+// partial[view][blk][KVSZ]: KV[h][m][d] = sum_s k[s,h,d] v[s,h,m] ; ksum[h][d] = sum_s k[s,h,d]  over a 256-token chunk
+constexpr int KV_CHUNK = 256, KV_TILE = 64;
+__global__ void __launch_bounds__(256)
+kv_partial_kernel(const float* __restrict__ kv, int ld, int koff, int voff, int L, float* __restrict__ partial) {
+  __shared__ __align__(16) float ks[KV_TILE][64];
+  __shared__ __align__(16) float vs[KV_TILE][64];
+  const int view = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+  const float* base = kv + (size_t)view * L * ld;
+  const int h = tid >> 6, m = (tid >> 2) & 15, d0 = (tid & 3) * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, ksum[4] = {0.f, 0.f, 0.f, 0.f};
+  const int s_begin = blk * KV_CHUNK, s_end = min(L, s_begin + KV_CHUNK);
+  for (int s0 = s_begin; s0 < s_end; s0 += KV_TILE) {
+    __syncthreads();
+    for (int i = tid; i < KV_TILE * 16; i += 256) {
+      int r = i >> 4, c = (i & 15) * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (s0 + r < s_end) {
+        a = ldg4(base + (size_t)(s0 + r) * ld + koff + c);
+        b = ldg4(base + (size_t)(s0 + r) * ld + voff + c);
+      }
+      *reinterpret_cast<float4*>(&ks[r][c]) = a;
+      *reinterpret_cast<float4*>(&vs[r][c]) = b;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < KV_TILE; ++r) {
+      float4 k4 = *reinterpret_cast<const float4*>(&ks[r][h * 16 + d0]);
+      float vv = vs[r][h * 16 + m];
+      acc[0] = fmaf(k4.x, vv, acc[0]); acc[1] = fmaf(k4.y, vv, acc[1]);
+      acc[2] = fmaf(k4.z, vv, acc[2]); acc[3] = fmaf(k4.w, vv, acc[3]);
+      ksum[0] += k4.x; ksum[1] += k4.y; ksum[2] += k4.z; ksum[3] += k4.w;
+    }
+  }
+  float* o = partial + ((size_t)view * gridDim.x + blk) * KVSZ;
+  *reinterpret_cast<float4*>(o + (h * 16 + m) * 16 + d0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  if (m == 0) *reinterpret_cast<float4*>(o + 1024 + h * 16 + d0) = make_float4(ksum[0], ksum[1], ksum[2], ksum[3]);
+}
+__global__ void kv_final_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ fin) {
+  const int view = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KVSZ) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[((size_t)view * nblk + b) * KVSZ + i];
+  fin[(size_t)view * KVSZ + i] = s;
+}
+
+// out[s][h*16+m] = (sum_d q[s,h,d] KV[h][m][d]) / (q[s,h,:] . ksum[h,:] + 1e-6)     (attention.py:281-284)
+__global__ void __launch_bounds__(128)
+linattn_apply_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kvfin, size_t kv_view_stride,
+                     float* __restrict__ out, int L, int M) {
+  __shared__ __align__(16) float kvs[256 + 16];
+  const int h = blockIdx.y;
+  const int s = blockIdx.x * 128 + threadIdx.x;
+  const int view = (blockIdx.x * 128) / L;  // host guarantees L % 128 == 0 or a single view per launch
+  const float* kvp = kvfin + (size_t)view * kv_view_stride;
+  for (int i = threadIdx.x; i < 256; i += 128) kvs[i] = __ldg(kvp + h * 256 + i);
+  if (threadIdx.x < 16) kvs[256 + threadIdx.x] = __ldg(kvp + 1024 + h * 16 + threadIdx.x);
+  __syncthreads();
+  if (s >= M) return;
+  float qv[16];
+  const float* qp = q + (size_t)s * ldq + h * 16;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float4 t = ldg4(qp + c * 4);
+    qv[c * 4] = t.x; qv[c * 4 + 1] = t.y; qv[c * 4 + 2] = t.z; qv[c * 4 + 3] = t.w;
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) den = fmaf(qv[d], kvs[256 + d], den);
+  const float z = __fdiv_rn(1.0f, den + 1e-6f);
+  float* op = out + (size_t)s * 64 + h * 16;
+#pragma unroll
+  for (int mq = 0; mq < 4; ++mq) {
+    float r[4];
+#pragma unroll
+    for (int mm = 0; mm < 4; ++mm) {
+      const float4* kp = reinterpret_cast<const float4*>(&kvs[(mq * 4 + mm) * 16]);
+      float4 a = kp[0], b = kp[1], c = kp[2], e = kp[3];
+      float t = qv[0] * a.x;
+      t = fmaf(qv[1], a.y, t); t = fmaf(qv[2], a.z, t); t = fmaf(qv[3], a.w, t);
+      t = fmaf(qv[4], b.x, t); t = fmaf(qv[5], b.y, t); t = fmaf(qv[6], b.z, t); t = fmaf(qv[7], b.w, t);
+      t = fmaf(qv[8], c.x, t); t = fmaf(qv[9], c.y, t); t = fmaf(qv[10], c.z, t); t = fmaf(qv[11], c.w, t);
+      t = fmaf(qv[12], e.x, t); t = fmaf(qv[13], e.y, t); t = fmaf(qv[14], e.z, t); t = fmaf(qv[15], e.w, t);
+      r[mm] = t * z;
+    }
+    *reinterpret_cast<float4*>(op + mq * 4) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// pre[v][y][x][c] = lateral_nchw[v][c][y][x] + bilinear_up2(red)[v][y][x][c]   (F.interpolate bilinear, align_corners=False)
+template <int C>
+__global__ void __launch_bounds__(256)
+upsample_add_kernel(const float* __restrict__ red, const float* __restrict__ lat, float* __restrict__ pre, int h, int w) {
+  __shared__ float tile[C][33];
+  const int H = 2 * h, W = 2 * w;
+  const int v = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 32;
+  const float* lv = lat + (size_t)v * C * H * W;
+  for (int i = threadIdx.x; i < C * 32; i += 256) {
+    int c = i >> 5, xx = i & 31;
+    if (x0 + xx < W) tile[c][xx] = __ldg(lv + ((size_t)c * H + y) * W + x0 + xx);
+  }
+  __syncthreads();
+  // ATen area_pixel_compute_source_index(scale=0.5, align_corners=False): src = 0.5*(dst+0.5)-0.5, clamped at 0
+  float sy = fmaxf(0.5f * ((float)y + 0.5f) - 0.5f, 0.0f);
+  int y0 = (int)sy;
+  int y1 = y0 + ((y0 < h - 1) ? 1 : 0);
+  float ly1 = sy - (float)y0, ly0 = 1.0f - ly1;
+  const float* rv = red + (size_t)v * h * w * C;
+  for (int i = threadIdx.x; i < 32 * C; i += 256) {
+    int xx = i / C, c = i - xx * C;
+    int x = x0 + xx;
+    if (x >= W) continue;
+    float sx = fmaxf(0.5f * ((float)x + 0.5f) - 0.5f, 0.0f);
+    int xa = (int)sx;
+    int xb = xa + ((xa < w - 1) ? 1 : 0);
+    float lx1 = sx - (float)xa, lx0 = 1.0f - lx1;
+    float v00 = __ldg(rv + ((size_t)y0 * w + xa) * C + c), v01 = __ldg(rv + ((size_t)y0 * w + xb) * C + c);
+    float v10 = __ldg(rv + ((size_t)y1 * w + xa) * C + c), v11 = __ldg(rv + ((size_t)y1 * w + xb) * C + c);
+    float up = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+    pre[(((size_t)v * H + y) * W + x) * C + c] = up + tile[c][xx];
+  }
+}
+
+// smooth_k: Conv2d(C, C, 3, padding=1, bias=False), channels-last.  Same register tiling as the 3-D conv kernel.
+template <int C>
+struct Conv2Cfg {
+  static constexpr int CT = C < 16 ? C : 16;
+  static constexpr int NCG = C / CT;
+  static constexpr int WARPS_H = 4 / NCG;
+  static constexpr int TH = 4 * WARPS_H;
+  static constexpr int IH_T = TH + 2, IW_T = 34;
+};
+template <int C>
+__global__ void __launch_bounds__(128)
+conv2d_k3_kernel(const float* __restrict__ in, const float* __restrict__ wts, float* __restrict__ out, int H, int W) {
+  using Cfg = Conv2Cfg<C>;
+  constexpr int CT = Cfg::CT, NCG = Cfg::NCG, TH = Cfg::TH, IH_T = Cfg::IH_T, IW_T = Cfg::IW_T;
+  __shared__ __align__(16) float4 in_s[IH_T * IW_T];
+  __shared__ __align__(16) float wt_s[9 * 4 * C];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int cg = wid % NCG, hg = wid / NCG;
+  const int v = blockIdx.z, oh0 = blockIdx.y * TH, ow0 = blockIdx.x * 32;
+  const float* iv = in + (size_t)v * H * W * C;
+  float acc[4][CT];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[j][c] = 0.f;
+  for (int pc = 0; pc < C / 4; ++pc) {
+    __syncthreads();
+    for (int i = tid; i < IH_T * IW_T; i += 128) {
+      int iy = i / IW_T, ix = i - iy * IW_T;
+      int ih = oh0 - 1 + iy, iw = ow0 - 1 + ix;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) t = ldg4(iv + ((size_t)ih * W + iw) * C + pc * 4);
+      in_s[i] = t;
+    }
+    for (int i = tid; i < 9 * 4 * C / 4; i += 128) {
+      int e = i * 4;
+      int tap = e / (4 * C), rem = e - tap * (4 * C);
+      int ci = rem / C, co = rem - ci * C;
+      *reinterpret_cast<float4*>(wt_s + e) = ldg4(wts + ((size_t)tap * C + pc * 4 + ci) * C + co);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        float4 a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = in_s[(hg * 4 + j + kh) * IW_T + lane + kw];
+        const float* wp = wt_s + (size_t)((kh * 3 + kw) * 4) * C + cg * CT;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+#pragma unroll
+          for (int q = 0; q < CT / 4; ++q) {
+            float4 w4 = *reinterpret_cast<const float4*>(wp + ci * C + q * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x = (ci == 0) ? a[j].x : (ci == 1) ? a[j].y : (ci == 2) ? a[j].z : a[j].w;
+              acc[j][q * 4 + 0] = fmaf(x, w4.x, acc[j][q * 4 + 0]);
+              acc[j][q * 4 + 1] = fmaf(x, w4.y, acc[j][q * 4 + 1]);
+              acc[j][q * 4 + 2] = fmaf(x, w4.z, acc[j][q * 4 + 2]);
+              acc[j][q * 4 + 3] = fmaf(x, w4.w, acc[j][q * 4 + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  const int ow = ow0 + lane;
+  if (ow >= W) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int oh = oh0 + hg * 4 + j;
+    if (oh >= H) continue;
+    float* o = out + (((size_t)v * H + oh) * W + ow) * C + cg * CT;
+#pragma unroll
+    for (int q = 0; q < CT / 4; ++q)
+      *reinterpret_cast<float4*>(o + q * 4) = make_float4(acc[j][q * 4], acc[j][q * 4 + 1], acc[j][q * 4 + 2], acc[j][q * 4 + 3]);
+  }
+}
+
+struct FmtWs {
+  float *xn, *qkv, *att, *hid, *ref0, *kvpart, *kvfin, *kvc;
+};
+
+// one CrossBlock over `M` tokens (nviews views of L tokens each) stored at x (in place).
+// self attention: kv_src == nullptr ; cross attention: kvc = precomputed K/V summary of the reference view.
+static int run_block(float* x, int nviews, int L, const float* bw, const float* kvc, const FmtWs& ws, cudaStream_t s) {
+  const int M = nviews * L;
+  int rc;
+  layernorm64_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, bw + B_N1W, bw + B_N1B, ws.xn, M, 1e-5f);
+  MVSF_LAUNCH_CHECK("fmt_ln1");
+  const float* kvsum;
+  size_t kv_stride;
+  int ldq;
+  if (!kvc) {
+    LinArgs a{};
+    a.A = ws.xn; a.lda = 64; a.W = bw + B_QKV; a.C = ws.qkv; a.ldc = 192; a.M = M; a.N = 192; a.K = 64; a.elu_cols = 128;
+    if ((rc = launch_linear(a, LIN_ELU1, s))) return rc;
+    const int nblk = cdiv(L, KV_CHUNK);
+    kv_partial_kernel<<<dim3(nblk, nviews), 256, 0, s>>>(ws.qkv, 192, 64, 128, L, ws.kvpart);
+    MVSF_LAUNCH_CHECK("fmt_kv_partial");
+    kv_final_kernel<<<dim3(cdiv(KVSZ, 256), nviews), 256, 0, s>>>(ws.kvpart, nblk, ws.kvfin);
+    MVSF_LAUNCH_CHECK("fmt_kv_final");
+    kvsum = ws.kvfin; kv_stride = KVSZ; ldq = 192;
+  } else {
+    LinArgs a{};
+    a.A = ws.xn; a.lda = 64; a.W = bw + B_QKV; a.C = ws.qkv; a.ldc = 64; a.M = M; a.N = 64; a.K = 64; a.elu_cols = 64;
+    if ((rc = launch_linear(a, LIN_ELU1, s))) return rc;
+    kvsum = kvc; kv_stride = 0; ldq = 64;
+  }
+  if (L % 128 == 0 || nviews == 1) {
+    linattn_apply_kernel<<<dim3(cdiv(M, 128), 4), 128, 0, s>>>(ws.qkv, ldq, kvsum, kv_stride, ws.att, L, M);
+    MVSF_LAUNCH_CHECK("fmt_linattn_apply");
+  } else {
+    for (int v = 0; v < nviews; ++v) {  // views do not align with 128-token blocks: one launch per view
+      linattn_apply_kernel<<<dim3(cdiv(L, 128), 4), 128, 0, s>>>(ws.qkv + (size_t)v * L * ldq, ldq,
+                                                                 kvsum + (size_t)v * kv_stride, 0,
+                                                                 ws.att + (size_t)v * L * 64, L, L);
+      MVSF_LAUNCH_CHECK("fmt_linattn_apply");
+    }
+  }
+  LinArgs p{};
+  p.A = ws.att; p.lda = 64; p.W = bw + B_PW; p.bias = bw + B_PB; p.C = x; p.ldc = 64; p.M = M; p.N = 64; p.K = 64;
+  p.res = x; p.ldres = 64; p.gamma = bw + B_G1;
+  if ((rc = launch_linear(p, LIN_RES, s))) return rc;
+  layernorm64_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, bw + B_N2W, bw + B_N2B, ws.xn, M, 1e-5f);
+  MVSF_LAUNCH_CHECK("fmt_ln2");
+  LinArgs f1{};
+  f1.A = ws.xn; f1.lda = 64; f1.W = bw + B_F1W; f1.bias = bw + B_F1B; f1.C = ws.hid; f1.ldc = 256; f1.M = M; f1.N = 256; f1.K = 64;
+  if ((rc = launch_linear(f1, LIN_GELU, s))) return rc;
+  LinArgs f2{};
+  f2.A = ws.hid; f2.lda = 256; f2.W = bw + B_F2W; f2.bias = bw + B_F2B; f2.C = x; f2.ldc = 64; f2.M = M; f2.N = 64; f2.K = 256;
+  f2.res = x; f2.ldres = 64; f2.gamma = bw + B_G2;
+  if ((rc = launch_linear(f2, LIN_RES, s))) return rc;
+  return MVSF_OK;
+}
+
+// K/V summary of a cross layer: key = value = norm1_layer(ref_feature)   (block.py:341-343, FMT.py:121-125)
+static int run_cross_kv(const float* ref_tok, int L, const float* bw, float* kvc_out, const FmtWs& ws, cudaStream_t s) {
+  int rc;
+  layernorm64_kernel<<<cdiv(L, 8), 256, 0, s>>>(ref_tok, bw + B_N1W, bw + B_N1B, ws.xn, L, 1e-5f);
+  MVSF_LAUNCH_CHECK("fmt_ln_key");
+  LinArgs a{};
+  a.A = ws.xn; a.lda = 64; a.W = bw + B_QKV + 64 * 64; a.C = ws.qkv; a.ldc = 128; a.M = L; a.N = 128; a.K = 64; a.elu_cols = 64;
+  if ((rc = launch_linear(a, LIN_ELU1, s))) return rc;
+  const int nblk = cdiv(L, KV_CHUNK);
+  kv_partial_kernel<<<dim3(nblk, 1), 256, 0, s>>>(ws.qkv, 128, 0, 64, L, ws.kvpart);
+  MVSF_LAUNCH_CHECK("fmt_kv_partial");
+  kv_final_kernel<<<dim3(cdiv(KVSZ, 256), 1), 256, 0, s>>>(ws.kvpart, nblk, kvc_out);
+  MVSF_LAUNCH_CHECK("fmt_kv_final");
+  return MVSF_OK;
+}
+
+template <int CIN, int COUT>
+static int run_pathway_level(const float* prev, const float* lat, const float* dr_w, const float* sm_w, float* red,
+                             float* pre, float* out, int V, int h, int w, cudaStream_t s) {
+  int rc;
+  LinArgs a{};
+  a.A = prev; a.lda = CIN; a.W = dr_w; a.C = red; a.ldc = COUT; a.M = V * h * w; a.N = COUT; a.K = CIN;
+  if ((rc = launch_linear(a, LIN_BIAS, s))) return rc;
+  const int H = 2 * h, W = 2 * w;
+  MVSF_REQUIRE(H <= 65535 && V <= 65535, "fmt pathway: image too large");
+  upsample_add_kernel<COUT><<<dim3(cdiv(W, 32), H, V), 256, 0, s>>>(red, lat, pre, h, w);
+  MVSF_LAUNCH_CHECK("fmt_upsample_add");
+  conv2d_k3_kernel<COUT><<<dim3(cdiv(W, 32), cdiv(H, Conv2Cfg<COUT>::TH), V), 128, 0, s>>>(pre, sm_w, out, H, W);
+  MVSF_LAUNCH_CHECK("fmt_smooth");
+  return MVSF_OK;
+}
+
+}  // namespace mvsf
+
+using namespace mvsf;
+
+extern "C" {
+
+int mvsf_fmt_workspace_bytes(int V, int H1, int W1, size_t* bytes) {
+  MVSF_REQUIRE(bytes && V >= 2 && H1 > 0 && W1 > 0, "fmt: bad arguments");
+  size_t L = (size_t)H1 * W1, VL = (size_t)V * L;
+  size_t nblk = (L + KV_CHUNK - 1) / KV_CHUNK;
+  size_t n = 640 * VL + 64 * L + (size_t)V * nblk * KVSZ + (size_t)(V + 2) * KVSZ + 64;
+  *bytes = n * sizeof(float);
+  return MVSF_OK;
+}
+
+int mvsf_fmt_forward(const float* f1, const float* f2, const float* f3, const float* f4, const float* pe,
+                     const float* wts, float* o1, float* o2, float* o3, float* o4, void* workspace,
+                     size_t workspace_bytes, int V, int H1, int W1, mvsf_stream_t stream) {
+  MVSF_REQUIRE(f1 && f2 && f3 && f4 && pe && wts && o1 && o2 && o3 && o4 && workspace, "fmt: null pointer");
+  size_t need = 0;
+  int rc = mvsf_fmt_workspace_bytes(V, H1, W1, &need);
+  if (rc) return rc;
+  if (workspace_bytes < need) return fail(MVSF_ERR_WORKSPACE, "fmt: workspace %zu < %zu bytes", workspace_bytes, need);
+  MVSF_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)wts & 15) == 0, "fmt: pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int L = H1 * W1;
+  const size_t VL = (size_t)V * L;
+  float* base = (float*)workspace;
+  FmtWs ws;
+  ws.xn = base;                       // [V*L][64]
+  ws.qkv = ws.xn + 64 * VL;           // [V*L][192]
+  ws.att = ws.qkv + 192 * VL;         // [V*L][64]
+  ws.hid = ws.att + 64 * VL;          // [V*L][256]   (xn..hid = 576 VL; the pathway reuses 640 VL from base)
+  ws.ref0 = base + 640 * VL;          // [L][64]
+  const size_t nblk = (L + KV_CHUNK - 1) / KV_CHUNK;
+  ws.kvpart = ws.ref0 + 64 * (size_t)L;
+  ws.kvfin = ws.kvpart + (size_t)V * nblk * KVSZ;
+  ws.kvc = ws.kvfin + (size_t)V * KVSZ;   // [2][KVSZ]
+
+  MVSF_REQUIRE(V <= 65535, "fmt: too many views");
+  tokens_add_pe_kernel<<<dim3(cdiv(L, 32), 2, V), dim3(32, 8), 0, s>>>(f1, pe, o1, L);
+  MVSF_LAUNCH_CHECK("fmt_tokens_add_pe");
+
+  const float* b0 = wts; const float* b1 = wts + B_SIZE; const float* b2 = wts + 2 * B_SIZE; const float* b3 = wts + 3 * B_SIZE;
+  // reference view: the two self layers (FMT.py:96-107); keep the output of the first one for cross layer 1
+  if ((rc = run_block(o1, 1, L, b0, nullptr, ws, s))) return rc;
+  MVSF_CUDA_OK(cudaMemcpyAsync(ws.ref0, o1, (size_t)L * 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if ((rc = run_block(o1, 1, L, b2, nullptr, ws, s))) return rc;
+  if ((rc = run_cross_kv(ws.ref0, L, b1, ws.kvc, ws, s))) return rc;
+  if ((rc = run_cross_kv(o1, L, b3, ws.kvc + KVSZ, ws, s))) return rc;
+  // source views as one batch: self, cross(ref_list[0]), self, cross(ref_list[1])   (FMT.py:119-135)
+  float* xs = o1 + (size_t)L * 64;
+  if ((rc = run_block(xs, V - 1, L, b0, nullptr, ws, s))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b1, ws.kvc, ws, s))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b2, nullptr, ws, s))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b3, ws.kvc + KVSZ, ws, s))) return rc;
+
+  // top-down pathway (FMT.py:195-197), all views batched
+  float* red = base;                  // <= 128 VL floats
+  float* pre = base + 128 * VL;       // <= 512 VL floats
+  if ((rc = run_pathway_level<64, 32>(o1, f2, wts + P_DR1, wts + P_SM1, red, pre, o2, V, H1, W1, s))) return rc;
+  if ((rc = run_pathway_level<32, 16>(o2, f3, wts + P_DR2, wts + P_SM2, red, pre, o3, V, 2 * H1, 2 * W1, s))) return rc;
+  if ((rc = run_pathway_level<16, 8>(o3, f4, wts + P_DR3, wts + P_SM3, red, pre, o4, V, 4 * H1, 4 * W1, s))) return rc;
+  return MVSF_OK;
+}
+}

@@ -32,6 +32,12 @@ import math
 import torch
 import torch.nn.functional as F
 
+# When True the two heavy gathers/contractions call the same ATen kernels the reference calls on CPU
+# (F.grid_sample at warping.py:105, F.scaled_dot_product_attention at attention.py:96) instead of the explicit
+# restatements below.  Used by bench.py's CPU-baseline arm so the timing reflects the reference's own CPU path;
+# parity tests use the explicit restatements (and check both agree).
+USE_ATEN_KERNELS = False
+
 
 # --------------------------------------------------------------------------------------------------
 # W1/W2: projection prep + homography warp
@@ -94,9 +100,14 @@ def homo_warp(src_fea, src_proj, ref_proj, depth_values):
     if depth_values.dim() == 2:
         depth_values = depth_values.view(B, D, 1, 1).expand(B, D, H, W)
     px, py, z = warp_coordinates(src_proj, ref_proj, depth_values, H, W)
-    warped = bilinear_gather_zeros(src_fea, px.reshape(B, -1), py.reshape(B, -1)).view(B, C, D, H, W)
     gx = px / ((W - 1) / 2) - 1
     gy = py / ((H - 1) / 2) - 1
+    if USE_ATEN_KERNELS:
+        grid = torch.stack((gx, gy), dim=3)
+        warped = F.grid_sample(src_fea, grid.view(B, D * H, W, 2), mode="bilinear", padding_mode="zeros",
+                               align_corners=True).view(B, C, D, H, W)
+    else:
+        warped = bilinear_gather_zeros(src_fea, px.reshape(B, -1), py.reshape(B, -1)).view(B, C, D, H, W)
     mask = ((gx > 1) | (gx < -1) | (gy > 1) | (gy < -1) | (z <= 0)).view(B, D, H, W)
     return warped, mask
 
@@ -218,6 +229,9 @@ def softmax_attention(x, qkv_w, proj_w, proj_b, num_heads, train_avg_length):
     scale = hd ** -0.5
     if train_avg_length is not None:
         scale *= math.log(N, train_avg_length)
+    if USE_ATEN_KERNELS:
+        x = F.scaled_dot_product_attention(q, k, v, scale=scale).transpose(1, 2).reshape(B, N, C)
+        return F.linear(x, proj_w, proj_b)
     out = torch.empty_like(q)
     blk = 4096  # blocked to bound memory; same arithmetic as softmax(q k^T * scale) v
     for h in range(num_heads):

@@ -1,0 +1,428 @@
+"""GPU parity tests: every libmvsf_b200 entry point (called through the ctypes C ABI / the host seam mirrors) against
+the CPU oracle on the same seeded inputs, and against the reference-executed golden fixtures.
+Tolerances: north-star 1e-3 relative L-inf on depth, 1e-4 absolute on per-pixel probability; intermediates tighter.
+A JSON report with every measured error is written to gpurun_out/parity_report.json."""
+import ctypes
+import json
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.common import TMP, build_case, load_golden, max_abs, rel_linf
+
+pytestmark = pytest.mark.gpu
+
+REPORT = {}
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rec(name, **kw):
+    REPORT[name] = {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in kw.items()}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def hp():
+    from mvsformerplusplus_b200 import hotpath
+    return hotpath
+
+
+@pytest.fixture(scope="module")
+def L():
+    from mvsformerplusplus_b200 import _lib
+    return _lib.lib()
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def S():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ck(rc, what):
+    from mvsformerplusplus_b200 import _lib
+    _lib.check(rc, what)
+
+
+# ----------------------------------------------------------------------------------------------- boundary helpers
+def test_layout_roundtrip(dev, hp):
+    x = torch.randn(3, 24, 13, 37, device=dev)
+    n = hp.to_nhwc(x)
+    assert torch.equal(n, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(hp.to_nchw(n), x)
+    assert hp.to_nhwc(n.permute(0, 3, 1, 2)).data_ptr() == n.data_ptr()  # channels-last view: zero copy
+
+
+def test_compose_geometry(dev, L):
+    from mvsformerplusplus_b200 import synth
+    from oracle import hotpath as O
+    pm = synth.make_proj_matrices(5, 1152, 1536)["stage3"][0]
+    homs = torch.empty(4 * 12, device=dev)
+    kinv = torch.empty(9, device=dev)
+    ck(L.mvsf_compose_geometry(P(pm.to(dev)), 5, P(homs), P(kinv), S()), "compose_geometry")
+    pm64 = pm.double()
+    ref = O.compose_projection(pm64[None, 0])[0]
+    want = []
+    for v in range(1, 5):
+        M = O.compose_projection(pm64[None, v])[0] @ torch.inverse(ref)
+        want.append(torch.cat([M[:3, :3].reshape(-1), M[:3, 3]]))
+    want = torch.stack(want).reshape(-1)
+    err = float(((homs.cpu().double() - want).abs() / want.abs().clamp_min(1e-3)).max())
+    kerr = max_abs(kinv.cpu(), torch.inverse(pm64[0, 1, :3, :3]).reshape(-1))
+    rec("compose_geometry", rel=err, kinv_abs=kerr)
+    assert err < 1e-6 and kerr < 1e-7
+
+
+def test_homo_warp_seam_vs_reference(dev, L):
+    g, _ = load_golden("warp_seam")
+    from oracle import hotpath as O
+    src = g["src"][0]
+    C, H, W = src.shape
+    D = g["depth_values"].shape[1]
+    M = (g["src_proj"].double() @ torch.inverse(g["ref_proj"].double()))[0]
+    hom = torch.cat([M[:3, :3].reshape(-1), M[:3, 3]]).float().to(dev)
+    src_nhwc = src.permute(1, 2, 0).contiguous().to(dev)
+    warped = torch.empty(C, D, H, W, device=dev)
+    mask = torch.empty(D, H, W, dtype=torch.uint8, device=dev)
+    ck(L.mvsf_homo_warp(P(src_nhwc), P(hom), P(g["depth_values"][0].contiguous().to(dev)), P(warped), P(mask), C, D, H, W, S()),
+       "homo_warp")
+    e = max_abs(warped.cpu(), g["warped"][0])
+    mm = float((mask.cpu().bool() != g["mask"][0]).float().mean())
+    rec("homo_warp_seam", abs=e, mask_mismatch=mm)
+    assert e < 2e-4 and mm < 0.01
+
+
+# ----------------------------------------------------------------------------------------------- scheduling
+def test_init_and_schedule_inverse_range(dev, L):
+    from oracle import hotpath as O
+    dv = (425.0 + 2.65 * torch.arange(192)).float()
+    D, H, W = 32, 12, 20
+    out = torch.empty(D, H, W, device=dev)
+    ck(L.mvsf_init_inverse_range(P(dv.to(dev)), 192, P(out), D, H, W, S()), "init_inverse_range")
+    want = O.init_inverse_range(dv[None], D, H, W)[0]
+    e0 = rel_linf(out.cpu(), want)
+    g = torch.Generator().manual_seed(1)
+    depth = 500.0 + 300.0 * torch.rand(1, H, W, generator=g)
+    hyp = want[None] * (1.0 + 0.01 * torch.rand(1, D, H, W, generator=g))
+    D2, H2, W2 = 16, 2 * H, 2 * W
+    out2 = torch.empty(D2, H2, W2, device=dev)
+    ck(L.mvsf_schedule_inverse_range(P(depth[0].contiguous().to(dev)), P(hyp[0].contiguous().to(dev)), D, 2.67,
+                                     P(out2), D2, H2, W2, S()), "schedule_inverse_range")
+    want2 = O.schedule_inverse_range(depth, hyp, D2, 2.67, H2, W2)[0]
+    e1 = rel_linf(out2.cpu(), want2)
+    rec("inverse_range", init_rel=e0, schedule_rel=e1)
+    assert e0 < 1e-6 and e1 < 2e-6
+
+
+def test_position3d(dev, L):
+    from mvsformerplusplus_b200 import synth
+    from oracle import hotpath as O
+    H, W, D = 12, 16, 8
+    pm = synth.make_proj_matrices(3, H * 8, W * 8)["stage1"]
+    dv = synth.make_depth_values(192)
+    ds = O.init_inverse_range(dv, D, H, W)
+    want, hmin, hmax, wmin, wmax = O.get_position_3d(1, H, W, pm[:, 0, 1, :3, :3], ds, dv.min(), dv.max(), None, None, None, None)
+    homs = torch.empty(2 * 12, device=dev)
+    kinv = torch.empty(9, device=dev)
+    ck(L.mvsf_compose_geometry(P(pm[0].to(dev)), 3, P(homs), P(kinv), S()), "compose_geometry")
+    stats = torch.zeros(8, device=dev)
+    pos = torch.empty(3, D, H, W, device=dev)
+    ck(L.mvsf_position3d(P(kinv), P(ds[0].contiguous().to(dev)), P(dv[0].to(dev)), 192, P(stats), 1, P(pos), D, H, W, S()),
+       "position3d")
+    e = max_abs(pos.cpu(), want[0])
+    se = max_abs(stats[:4].cpu(), torch.stack([wmin, wmax, hmin, hmax]))
+    rec("position3d", abs=e, stats_abs=se)
+    assert e < 2e-6
+
+
+# ----------------------------------------------------------------------------------------------- cost volume
+def _rand_vis_sd(seed):
+    from mvsformerplusplus_b200 import synth
+    from mvsformerplusplus_b200.config import default_args
+    from mvsformerplusplus_b200.params import build_hotpath_params
+    torch.manual_seed(0)
+    params = build_hotpath_params(default_args()).eval()
+    return synth.randomize_state_dict(params, seed=seed)
+
+
+COST_CASES = [  # C, D, H, W, V, theta_step
+    (8, 4, 37, 53, 3, 0.1), (16, 8, 24, 40, 3, 0.1), (32, 16, 16, 24, 4, 0.12), (64, 32, 12, 16, 5, 0.1),
+    (8, 4, 31, 45, 3, 0.6),   # wide baseline: many taps leave the image (zero padding per corner)
+    (8, 48, 10, 14, 3, 0.1),  # generic-D path (D-sweep configuration)
+    (64, 8, 9, 11, 2, 0.1),
+]
+
+
+@pytest.mark.parametrize("C,D,H,W,V,th", COST_CASES)
+def test_cost_volume_kernels(dev, L, C, D, H, W, V, th):
+    from mvsformerplusplus_b200 import packing, synth
+    from oracle import hotpath as O
+    sd = _rand_vis_sd(5)
+    g = torch.Generator().manual_seed(C * 1000 + D)
+    feats = torch.randn(1, V, C, H, W, generator=g)
+    sc = {8: 1, 16: 2, 32: 4, 64: 8}[C]
+    pm = synth.make_proj_matrices(V, H * sc, W * sc, theta_step=th)[f"stage{ {1: 4, 2: 3, 4: 2, 8: 1}[sc] }"]
+    dv = synth.make_depth_values(192)
+    dvals = O.init_inverse_range(dv, D, H, W) * (1.0 + 0.02 * torch.rand(1, D, H, W, generator=g))
+    want = O.cost_volume(feats, pm, dvals, sd, "fusions.3.", 8)
+    homs = torch.empty((V - 1) * 12, device=dev)
+    kinv = torch.empty(9, device=dev)
+    ck(L.mvsf_compose_geometry(P(pm[0].to(dev)), V, P(homs), P(kinv), S()), "compose_geometry")
+    f = feats[0].permute(0, 2, 3, 1).contiguous().to(dev)
+    dd = dvals[0].contiguous().to(dev)
+    ent = torch.empty(V - 1, H, W, device=dev)
+    ck(L.mvsf_warp_corr_entropy(P(f), P(homs), P(dd), P(ent), V, C, 8, D, H, W, S()), "warp_corr_entropy")
+    wts = packing.pack_vis(sd, "fusions.3.vis.").to(dev)
+    vis = torch.empty(V - 1, H, W, device=dev)
+    ck(L.mvsf_vis_cnn(P(ent), P(wts), P(vis), V - 1, H, W, S()), "vis_cnn")
+    vol = torch.empty(D, H, W, 8, device=dev)
+    ck(L.mvsf_warp_corr_aggregate(P(f), P(homs), P(dd), P(vis), P(vol), V, C, 8, D, H, W, S()), "warp_corr_aggregate")
+    e_ent = max_abs(ent.cpu(), want["entropy"][0])
+    e_vis = max_abs(vis.cpu(), want["vis_weight"][0])
+    e_vol = max_abs(vol.cpu().permute(3, 0, 1, 2), want["volume_mean"][0])
+    # vis CNN in isolation on the oracle's entropy (removes the entropy noise from the comparison)
+    vis2 = torch.empty(V - 1, H, W, device=dev)
+    ck(L.mvsf_vis_cnn(P(want["entropy"][0].contiguous().to(dev)), P(wts), P(vis2), V - 1, H, W, S()), "vis_cnn")
+    e_vis2 = max_abs(vis2.cpu(), want["vis_weight"][0])
+    rec(f"cost_volume_C{C}_D{D}_{H}x{W}_V{V}_th{th}", entropy=e_ent, vis=e_vis, vis_isolated=e_vis2, volume=e_vol,
+        vol_scale=float(want["volume_mean"].abs().max()))
+    assert e_ent < 5e-4 and e_vis < 5e-4 and e_vis2 < 2e-5 and e_vol < 1e-3
+
+
+def test_vis_cnn_tile_borders(dev, L):
+    from mvsformerplusplus_b200 import packing
+    from oracle import hotpath as O
+    sd = _rand_vis_sd(9)
+    g = torch.Generator().manual_seed(3)
+    for (N, H, W) in [(1, 30, 30), (2, 61, 95), (3, 7, 5), (1, 1, 1), (2, 64, 128)]:
+        ent = 3.0 * torch.rand(1, N, H, W, generator=g)
+        want = torch.cat([O.vis_cnn(ent[:, i:i + 1], sd, "fusions.1.") for i in range(N)], 1)[0]
+        vis = torch.empty(N, H, W, device=dev)
+        ck(L.mvsf_vis_cnn(P(ent[0].contiguous().to(dev)), P(packing.pack_vis(sd, "fusions.1.vis.").to(dev)), P(vis), N, H, W, S()),
+           "vis_cnn")
+        e = max_abs(vis.cpu(), want)
+        rec(f"vis_cnn_{N}x{H}x{W}", abs=e)
+        assert e < 2e-5
+
+
+# ----------------------------------------------------------------------------------------------- regularisers
+@pytest.mark.parametrize("stage,D,H,W", [(1, 16, 16, 24), (1, 8, 8, 40), (2, 8, 16, 24), (3, 4, 24, 40), (3, 3, 8, 8)])
+def test_costreg_unet(dev, L, stage, D, H, W):
+    from mvsformerplusplus_b200 import packing
+    from oracle import hotpath as O
+    sd = _rand_vis_sd(13)
+    g = torch.Generator().manual_seed(stage * 7 + D)
+    vol = torch.randn(1, 8, D, H, W, generator=g) * 0.5
+    p = f"fusions.{stage}.cost_reg."
+    want = O.costreg_unet(vol, sd, p)[0, 0]
+    kind, flat = packing.pack_costreg_unet(sd, p)
+    need = ctypes.c_size_t(0)
+    ck(L.mvsf_costreg_unet_workspace_bytes(kind, 8, D, H, W, ctypes.byref(need)), "ws")
+    ws = torch.empty(need.value // 4 + 4, device=dev)
+    logits = torch.empty(D, H, W, device=dev)
+    v = vol[0].permute(1, 2, 3, 0).contiguous().to(dev)
+    ck(L.mvsf_costreg_unet_forward(kind, P(v), P(flat.to(dev)), P(logits), P(ws), ctypes.c_size_t(ws.numel() * 4), 8, D, H, W, S()),
+       "costreg_unet_forward")
+    e = max_abs(logits.cpu(), want)
+    rec(f"costreg_unet_stage{stage}_{D}x{H}x{W}", abs=e, scale=float(want.abs().max()))
+    assert e < 2e-4 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("D,H,W", [(8, 12, 16), (32, 16, 16), (4, 8, 8)])
+def test_costreg_transformer(dev, L, D, H, W):
+    from mvsformerplusplus_b200 import packing
+    from mvsformerplusplus_b200.config import default_args
+    from oracle import hotpath as O
+    sd = _rand_vis_sd(17)
+    cfg = default_args()["transformer_config"][0]
+    g = torch.Generator().manual_seed(D)
+    vol = torch.randn(1, 8, D, H, W, generator=g) * 0.5
+    pos = torch.rand(1, 3, D, H, W, generator=g)
+    p = "fusions.0.cost_reg."
+    want = O.costreg_transformer(vol, pos, sd, p, cfg)[0, 0]
+    flat = packing.pack_costreg_tr(sd, p, cfg["layer_num"]).to(dev)
+    need = ctypes.c_size_t(0)
+    ck(L.mvsf_costreg_tr_workspace_bytes(8, D, H, W, ctypes.byref(need)), "ws")
+    ws = torch.empty(need.value // 4 + 4, device=dev)
+    logits = torch.empty(D, H, W, device=dev)
+    v = vol[0].permute(1, 2, 3, 0).contiguous().to(dev)
+    n_tok = (D // 2) * (H // 4) * (W // 4)
+    scale = 16 ** -0.5 * math.log(n_tok, cfg["train_avg_length"])
+    ck(L.mvsf_costreg_tr_forward(P(v), P(pos[0].contiguous().to(dev)), P(flat), P(logits), P(ws), ctypes.c_size_t(ws.numel() * 4),
+                                 8, D, H, W, cfg["layer_num"], float(scale), S()), "costreg_tr_forward")
+    e = max_abs(logits.cpu(), want)
+    rec(f"costreg_tr_{D}x{H}x{W}", abs=e, scale=float(want.abs().max()), tokens=n_tok)
+    assert e < 2e-4 * max(1.0, float(want.abs().max()))
+
+
+def test_softargmax(dev, L):
+    g = torch.Generator().manual_seed(2)
+    for D in (4, 8, 16, 32, 5):
+        H, W = 9, 21
+        z = 3.0 * torch.randn(D, H, W, generator=g)
+        hyp = 425.0 + 500.0 * torch.rand(D, H, W, generator=g)
+        prob = torch.empty(D, H, W, device=dev)
+        depth = torch.empty(H, W, device=dev)
+        conf = torch.empty(H, W, device=dev)
+        ck(L.mvsf_softargmax(P(z.to(dev)), P(hyp.to(dev)), 5.0, P(prob), P(depth), P(conf), D, H, W, S()), "softargmax")
+        wp = F.softmax(z, 0)
+        wd = (F.softmax(z * 5.0, 0) * hyp).sum(0)
+        e = (max_abs(prob.cpu(), wp), rel_linf(depth.cpu(), wd), max_abs(conf.cpu(), wp.max(0)[0]))
+        rec(f"softargmax_D{D}", prob=e[0], depth_rel=e[1], conf=e[2])
+        assert e[0] < 1e-6 and e[1] < 1e-6 and e[2] < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------- FMT
+@pytest.mark.parametrize("V,H1,W1", [(3, 8, 12), (2, 16, 16), (4, 6, 10)])
+def test_fmt_with_pathway(dev, hp, V, H1, W1):
+    from mvsformerplusplus_b200 import synth
+    from mvsformerplusplus_b200.config import default_args
+    from oracle import hotpath as O
+    args = default_args()
+    torch.manual_seed(0)
+    net = hp.HotPathNet(args).eval()
+    sd = synth.randomize_state_dict(net, seed=23)
+    net = net.to(dev)
+    feats = synth.make_features(V, H1 * 8, W1 * 8, seed=V)
+    out = net.FMT_module.forward({k: v.to(dev) for k, v in feats.items()})
+    with torch.no_grad():
+        want = O.fmt_with_pathway(feats, sd, args["FMT_config"])
+    errs = {k: max_abs(out[k].cpu(), want[k]) for k in want}
+    rec(f"fmt_V{V}_{H1}x{W1}", **errs)
+    assert max(errs.values()) < 2e-4
+
+
+# ----------------------------------------------------------------------------------------------- stage seam + cascade
+@pytest.fixture(scope="module", params=["hotpath_v3_96x128", "hotpath_v4_64x96"])
+def cascade(request, dev, hp):
+    from oracle import hotpath as O
+    gold, meta = load_golden(request.param)
+    args, params, sd, feats, proj, dv = build_case(meta)
+    net = hp.HotPathNet(args).eval()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev)
+    out = net.forward_features({k: v.to(dev) for k, v in feats.items()}, {k: v.to(dev) for k, v in proj.items()},
+                               dv.to(dev), TMP, keep_intermediates=True)
+    with torch.no_grad():
+        ora = O.hotpath_forward(feats, proj, dv, sd, args, tmp=TMP, keep_intermediates=True)
+    return request.param, gold, out, ora, net, args, sd, proj, dv
+
+
+@pytest.mark.parametrize("s", [1, 2, 3, 4])
+def test_stage_seam_teacher_forced(cascade, dev, s):
+    """StageNet.forward on the ORACLE's stage inputs (features, hypotheses, 3-D positions): per-stage parity at the
+    north-star tolerances without cascade error accumulation."""
+    from oracle import hotpath as O
+    name, gold, out, ora, net, args, sd, proj, dv = cascade
+    f = ora["features"][f"stage{s}"]
+    ds = ora[f"stage{s}"]["depth_values"]
+    p3d = None
+    if s == 1:
+        B, _, _, H, W = f.shape
+        p3d, *_ = O.get_position_3d(B, H, W, proj["stage1"][:, 0, 1, :3, :3], ds, dv.min(), dv.max(), None, None, None, None)
+    so = net.fusions[s - 1].forward(f.to(dev), proj[f"stage{s}"].to(dev), ds.to(dev), TMP[s - 1],
+                                    position3d=None if p3d is None else p3d.to(dev), keep_intermediates=True)
+    want = ora[f"stage{s}"]
+    e = dict(entropy=max_abs(so["entropy"].cpu(), want["entropy"]), vis=max_abs(so["vis_weight"].cpu(), want["vis_weight"]),
+             volume=max_abs(so["volume_mean"].cpu().permute(0, 4, 1, 2, 3), want["volume_mean"]),
+             logits=max_abs(so["prob_volume_pre"].cpu(), want["prob_volume_pre"]),
+             prob=max_abs(so["prob_volume"].cpu(), want["prob_volume"]),
+             conf=max_abs(so["photometric_confidence"].cpu(), want["photometric_confidence"]),
+             depth_rel=rel_linf(so["depth"].cpu(), want["depth"]))
+    rec(f"stage_seam_{name}_s{s}", **e)
+    assert e["prob"] < 1e-4 and e["conf"] < 1e-4 and e["depth_rel"] < 1e-3
+
+
+@pytest.mark.parametrize("s", [1, 2, 3, 4])
+def test_cascade_vs_reference_golden(cascade, s):
+    """Full FMT + cascade on the GPU against the reference-executed fixture (fp32 reference forward)."""
+    name, gold, out, ora, *_ = cascade
+    so = out[f"stage{s}"]
+    gp = torch.softmax(gold[f"stage{s}.prob_volume_pre"], dim=0)
+    e = dict(depth_values_rel=rel_linf(so["depth_values"][0].cpu(), gold[f"stage{s}.depth_values"]),
+             entropy=max_abs(so["entropy"][0].cpu(), gold[f"stage{s}.entropy"]),
+             vis=max_abs(so["vis_weight"][0].cpu(), gold[f"stage{s}.vis_weight"]),
+             prob=max_abs(so["prob_volume"][0].cpu(), gp),
+             conf=max_abs(so["photometric_confidence"][0].cpu(), gold[f"stage{s}.photometric_confidence"]),
+             depth_rel=rel_linf(so["depth"][0].cpu(), gold[f"stage{s}.depth"]))
+    rec(f"cascade_{name}_s{s}", **e)
+    assert e["prob"] < 1e-4 and e["conf"] < 1e-4 and e["depth_rel"] < 1e-3
+
+
+def test_cascade_final_outputs(cascade):
+    name, gold, out, ora, *_ = cascade
+    e = dict(refined_depth_rel=rel_linf(out["refined_depth"][0].cpu(), gold["refined_depth"]),
+             confidence=max_abs(out["photometric_confidence"][0].cpu(), gold["photometric_confidence"]),
+             fmt_stage1=max_abs(out["features"]["stage1"][0].cpu(), gold["fmt.stage1"]),
+             fmt_stage4_view1=max_abs(out["features"]["stage4"][0, 1].cpu(), gold["fmt.stage4.view1"]))
+    rec(f"cascade_{name}_final", **e)
+    assert e["refined_depth_rel"] < 1e-3 and e["confidence"] < 1e-4 and e["fmt_stage1"] < 2e-4
+
+
+# ----------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties(dev, hp):
+    """BASELINE config 2 sizes (V=5, 1152x1536, ndepths 32/16/8/4): properties that do not need the CPU oracle."""
+    from mvsformerplusplus_b200 import synth
+    from mvsformerplusplus_b200.config import default_args
+    args = default_args()
+    V, H, W = 5, 1152, 1536
+    torch.manual_seed(0)
+    net = hp.HotPathNet(args).eval()
+    synth.randomize_state_dict(net, seed=7)
+    net = net.to(dev)
+    feats = {k: v.to(dev) for k, v in synth.make_features(V, H, W, seed=1234, smooth=False).items()}
+    proj = {k: v.to(dev) for k, v in synth.make_proj_matrices(V, H, W).items()}
+    dv = synth.make_depth_values(192).to(dev)
+    out = net.forward_features(feats, proj, dv, TMP)
+    out2 = net.forward_features(feats, proj, dv, TMP)
+    torch.cuda.synchronize()
+    facts = {}
+    for s in range(1, 5):
+        so = out[f"stage{s}"]
+        pv = so["prob_volume"]
+        facts[f"s{s}_finite"] = bool(torch.isfinite(pv).all() and torch.isfinite(so["depth"]).all())
+        facts[f"s{s}_prob_sum_err"] = float((pv.sum(1) - 1).abs().max())
+        facts[f"s{s}_conf_is_max"] = float((so["photometric_confidence"] - pv.max(1)[0]).abs().max())
+        lo, hi = so["depth_values"].min(1)[0], so["depth_values"].max(1)[0]
+        facts[f"s{s}_depth_in_range"] = bool(((so["depth"] >= lo * (1 - 1e-5)) & (so["depth"] <= hi * (1 + 1e-5))).all())
+        facts[f"s{s}_deterministic"] = bool(torch.equal(so["depth"], out2[f"stage{s}"]["depth"]))
+    facts["refined_shape"] = list(out["refined_depth"].shape)
+    rec("full_size_properties", **{k: (v if not isinstance(v, bool) else int(v)) for k, v in facts.items()})
+    for s in range(1, 5):
+        assert facts[f"s{s}_finite"] and facts[f"s{s}_depth_in_range"] and facts[f"s{s}_deterministic"]
+        assert facts[f"s{s}_prob_sum_err"] < 1e-5 and facts[f"s{s}_conf_is_max"] == 0.0
+    assert facts["refined_shape"] == [1, H, W]
+
+
+def test_identity_homography_property(dev, L):
+    """src camera == ref camera: the warp must return the source itself, so pass B equals the closed form
+    vol[g] = mean_{c in g} ref*src (all views weighted alike) at full DTU stage-4 size."""
+    from mvsformerplusplus_b200 import synth
+    H, W, C, D, V = 1152, 1536, 8, 4, 2
+    pm = synth.make_proj_matrices(1, H, W)["stage4"][0]
+    pm = torch.cat([pm, pm], 0).to(dev)
+    homs = torch.empty(12, device=dev)
+    kinv = torch.empty(9, device=dev)
+    ck(L.mvsf_compose_geometry(P(pm), 2, P(homs), P(kinv), S()), "compose_geometry")
+    g = torch.Generator(device="cpu").manual_seed(0)
+    f = torch.randn(V, H, W, C, generator=g).to(dev)
+    dd = (425.0 + 100.0 * torch.arange(D, dtype=torch.float32)).view(D, 1, 1).expand(D, H, W).contiguous().to(dev)
+    vis = torch.full((1, H, W), 0.7, device=dev)
+    vol = torch.empty(D, H, W, C, device=dev)
+    ck(L.mvsf_warp_corr_aggregate(P(f), P(homs), P(dd), P(vis), P(vol), V, C, 8, D, H, W, S()), "warp_corr_aggregate")
+    want = (f[0] * f[1]) * (0.7 / (0.7 + 1e-6))
+    e = float((vol - want[None]).abs().max())
+    rec("identity_homography", abs=e)
+    assert e < 5e-3  # coordinates round-trip through fp32 normalisation (<=1e-4 px) on white-noise features

@@ -58,3 +58,19 @@ def test_final_outputs_match_reference(run):
     gold, out = run
     assert rel_linf(out["refined_depth"][0], gold["refined_depth"]) < 1e-3
     assert max_abs(out["photometric_confidence"][0], gold["photometric_confidence"]) < 1e-4
+
+
+def test_aten_kernel_variant_agrees_with_explicit_restatement():
+    """bench.py's CPU arm switches the oracle to the reference's own ATen kernels (grid_sample, SDPA); both forms
+    must agree."""
+    gold, meta = load_golden("hotpath_v4_64x96")
+    args, params, sd, feats, proj, dv = build_case(meta)
+    with torch.no_grad():
+        a = O.hotpath_forward(feats, proj, dv, sd, args, tmp=TMP)
+        O.USE_ATEN_KERNELS = True
+        try:
+            b = O.hotpath_forward(feats, proj, dv, sd, args, tmp=TMP)
+        finally:
+            O.USE_ATEN_KERNELS = False
+    assert rel_linf(a["refined_depth"], b["refined_depth"]) < 1e-4
+    assert max_abs(a["stage4"]["prob_volume"], b["stage4"]["prob_volume"]) < 1e-4
