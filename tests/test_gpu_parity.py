@@ -71,7 +71,8 @@ def test_compose_geometry(dev, L):
     pm = synth.make_proj_matrices(5, 1152, 1536)["stage3"][0]
     homs = torch.empty(4 * 12, device=dev)
     kinv = torch.empty(9, device=dev)
-    ck(L.mvsf_compose_geometry(P(pm.to(dev)), 5, P(homs), P(kinv), S()), "compose_geometry")
+    pmd = pm.to(dev)
+    ck(L.mvsf_compose_geometry(P(pmd), 5, P(homs), P(kinv), S()), "compose_geometry")
     pm64 = pm.double()
     ref = O.compose_projection(pm64[None, 0])[0]
     want = []
@@ -96,8 +97,8 @@ def test_homo_warp_seam_vs_reference(dev, L):
     src_nhwc = src.permute(1, 2, 0).contiguous().to(dev)
     warped = torch.empty(C, D, H, W, device=dev)
     mask = torch.empty(D, H, W, dtype=torch.uint8, device=dev)
-    ck(L.mvsf_homo_warp(P(src_nhwc), P(hom), P(g["depth_values"][0].contiguous().to(dev)), P(warped), P(mask), C, D, H, W, S()),
-       "homo_warp")
+    dvd = g["depth_values"][0].contiguous().to(dev)
+    ck(L.mvsf_homo_warp(P(src_nhwc), P(hom), P(dvd), P(warped), P(mask), C, D, H, W, S()), "homo_warp")
     e = max_abs(warped.cpu(), g["warped"][0])
     mm = float((mask.cpu().bool() != g["mask"][0]).float().mean())
     rec("homo_warp_seam", abs=e, mask_mismatch=mm)
@@ -110,7 +111,8 @@ def test_init_and_schedule_inverse_range(dev, L):
     dv = (425.0 + 2.65 * torch.arange(192)).float()
     D, H, W = 32, 12, 20
     out = torch.empty(D, H, W, device=dev)
-    ck(L.mvsf_init_inverse_range(P(dv.to(dev)), 192, P(out), D, H, W, S()), "init_inverse_range")
+    dvd = dv.to(dev)  # keep device inputs alive until the (asynchronous) kernels have consumed them
+    ck(L.mvsf_init_inverse_range(P(dvd), 192, P(out), D, H, W, S()), "init_inverse_range")
     want = O.init_inverse_range(dv[None], D, H, W)[0]
     e0 = rel_linf(out.cpu(), want)
     g = torch.Generator().manual_seed(1)
@@ -118,8 +120,8 @@ def test_init_and_schedule_inverse_range(dev, L):
     hyp = want[None] * (1.0 + 0.01 * torch.rand(1, D, H, W, generator=g))
     D2, H2, W2 = 16, 2 * H, 2 * W
     out2 = torch.empty(D2, H2, W2, device=dev)
-    ck(L.mvsf_schedule_inverse_range(P(depth[0].contiguous().to(dev)), P(hyp[0].contiguous().to(dev)), D, 2.67,
-                                     P(out2), D2, H2, W2, S()), "schedule_inverse_range")
+    depth_d, hyp_d = depth[0].contiguous().to(dev), hyp[0].contiguous().to(dev)
+    ck(L.mvsf_schedule_inverse_range(P(depth_d), P(hyp_d), D, 2.67, P(out2), D2, H2, W2, S()), "schedule_inverse_range")
     want2 = O.schedule_inverse_range(depth, hyp, D2, 2.67, H2, W2)[0]
     e1 = rel_linf(out2.cpu(), want2)
     rec("inverse_range", init_rel=e0, schedule_rel=e1)
@@ -136,11 +138,11 @@ def test_position3d(dev, L):
     want, hmin, hmax, wmin, wmax = O.get_position_3d(1, H, W, pm[:, 0, 1, :3, :3], ds, dv.min(), dv.max(), None, None, None, None)
     homs = torch.empty(2 * 12, device=dev)
     kinv = torch.empty(9, device=dev)
-    ck(L.mvsf_compose_geometry(P(pm[0].to(dev)), 3, P(homs), P(kinv), S()), "compose_geometry")
+    pmd, dsd, dvd = pm[0].to(dev), ds[0].contiguous().to(dev), dv[0].to(dev)
+    ck(L.mvsf_compose_geometry(P(pmd), 3, P(homs), P(kinv), S()), "compose_geometry")
     stats = torch.zeros(8, device=dev)
     pos = torch.empty(3, D, H, W, device=dev)
-    ck(L.mvsf_position3d(P(kinv), P(ds[0].contiguous().to(dev)), P(dv[0].to(dev)), 192, P(stats), 1, P(pos), D, H, W, S()),
-       "position3d")
+    ck(L.mvsf_position3d(P(kinv), P(dsd), P(dvd), 192, P(stats), 1, P(pos), D, H, W, S()), "position3d")
     e = max_abs(pos.cpu(), want[0])
     se = max_abs(stats[:4].cpu(), torch.stack([wmin, wmax, hmin, hmax]))
     rec("position3d", abs=e, stats_abs=se)
@@ -179,7 +181,8 @@ def test_cost_volume_kernels(dev, L, C, D, H, W, V, th):
     want = O.cost_volume(feats, pm, dvals, sd, "fusions.3.", 8)
     homs = torch.empty((V - 1) * 12, device=dev)
     kinv = torch.empty(9, device=dev)
-    ck(L.mvsf_compose_geometry(P(pm[0].to(dev)), V, P(homs), P(kinv), S()), "compose_geometry")
+    pmd = pm[0].to(dev)
+    ck(L.mvsf_compose_geometry(P(pmd), V, P(homs), P(kinv), S()), "compose_geometry")
     f = feats[0].permute(0, 2, 3, 1).contiguous().to(dev)
     dd = dvals[0].contiguous().to(dev)
     ent = torch.empty(V - 1, H, W, device=dev)
@@ -194,7 +197,8 @@ def test_cost_volume_kernels(dev, L, C, D, H, W, V, th):
     e_vol = max_abs(vol.cpu().permute(3, 0, 1, 2), want["volume_mean"][0])
     # vis CNN in isolation on the oracle's entropy (removes the entropy noise from the comparison)
     vis2 = torch.empty(V - 1, H, W, device=dev)
-    ck(L.mvsf_vis_cnn(P(want["entropy"][0].contiguous().to(dev)), P(wts), P(vis2), V - 1, H, W, S()), "vis_cnn")
+    ent_o = want["entropy"][0].contiguous().to(dev)
+    ck(L.mvsf_vis_cnn(P(ent_o), P(wts), P(vis2), V - 1, H, W, S()), "vis_cnn")
     e_vis2 = max_abs(vis2.cpu(), want["vis_weight"][0])
     rec(f"cost_volume_C{C}_D{D}_{H}x{W}_V{V}_th{th}", entropy=e_ent, vis=e_vis, vis_isolated=e_vis2, volume=e_vol,
         vol_scale=float(want["volume_mean"].abs().max()))
@@ -210,8 +214,8 @@ def test_vis_cnn_tile_borders(dev, L):
         ent = 3.0 * torch.rand(1, N, H, W, generator=g)
         want = torch.cat([O.vis_cnn(ent[:, i:i + 1], sd, "fusions.1.") for i in range(N)], 1)[0]
         vis = torch.empty(N, H, W, device=dev)
-        ck(L.mvsf_vis_cnn(P(ent[0].contiguous().to(dev)), P(packing.pack_vis(sd, "fusions.1.vis.").to(dev)), P(vis), N, H, W, S()),
-           "vis_cnn")
+        ent_d, wts = ent[0].contiguous().to(dev), packing.pack_vis(sd, "fusions.1.vis.").to(dev)
+        ck(L.mvsf_vis_cnn(P(ent_d), P(wts), P(vis), N, H, W, S()), "vis_cnn")
         e = max_abs(vis.cpu(), want)
         rec(f"vis_cnn_{N}x{H}x{W}", abs=e)
         assert e < 2e-5
@@ -233,7 +237,8 @@ def test_costreg_unet(dev, L, stage, D, H, W):
     ws = torch.empty(need.value // 4 + 4, device=dev)
     logits = torch.empty(D, H, W, device=dev)
     v = vol[0].permute(1, 2, 3, 0).contiguous().to(dev)
-    ck(L.mvsf_costreg_unet_forward(kind, P(v), P(flat.to(dev)), P(logits), P(ws), ctypes.c_size_t(ws.numel() * 4), 8, D, H, W, S()),
+    flat_d = flat.to(dev)
+    ck(L.mvsf_costreg_unet_forward(kind, P(v), P(flat_d), P(logits), P(ws), ctypes.c_size_t(ws.numel() * 4), 8, D, H, W, S()),
        "costreg_unet_forward")
     e = max_abs(logits.cpu(), want)
     rec(f"costreg_unet_stage{stage}_{D}x{H}x{W}", abs=e, scale=float(want.abs().max()))
@@ -260,7 +265,8 @@ def test_costreg_transformer(dev, L, D, H, W):
     v = vol[0].permute(1, 2, 3, 0).contiguous().to(dev)
     n_tok = (D // 2) * (H // 4) * (W // 4)
     scale = 16 ** -0.5 * math.log(n_tok, cfg["train_avg_length"])
-    ck(L.mvsf_costreg_tr_forward(P(v), P(pos[0].contiguous().to(dev)), P(flat), P(logits), P(ws), ctypes.c_size_t(ws.numel() * 4),
+    pos_d = pos[0].contiguous().to(dev)
+    ck(L.mvsf_costreg_tr_forward(P(v), P(pos_d), P(flat), P(logits), P(ws), ctypes.c_size_t(ws.numel() * 4),
                                  8, D, H, W, cfg["layer_num"], float(scale), S()), "costreg_tr_forward")
     e = max_abs(logits.cpu(), want)
     rec(f"costreg_tr_{D}x{H}x{W}", abs=e, scale=float(want.abs().max()), tokens=n_tok)
@@ -276,7 +282,8 @@ def test_softargmax(dev, L):
         prob = torch.empty(D, H, W, device=dev)
         depth = torch.empty(H, W, device=dev)
         conf = torch.empty(H, W, device=dev)
-        ck(L.mvsf_softargmax(P(z.to(dev)), P(hyp.to(dev)), 5.0, P(prob), P(depth), P(conf), D, H, W, S()), "softargmax")
+        zd, hd = z.to(dev), hyp.to(dev)
+        ck(L.mvsf_softargmax(P(zd), P(hd), 5.0, P(prob), P(depth), P(conf), D, H, W, S()), "softargmax")
         wp = F.softmax(z, 0)
         wd = (F.softmax(z * 5.0, 0) * hyp).sum(0)
         e = (max_abs(prob.cpu(), wp), rel_linf(depth.cpu(), wd), max_abs(conf.cpu(), wp.max(0)[0]))

@@ -1,0 +1,37 @@
+"""Runs a few hot-path forwards at a named workload for ncu / timing breakdowns.
+  python tools/profile_forward.py [--workload dtu] [--iters 2] [--breakdown]"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from mvsformerplusplus_b200 import _lib  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="dtu")
+ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--breakdown", action="store_true")
+a = ap.parse_args()
+wl = bench.WORKLOADS[a.workload]
+dev = torch.device("cuda:0")
+net, _ = bench.make_net()
+net = net.to(dev)
+feats, proj, dv = bench.make_inputs(wl, 1234)
+f = {k: v.to(dev) for k, v in feats.items()}
+p = {k: v.to(dev) for k, v in proj.items()}
+d = dv.to(dev)
+for _ in range(a.iters):
+    net.forward_features(f, p, d, bench.TMP)
+torch.cuda.synchronize()
+if a.breakdown:
+    with _lib.profile_calls() as prof:
+        for _ in range(3):
+            net.forward_features(f, p, d, bench.TMP)
+    summ = prof.summary()
+    tot = sum(v["ms"] for v in summ.values()) / 3
+    print(json.dumps({k: {"ms_per_map": round(v["ms"] / 3, 4), "calls_per_map": v["calls"] // 3} for k, v in sorted(summ.items())}, indent=1))
+    print("total ms per depth map (sum of bracketed calls):", round(tot, 3))
