@@ -271,7 +271,7 @@ class FMT_with_pathway(_PackedMixin, nn.Module):
             for k in range(4):
                 outs[f"stage{k + 1}"].append(o[k])
         # logical [B,V,C,H,W]; channels-last in memory (StageNet consumes it without a copy)
-        return {k: torch.stack(v, 0).permute(0, 1, 4, 2, 3) for k, v in outs.items()}
+        return {k: (v[0].unsqueeze(0) if B == 1 else torch.stack(v, 0)).permute(0, 1, 4, 2, 3) for k, v in outs.items()}
 
 
 # =====================================================================================================
