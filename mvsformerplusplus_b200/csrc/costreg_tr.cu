@@ -7,6 +7,7 @@
 //   --> un-patchify GEMM (64 -> 2*4*4*8) --> per-voxel LN3D(8) + 1x1x1 prob --> logits [D][H][W]
 // Softmax attention is order-free over tokens, so tokens are kept in (d', h', w') raster order instead of the
 // reference's "(h w d)" (module.py:573) - the result is identical.
+#include <cuda_bf16.h>
 #include <float.h>
 
 #include "linear.cuh"
@@ -158,6 +159,235 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core softmax attention (product path).  head_dim 16 makes QK^T a single k16 MMA step and PV an n16 tile, so
+// the kernel is bound by the SIMT softmax work, not by the tensor pipe; it is written FlashAttention-2 style on
+// mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with every operand split into hi + lo bf16 parts and three MMAs per
+// product (hi*hi + hi*lo + lo*hi, error ~2^-17 relative) so the result stays within the fp32 parity budget
+// (a single bf16/tf32 pass moves probabilities by ~1e-3).
+//   split kernel : qkv [N][3][4][16] fp32 -> Qh,Ql,Kh,Kl,Vh,Vl [4][N][16] bf16   (q pre-scaled by scale*log2(e))
+//   main kernel  : CTA = 8 warps x 16 queries, 64-key tiles of K/V streamed with cp.async (3 stages), swizzled rows
+//                  so ldmatrix is bank-conflict free; S/P live in registers (C-fragment == A-fragment layout).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__global__ void qkv_split_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ split, int N, float qscale) {
+  // split layout: [6][4 heads][N][16]  (0 Qh, 1 Ql, 2 Kh, 3 Kl, 4 Vh, 5 Vl)
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (token, which(q/k/v), head, quad of 4 dims)
+  int total = N * 3 * 4 * 4;
+  if (i >= total) return;
+  int quad = i & 3, h = (i >> 2) & 3, which = (i >> 4) % 3, tok = i / 48;
+  float4 v = ldg4(qkv + (size_t)tok * 192 + which * 64 + h * 16 + quad * 4);
+  if (which == 0) { v.x *= qscale; v.y *= qscale; v.z *= qscale; v.w *= qscale; }
+  __nv_bfloat16 hi[4], lo[4];
+  split_bf16(v.x, hi[0], lo[0]); split_bf16(v.y, hi[1], lo[1]); split_bf16(v.z, hi[2], lo[2]); split_bf16(v.w, hi[3], lo[3]);
+  size_t plane = (size_t)4 * N * 16;
+  size_t off = ((size_t)h * N + tok) * 16 + quad * 4;
+  __nv_bfloat16* ph = split + (size_t)(which * 2) * plane + off;
+  __nv_bfloat16* pl = split + (size_t)(which * 2 + 1) * plane + off;
+  *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(hi);
+  *reinterpret_cast<uint2*>(pl) = *reinterpret_cast<uint2*>(lo);
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr, bool valid) {
+  int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_)); }
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr int FA_BM = 128, FA_BN = 64, FA_STAGES = 3;
+// one stage = 4 arrays (Kh, Kl, Vh, Vl) x 64 keys x 32 bytes
+constexpr int FA_ARR_BYTES = FA_BN * 32, FA_STAGE_BYTES = 4 * FA_ARR_BYTES;
+
+// byte offset of (key row r, 16-byte chunk c) inside one 64x32B array, XOR-swizzled so that the 8 rows an ldmatrix
+// 8x8 tile touches fall into 8 distinct 16-byte bank groups
+__device__ __forceinline__ int fa_off(int r, int c) { return r * 32 + ((c ^ ((r >> 2) & 1)) << 4); }
+
+__global__ void __launch_bounds__(256)
+attention_mma_kernel(const __nv_bfloat16* __restrict__ split, float* __restrict__ out, int N) {
+  __shared__ __align__(128) unsigned char smem[FA_STAGES * FA_STAGE_BYTES];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.y;
+  const int q0 = blockIdx.x * FA_BM + warp * 16;
+  const size_t plane = (size_t)4 * N * 16;
+  const __nv_bfloat16* Qh = split + 0 * plane + (size_t)h * N * 16;
+  const __nv_bfloat16* Ql = split + 1 * plane + (size_t)h * N * 16;
+  const __nv_bfloat16* KV[4] = {split + 2 * plane + (size_t)h * N * 16, split + 3 * plane + (size_t)h * N * 16,
+                                split + 4 * plane + (size_t)h * N * 16, split + 5 * plane + (size_t)h * N * 16};
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+
+  // Q fragments (A operand, 16 queries x 16 dims), hi and lo
+  uint32_t qh[4], ql[4];
+  {
+    int r0 = min(q0 + g, N - 1), r1 = min(q0 + g + 8, N - 1);
+    qh[0] = *reinterpret_cast<const uint32_t*>(Qh + (size_t)r0 * 16 + 2 * t);
+    qh[1] = *reinterpret_cast<const uint32_t*>(Qh + (size_t)r1 * 16 + 2 * t);
+    qh[2] = *reinterpret_cast<const uint32_t*>(Qh + (size_t)r0 * 16 + 2 * t + 8);
+    qh[3] = *reinterpret_cast<const uint32_t*>(Qh + (size_t)r1 * 16 + 2 * t + 8);
+    ql[0] = *reinterpret_cast<const uint32_t*>(Ql + (size_t)r0 * 16 + 2 * t);
+    ql[1] = *reinterpret_cast<const uint32_t*>(Ql + (size_t)r1 * 16 + 2 * t);
+    ql[2] = *reinterpret_cast<const uint32_t*>(Ql + (size_t)r0 * 16 + 2 * t + 8);
+    ql[3] = *reinterpret_cast<const uint32_t*>(Ql + (size_t)r1 * 16 + 2 * t + 8);
+  }
+
+  const int ntiles = (N + FA_BN - 1) / FA_BN;
+  auto issue_tile = [&](int tile, int stage) {
+    // 4 arrays x 64 rows x 2 chunks = 512 16-byte copies, 2 per thread
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int idx = tid + i * 256;
+      int arr = idx >> 7, rem = idx & 127;
+      int r = rem >> 1, c = rem & 1;
+      int key = tile * FA_BN + r;
+      bool valid = key < N;
+      const __nv_bfloat16* src = KV[arr] + (size_t)(valid ? key : 0) * 16 + c * 8;
+      cp_async16(smem_base + stage * FA_STAGE_BYTES + arr * FA_ARR_BYTES + fa_off(r, c), src, valid);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < FA_STAGES - 1; ++s) {
+    if (s < ntiles) issue_tile(s, s);
+    cp_async_commit();
+  }
+
+  float o[2][4];
+#pragma unroll
+  for (int nd = 0; nd < 2; ++nd)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
+  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    cp_async_wait<FA_STAGES - 2>();
+    __syncthreads();
+    {  // prefetch tile + STAGES-1 into the stage that was consumed in the previous iteration
+      int nt = tile + FA_STAGES - 1;
+      if (nt < ntiles) issue_tile(nt, nt % FA_STAGES);
+      cp_async_commit();
+    }
+    const uint32_t sb = smem_base + (tile % FA_STAGES) * FA_STAGE_BYTES;
+    const uint32_t sKh = sb, sKl = sb + FA_ARR_BYTES, sVh = sb + 2 * FA_ARR_BYTES, sVl = sb + 3 * FA_ARR_BYTES;
+
+    // ---- S = Q K^T  (8 n-tiles of 8 keys)
+    float sacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sacc[j][i] = 0.f;
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      // ldmatrix.x4: matrices (ntile 2jp, k 0-7), (2jp, k 8-15), (2jp+1, k 0-7), (2jp+1, k 8-15)
+      int mtx = lane >> 3, row = (2 * jp + (mtx >> 1)) * 8 + (lane & 7), chunk = mtx & 1;
+      uint32_t off = fa_off(row, chunk);
+      uint32_t bh[4], bl[4];
+      ldsm_x4(bh, sKh + off);
+      ldsm_x4(bl, sKl + off);
+      mma_bf16_16816(sacc[2 * jp], qh, bh[0], bh[1]);
+      mma_bf16_16816(sacc[2 * jp], qh, bl[0], bl[1]);
+      mma_bf16_16816(sacc[2 * jp], ql, bh[0], bh[1]);
+      mma_bf16_16816(sacc[2 * jp + 1], qh, bh[2], bh[3]);
+      mma_bf16_16816(sacc[2 * jp + 1], qh, bl[2], bl[3]);
+      mma_bf16_16816(sacc[2 * jp + 1], ql, bh[2], bh[3]);
+    }
+    // ---- mask keys beyond N (last tile only)
+    if (tile == ntiles - 1 && (N % FA_BN) != 0) {
+      int kbase = tile * FA_BN;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int k0 = kbase + j * 8 + 2 * t;
+        if (k0 >= N) { sacc[j][0] = -1e30f; sacc[j][2] = -1e30f; }
+        if (k0 + 1 >= N) { sacc[j][1] = -1e30f; sacc[j][3] = -1e30f; }
+      }
+    }
+    // ---- online softmax (rows g and g+8; a row is spread over the 4 lanes of a quad)
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(sacc[j][0], sacc[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(sacc[j][2], sacc[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = ex2f(m0 - mx0), c1 = ex2f(m1 - mx1);
+    m0 = mx0; m1 = mx1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int nd = 0; nd < 2; ++nd) { o[nd][0] *= c0; o[nd][1] *= c0; o[nd][2] *= c1; o[nd][3] *= c1; }
+
+    // ---- P = exp2(S - m), split into hi/lo bf16 A-fragments; O += P V
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int j = 2 * ks + half;
+        float p0 = ex2f(sacc[j][0] - m0), p1 = ex2f(sacc[j][1] - m0);
+        float p2 = ex2f(sacc[j][2] - m1), p3 = ex2f(sacc[j][3] - m1);
+        l0 += p0 + p1;
+        l1 += p2 + p3;
+        uint32_t h01 = pack_bf16x2(p0, p1), h23 = pack_bf16x2(p2, p3);
+        float r0 = p0 - __uint_as_float(h01 << 16), r1 = p1 - __uint_as_float(h01 & 0xffff0000u);
+        float r2 = p2 - __uint_as_float(h23 << 16), r3 = p3 - __uint_as_float(h23 & 0xffff0000u);
+        ah[half * 2 + 0] = h01; ah[half * 2 + 1] = h23;
+        al[half * 2 + 0] = pack_bf16x2(r0, r1); al[half * 2 + 1] = pack_bf16x2(r2, r3);
+      }
+      // ldmatrix.x4.trans on V[key][dim]: matrices (keys lo, dims 0-7), (keys hi, dims 0-7), (keys lo, 8-15), (keys hi, 8-15)
+      int mtx = lane >> 3, row = ks * 16 + (mtx & 1) * 8 + (lane & 7), chunk = mtx >> 1;
+      uint32_t off = fa_off(row, chunk);
+      uint32_t vh[4], vl[4];
+      ldsm_x4_trans(vh, sVh + off);
+      ldsm_x4_trans(vl, sVl + off);
+      mma_bf16_16816(o[0], ah, vh[0], vh[1]);
+      mma_bf16_16816(o[0], ah, vl[0], vl[1]);
+      mma_bf16_16816(o[0], al, vh[0], vh[1]);
+      mma_bf16_16816(o[1], ah, vh[2], vh[3]);
+      mma_bf16_16816(o[1], ah, vl[2], vl[3]);
+      mma_bf16_16816(o[1], al, vh[2], vh[3]);
+    }
+  }
+  cp_async_wait<0>();
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = __fdiv_rn(1.0f, l0), i1 = __fdiv_rn(1.0f, l1);
+  const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+  for (int nd = 0; nd < 2; ++nd) {
+    if (r0 < N) *reinterpret_cast<float2*>(out + (size_t)r0 * 64 + h * 16 + nd * 8 + 2 * t) = make_float2(o[nd][0] * i0, o[nd][1] * i0);
+    if (r1 < N) *reinterpret_cast<float2*>(out + (size_t)r1 * 64 + h * 16 + nd * 8 + 2 * t) = make_float2(o[nd][2] * i1, o[nd][3] * i1);
+  }
+}
+
 // un-patchify epilogue: u [N][256] (n = vox*8+co) -> LayerNorm3D over the 8 channels of each voxel (eps 1e-6)
 // -> prob 1x1x1 (8 -> 1) + bias -> logits [D][H][W]
 __global__ void unpatch_ln_prob_kernel(const float* __restrict__ u, const float* __restrict__ tail,
@@ -191,6 +421,21 @@ __global__ void unpatch_ln_prob_kernel(const float* __restrict__ u, const float*
   logits[((size_t)(dp * 2 + kd) * H + hp * 4 + kh) * W + wp * 4 + kw] = s;
 }
 
+
+// impl 0: tensor-core split-bf16 kernel (product path); impl 1: fp32 SIMT kernel (check kernel, tests only)
+static int run_attention(const float* qkv, float* o, __nv_bfloat16* split, int N, float scale_log2e, int impl, cudaStream_t s) {
+  if (impl == 1) {
+    attention_f32_kernel<<<dim3(cdiv(N, 128), 4), 128, 0, s>>>(qkv, o, N, scale_log2e);
+    MVSF_LAUNCH_CHECK("attention_f32");
+    return MVSF_OK;
+  }
+  qkv_split_kernel<<<cdiv((long long)N * 48, 256), 256, 0, s>>>(qkv, split, N, scale_log2e);
+  MVSF_LAUNCH_CHECK("qkv_split");
+  attention_mma_kernel<<<dim3(cdiv(N, FA_BM), 4), 256, 0, s>>>(split, o, N);
+  MVSF_LAUNCH_CHECK("attention_mma");
+  return MVSF_OK;
+}
+
 }  // namespace mvsf
 
 using namespace mvsf;
@@ -202,8 +447,8 @@ int mvsf_costreg_tr_workspace_bytes(int C, int D, int H, int W, size_t* bytes) {
   MVSF_REQUIRE(D % 2 == 0 && H % 4 == 0 && W % 4 == 0 && D > 0 && H > 0 && W > 0,
                "costreg_tr: D %% 2, H %% 4, W %% 4 must be 0 (down_rate (2,4,4))");
   size_t N = (size_t)(D / 2) * (H / 4) * (W / 4);
-  // patches/u/h [N][256], x [N][64], y [N][64], o [N][64], qkv [N][192]
-  *bytes = N * (256 + 64 + 64 + 64 + 192) * sizeof(float);
+  // patches/u/h [N][256], x [N][64], y [N][64], o [N][64], qkv [N][192], split bf16 [6][4][N][16] (= 192 floats / token)
+  *bytes = N * (256 + 64 + 64 + 64 + 192 + 192) * sizeof(float);
   return MVSF_OK;
 }
 
@@ -225,6 +470,7 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, f
   float* y = x + (size_t)N * 64;           // [N][64]
   float* o = y + (size_t)N * 64;           // [N][64]
   float* qkv = o + (size_t)N * 64;         // [N][192]
+  __nv_bfloat16* split = reinterpret_cast<__nv_bfloat16*>(qkv + (size_t)N * 192);  // [6][4][N][16] bf16
 
   if (pos) {
     pe3d_add_kernel<<<cdiv((long long)nvox, 256), 256, 0, s>>>(volume, pos, wts + TR_PE, nvox);
@@ -244,9 +490,7 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, f
     LinArgs q{};
     q.A = x; q.lda = 64; q.W = lw + L_QKV; q.bias = nullptr; q.C = qkv; q.ldc = 192; q.M = N; q.N = 192; q.K = 64;
     if ((rc = launch_linear(q, LIN_BIAS, s))) return rc;
-    dim3 agrid(cdiv(N, 128), 4);
-    attention_f32_kernel<<<agrid, 128, 0, s>>>(qkv, o, N, scale_log2e);
-    MVSF_LAUNCH_CHECK("attention_f32");
+    if ((rc = run_attention(qkv, o, split, N, scale_log2e, 0, s))) return rc;
     LinArgs p{};
     p.A = o; p.lda = 64; p.W = lw + L_PROJ_W; p.bias = lw + L_PROJ_B; p.C = y; p.ldc = 64; p.M = N; p.N = 64; p.K = 64;
     p.res = x; p.ldres = 64; p.gamma = lw + L_G1; p.ln_w = lw + L_N1W; p.ln_b = lw + L_N1B; p.ln_eps = 1e-5f;
@@ -266,5 +510,15 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, f
   unpatch_ln_prob_kernel<<<cdiv((long long)nvox, 256), 256, 0, s>>>(big, uw + U_LNW, logits, D, H, W);
   MVSF_LAUNCH_CHECK("unpatch_ln_prob");
   return MVSF_OK;
+}
+
+/* Softmax attention alone (attention.py:141-170): qkv [N][3][4][16] fp32 -> out [N][64].  workspace >= N*768 bytes.
+ * impl 0 = product tensor-core kernel, impl 1 = fp32 SIMT check kernel (used by tests to validate impl 0 at full size). */
+int mvsf_attention_forward(const float* qkv, float* out, void* workspace, size_t workspace_bytes, int N,
+                           float softmax_scale, int impl, mvsf_stream_t stream) {
+  MVSF_REQUIRE(qkv && out && workspace && N > 0 && (impl == 0 || impl == 1), "attention_forward: bad arguments");
+  if (workspace_bytes < (size_t)N * 768) return fail(MVSF_ERR_WORKSPACE, "attention_forward: workspace %zu < %zu bytes", workspace_bytes, (size_t)N * 768);
+  return run_attention(qkv, out, reinterpret_cast<__nv_bfloat16*>(workspace), N, softmax_scale * 1.4426950408889634f, impl,
+                       (cudaStream_t)stream);
 }
 }

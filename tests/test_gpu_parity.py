@@ -433,3 +433,30 @@ def test_identity_homography_property(dev, L):
     e = float((vol - want[None]).abs().max())
     rec("identity_homography", abs=e)
     assert e < 5e-3  # coordinates round-trip through fp32 normalisation (<=1e-4 px) on white-noise features
+
+
+# ----------------------------------------------------------------------------------------------- tensor-core attention
+@pytest.mark.parametrize("N", [200, 1000, 27648])
+def test_attention_tensor_core_vs_fp32(dev, L, N):
+    """Product attention kernel (mma.sync, 3-term split-bf16) against (a) the fp32 SIMT check kernel on the GPU and
+    (b) for small N an fp64 softmax(QK^T*scale)V on the CPU.  Inputs have LayerNorm-like statistics."""
+    g = torch.Generator().manual_seed(N)
+    qkv = torch.randn(N, 192, generator=g) * 1.5
+    scale = 16 ** -0.5 * math.log(N, 12185)
+    qd = qkv.to(dev)
+    ws = torch.empty(N * 192 + 16, device=dev)
+    o0 = torch.empty(N, 64, device=dev)
+    o1 = torch.empty(N, 64, device=dev)
+    ck(L.mvsf_attention_forward(P(qd), P(o0), P(ws), ctypes.c_size_t(ws.numel() * 4), N, float(scale), 0, S()), "attention impl0")
+    ck(L.mvsf_attention_forward(P(qd), P(o1), P(ws), ctypes.c_size_t(ws.numel() * 4), N, float(scale), 1, S()), "attention impl1")
+    torch.cuda.synchronize()
+    e01 = max_abs(o0.cpu(), o1.cpu())
+    out = {"tc_vs_f32": e01, "scale": float(o1.abs().max())}
+    if N <= 1000:
+        q, k, v = [qkv[:, i * 64:(i + 1) * 64].double().view(N, 4, 16).transpose(0, 1) for i in range(3)]
+        want = (torch.softmax(q @ k.transpose(1, 2) * scale, -1) @ v).transpose(0, 1).reshape(N, 64)
+        out["tc_vs_f64"] = max_abs(o0.cpu(), want)
+        out["f32_vs_f64"] = max_abs(o1.cpu(), want)
+        assert out["tc_vs_f64"] < 2e-5
+    rec(f"attention_N{N}", **out)
+    assert e01 < 2e-5
