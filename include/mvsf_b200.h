@@ -97,10 +97,10 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, f
                             mvsf_stream_t stream);
 
 /* softmax attention of R1 alone: models/dino/layers/attention.py:141-170 (FlashAttention2.forward after the qkv linear).
- * qkv [N][3][4][16] -> out [N][64]; workspace >= N*768 bytes.  impl 0 = product (tensor cores, split-bf16),
- * impl 1 = fp32 SIMT check kernel used by the tests to validate impl 0 at full size. */
+ * qkv [N][3][4][16] fp32 -> out [N][64]; workspace >= N*768 bytes.  Tensor cores (mma.sync), 3-term split-fp16 operands,
+ * fp32 accumulate; |q*scale|, |k|, |v| must be < 65504. */
 int mvsf_attention_forward(const float* qkv, float* out, void* workspace, size_t workspace_bytes, int N,
-                           float softmax_scale, int impl, mvsf_stream_t stream);
+                           float softmax_scale, mvsf_stream_t stream);
 
 /* ---- S1: models/cost_volume.py:105-117 + models/module.py:649-655 (eval, depth_type 'ce').
  * logits [D][H][W], depth hypotheses [D][H][W] -> prob [D][H][W], depth [H][W], conf [H][W] */

@@ -7,7 +7,7 @@
 //   --> un-patchify GEMM (64 -> 2*4*4*8) --> per-voxel LN3D(8) + 1x1x1 prob --> logits [D][H][W]
 // Softmax attention is order-free over tokens, so tokens are kept in (d', h', w') raster order instead of the
 // reference's "(h w d)" (module.py:573) - the result is identical.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <float.h>
 
 #include "linear.cuh"
@@ -76,110 +76,32 @@ __global__ void patch_gather_kernel(const float* __restrict__ vol, float* __rest
   reinterpret_cast<float4*>(patches)[i] = ldg4(vol + src);
 }
 
-// fp32 softmax attention, one thread per query, K/V tiles broadcast from shared memory, online softmax in
-// blocks of 8 keys.  qkv [N][3][4][16] (attention.py:77), out [N][4][16].
-constexpr int ATT_KT = 128;
-__global__ void __launch_bounds__(128)
-attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int N, float scale_log2e) {
-  __shared__ __align__(16) float Ks[ATT_KT][16];
-  __shared__ __align__(16) float Vs[ATT_KT][16];
-  const int h = blockIdx.y;
-  const int qi = blockIdx.x * 128 + threadIdx.x;
-  const bool qvalid = qi < N;
-  float q[16];
-  {
-    const float* qp = qkv + (size_t)(qvalid ? qi : 0) * 192 + h * 16;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float4 t = ldg4(qp + c * 4);
-      q[c * 4 + 0] = t.x * scale_log2e; q[c * 4 + 1] = t.y * scale_log2e;
-      q[c * 4 + 2] = t.z * scale_log2e; q[c * 4 + 3] = t.w * scale_log2e;
-    }
-  }
-  float m = -1e30f, l = 0.f, o[16];
-#pragma unroll
-  for (int d = 0; d < 16; ++d) o[d] = 0.f;
-
-  for (int k0 = 0; k0 < N; k0 += ATT_KT) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < ATT_KT * 4; i += 128) {
-      int kk = i >> 2, c = i & 3;
-      int key = k0 + kk;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (key < N) {
-        kv = ldg4(qkv + (size_t)key * 192 + 64 + h * 16 + c * 4);
-        vv = ldg4(qkv + (size_t)key * 192 + 128 + h * 16 + c * 4);
-      }
-      *reinterpret_cast<float4*>(&Ks[kk][c * 4]) = kv;
-      *reinterpret_cast<float4*>(&Vs[kk][c * 4]) = vv;
-    }
-    __syncthreads();
-    const int kmax = min(ATT_KT, N - k0);
-    for (int j = 0; j < ATT_KT; j += 8) {
-      if (j >= kmax) break;
-      float s[8];
-      float mb = m;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4* kp = reinterpret_cast<const float4*>(&Ks[j + i][0]);
-        float4 k0v = kp[0], k1v = kp[1], k2v = kp[2], k3v = kp[3];
-        float a = q[0] * k0v.x;
-        a = fmaf(q[1], k0v.y, a); a = fmaf(q[2], k0v.z, a); a = fmaf(q[3], k0v.w, a);
-        a = fmaf(q[4], k1v.x, a); a = fmaf(q[5], k1v.y, a); a = fmaf(q[6], k1v.z, a); a = fmaf(q[7], k1v.w, a);
-        a = fmaf(q[8], k2v.x, a); a = fmaf(q[9], k2v.y, a); a = fmaf(q[10], k2v.z, a); a = fmaf(q[11], k2v.w, a);
-        a = fmaf(q[12], k3v.x, a); a = fmaf(q[13], k3v.y, a); a = fmaf(q[14], k3v.z, a); a = fmaf(q[15], k3v.w, a);
-        s[i] = (j + i < kmax) ? a : -1e30f;
-        mb = fmaxf(mb, s[i]);
-      }
-      const float corr = exp2f(m - mb);
-      m = mb;
-      l *= corr;
-#pragma unroll
-      for (int d = 0; d < 16; ++d) o[d] *= corr;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float p = exp2f(s[i] - mb);
-        l += p;
-        const float4* vp = reinterpret_cast<const float4*>(&Vs[j + i][0]);
-        float4 v0 = vp[0], v1 = vp[1], v2 = vp[2], v3 = vp[3];
-        o[0] = fmaf(p, v0.x, o[0]); o[1] = fmaf(p, v0.y, o[1]); o[2] = fmaf(p, v0.z, o[2]); o[3] = fmaf(p, v0.w, o[3]);
-        o[4] = fmaf(p, v1.x, o[4]); o[5] = fmaf(p, v1.y, o[5]); o[6] = fmaf(p, v1.z, o[6]); o[7] = fmaf(p, v1.w, o[7]);
-        o[8] = fmaf(p, v2.x, o[8]); o[9] = fmaf(p, v2.y, o[9]); o[10] = fmaf(p, v2.z, o[10]); o[11] = fmaf(p, v2.w, o[11]);
-        o[12] = fmaf(p, v3.x, o[12]); o[13] = fmaf(p, v3.y, o[13]); o[14] = fmaf(p, v3.z, o[14]); o[15] = fmaf(p, v3.w, o[15]);
-      }
-    }
-  }
-  if (qvalid) {
-    const float inv = __fdiv_rn(1.0f, l);
-    float* op = out + (size_t)qi * 64 + h * 16;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      *reinterpret_cast<float4*>(op + c * 4) =
-          make_float4(o[c * 4 + 0] * inv, o[c * 4 + 1] * inv, o[c * 4 + 2] * inv, o[c * 4 + 3] * inv);
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------------------------
 // Tensor-core softmax attention (product path).  head_dim 16 makes QK^T a single k16 MMA step and PV an n16 tile, so
 // the kernel is bound by the SIMT softmax work, not by the tensor pipe; it is written FlashAttention-2 style on
-// mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with every operand split into hi + lo bf16 parts and three MMAs per
-// product (hi*hi + hi*lo + lo*hi, error ~2^-17 relative) so the result stays within the fp32 parity budget
-// (a single bf16/tf32 pass moves probabilities by ~1e-3).
-//   split kernel : qkv [N][3][4][16] fp32 -> Qh,Ql,Kh,Kl,Vh,Vl [4][N][16] bf16   (q pre-scaled by scale*log2(e))
+// mma.sync.m16n8k16 (fp16 in, fp32 accumulate) with every operand split into hi + lo fp16 parts and three MMAs per
+// product (lo*hi + hi*lo + hi*hi; hi+lo carries 22 mantissa bits, the dropped lo*lo term is 2^-22 relative) so the
+// result stays within the fp32 parity budget.  A single bf16/tf32 pass moves probabilities by ~1e-3
+// and a bf16 split (2^-17 per product) still left 4e-4 at N = 27648 where |score| reaches 14 in log2 units.
+// Range assumption: |q*scale|, |k|, |v| < 65504 (LayerNorm-ed tokens through 64x64 linears: O(10)).
+//   split kernel : qkv [N][3][4][16] fp32 -> Qh,Ql,Kh,Kl,Vh,Vl [4][N][16] fp16   (q pre-scaled by scale*log2(e))
 //   main kernel  : CTA = 8 warps x 16 queries, 64-key tiles of K/V streamed with cp.async (3 stages), swizzled rows
 //                  so ldmatrix is bank-conflict free; S/P live in registers (C-fragment == A-fragment layout).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
 }
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(h);  // .x = low half, .y = high half
 }
-__global__ void qkv_split_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ split, int N, float qscale) {
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+__global__ void qkv_split_kernel(const float* __restrict__ qkv, __half* __restrict__ split, int N, float qscale) {
   // split layout: [6][4 heads][N][16]  (0 Qh, 1 Ql, 2 Kh, 3 Kl, 4 Vh, 5 Vl)
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // (token, which(q/k/v), head, quad of 4 dims)
   int total = N * 3 * 4 * 4;
@@ -187,18 +109,18 @@ __global__ void qkv_split_kernel(const float* __restrict__ qkv, __nv_bfloat16* _
   int quad = i & 3, h = (i >> 2) & 3, which = (i >> 4) % 3, tok = i / 48;
   float4 v = ldg4(qkv + (size_t)tok * 192 + which * 64 + h * 16 + quad * 4);
   if (which == 0) { v.x *= qscale; v.y *= qscale; v.z *= qscale; v.w *= qscale; }
-  __nv_bfloat16 hi[4], lo[4];
-  split_bf16(v.x, hi[0], lo[0]); split_bf16(v.y, hi[1], lo[1]); split_bf16(v.z, hi[2], lo[2]); split_bf16(v.w, hi[3], lo[3]);
+  __half hi[4], lo[4];
+  split_f16(v.x, hi[0], lo[0]); split_f16(v.y, hi[1], lo[1]); split_f16(v.z, hi[2], lo[2]); split_f16(v.w, hi[3], lo[3]);
   size_t plane = (size_t)4 * N * 16;
   size_t off = ((size_t)h * N + tok) * 16 + quad * 4;
-  __nv_bfloat16* ph = split + (size_t)(which * 2) * plane + off;
-  __nv_bfloat16* pl = split + (size_t)(which * 2 + 1) * plane + off;
+  __half* ph = split + (size_t)(which * 2) * plane + off;
+  __half* pl = split + (size_t)(which * 2 + 1) * plane + off;
   *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(hi);
   *reinterpret_cast<uint2*>(pl) = *reinterpret_cast<uint2*>(lo);
 }
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -232,16 +154,16 @@ constexpr int FA_ARR_BYTES = FA_BN * 32, FA_STAGE_BYTES = 4 * FA_ARR_BYTES;
 __device__ __forceinline__ int fa_off(int r, int c) { return r * 32 + ((c ^ ((r >> 2) & 1)) << 4); }
 
 __global__ void __launch_bounds__(256)
-attention_mma_kernel(const __nv_bfloat16* __restrict__ split, float* __restrict__ out, int N) {
+attention_mma_kernel(const __half* __restrict__ split, float* __restrict__ out, int N) {
   __shared__ __align__(128) unsigned char smem[FA_STAGES * FA_STAGE_BYTES];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y;
   const int q0 = blockIdx.x * FA_BM + warp * 16;
   const size_t plane = (size_t)4 * N * 16;
-  const __nv_bfloat16* Qh = split + 0 * plane + (size_t)h * N * 16;
-  const __nv_bfloat16* Ql = split + 1 * plane + (size_t)h * N * 16;
-  const __nv_bfloat16* KV[4] = {split + 2 * plane + (size_t)h * N * 16, split + 3 * plane + (size_t)h * N * 16,
+  const __half* Qh = split + 0 * plane + (size_t)h * N * 16;
+  const __half* Ql = split + 1 * plane + (size_t)h * N * 16;
+  const __half* KV[4] = {split + 2 * plane + (size_t)h * N * 16, split + 3 * plane + (size_t)h * N * 16,
                                 split + 4 * plane + (size_t)h * N * 16, split + 5 * plane + (size_t)h * N * 16};
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 
@@ -269,7 +191,7 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ split, float* __restrict_
       int r = rem >> 1, c = rem & 1;
       int key = tile * FA_BN + r;
       bool valid = key < N;
-      const __nv_bfloat16* src = KV[arr] + (size_t)(valid ? key : 0) * 16 + c * 8;
+      const __half* src = KV[arr] + (size_t)(valid ? key : 0) * 16 + c * 8;
       cp_async16(smem_base + stage * FA_STAGE_BYTES + arr * FA_ARR_BYTES + fa_off(r, c), src, valid);
     }
   };
@@ -311,12 +233,12 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ split, float* __restrict_
       uint32_t bh[4], bl[4];
       ldsm_x4(bh, sKh + off);
       ldsm_x4(bl, sKl + off);
-      mma_bf16_16816(sacc[2 * jp], qh, bh[0], bh[1]);
-      mma_bf16_16816(sacc[2 * jp], qh, bl[0], bl[1]);
-      mma_bf16_16816(sacc[2 * jp], ql, bh[0], bh[1]);
-      mma_bf16_16816(sacc[2 * jp + 1], qh, bh[2], bh[3]);
-      mma_bf16_16816(sacc[2 * jp + 1], qh, bl[2], bl[3]);
-      mma_bf16_16816(sacc[2 * jp + 1], ql, bh[2], bh[3]);
+      mma_f16_16816(sacc[2 * jp], ql, bh[0], bh[1]);
+      mma_f16_16816(sacc[2 * jp], qh, bl[0], bl[1]);
+      mma_f16_16816(sacc[2 * jp], qh, bh[0], bh[1]);
+      mma_f16_16816(sacc[2 * jp + 1], ql, bh[2], bh[3]);
+      mma_f16_16816(sacc[2 * jp + 1], qh, bl[2], bl[3]);
+      mma_f16_16816(sacc[2 * jp + 1], qh, bh[2], bh[3]);
     }
     // ---- mask keys beyond N (last tile only)
     if (tile == ntiles - 1 && (N % FA_BN) != 0) {
@@ -342,10 +264,16 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ split, float* __restrict_
     const float c0 = ex2f(m0 - mx0), c1 = ex2f(m1 - mx1);
     m0 = mx0; m1 = mx1;
     l0 *= c0; l1 *= c1;
+    // Tensor-core fp32 accumulation truncates; chaining all 5k MMAs of a row on one accumulator biases the result by
+    // ~1e-4 relative.  Each tile therefore accumulates into fresh registers (12 chained MMAs) that are folded into the
+    // running output with a round-to-nearest FMA below.
+    float ot[2][4];
 #pragma unroll
-    for (int nd = 0; nd < 2; ++nd) { o[nd][0] *= c0; o[nd][1] *= c0; o[nd][2] *= c1; o[nd][3] *= c1; }
+    for (int nd = 0; nd < 2; ++nd)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ot[nd][i] = 0.f;
 
-    // ---- P = exp2(S - m), split into hi/lo bf16 A-fragments; O += P V
+    // ---- P = exp2(S - m), split into hi/lo fp16 A-fragments; O += P V
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t ah[4], al[4];
@@ -356,11 +284,10 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ split, float* __restrict_
         float p2 = ex2f(sacc[j][2] - m1), p3 = ex2f(sacc[j][3] - m1);
         l0 += p0 + p1;
         l1 += p2 + p3;
-        uint32_t h01 = pack_bf16x2(p0, p1), h23 = pack_bf16x2(p2, p3);
-        float r0 = p0 - __uint_as_float(h01 << 16), r1 = p1 - __uint_as_float(h01 & 0xffff0000u);
-        float r2 = p2 - __uint_as_float(h23 << 16), r3 = p3 - __uint_as_float(h23 & 0xffff0000u);
+        uint32_t h01 = pack_f16x2(p0, p1), h23 = pack_f16x2(p2, p3);
+        float2 f01 = unpack_f16x2(h01), f23 = unpack_f16x2(h23);
         ah[half * 2 + 0] = h01; ah[half * 2 + 1] = h23;
-        al[half * 2 + 0] = pack_bf16x2(r0, r1); al[half * 2 + 1] = pack_bf16x2(r2, r3);
+        al[half * 2 + 0] = pack_f16x2(p0 - f01.x, p1 - f01.y); al[half * 2 + 1] = pack_f16x2(p2 - f23.x, p3 - f23.y);
       }
       // ldmatrix.x4.trans on V[key][dim]: matrices (keys lo, dims 0-7), (keys hi, dims 0-7), (keys lo, 8-15), (keys hi, 8-15)
       int mtx = lane >> 3, row = ks * 16 + (mtx & 1) * 8 + (lane & 7), chunk = mtx >> 1;
@@ -368,12 +295,17 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ split, float* __restrict_
       uint32_t vh[4], vl[4];
       ldsm_x4_trans(vh, sVh + off);
       ldsm_x4_trans(vl, sVl + off);
-      mma_bf16_16816(o[0], ah, vh[0], vh[1]);
-      mma_bf16_16816(o[0], ah, vl[0], vl[1]);
-      mma_bf16_16816(o[0], al, vh[0], vh[1]);
-      mma_bf16_16816(o[1], ah, vh[2], vh[3]);
-      mma_bf16_16816(o[1], ah, vl[2], vl[3]);
-      mma_bf16_16816(o[1], al, vh[2], vh[3]);
+      mma_f16_16816(ot[0], al, vh[0], vh[1]);
+      mma_f16_16816(ot[0], ah, vl[0], vl[1]);
+      mma_f16_16816(ot[0], ah, vh[0], vh[1]);
+      mma_f16_16816(ot[1], al, vh[2], vh[3]);
+      mma_f16_16816(ot[1], ah, vl[2], vl[3]);
+      mma_f16_16816(ot[1], ah, vh[2], vh[3]);
+    }
+#pragma unroll
+    for (int nd = 0; nd < 2; ++nd) {
+      o[nd][0] = fmaf(o[nd][0], c0, ot[nd][0]); o[nd][1] = fmaf(o[nd][1], c0, ot[nd][1]);
+      o[nd][2] = fmaf(o[nd][2], c1, ot[nd][2]); o[nd][3] = fmaf(o[nd][3], c1, ot[nd][3]);
     }
   }
   cp_async_wait<0>();
@@ -422,13 +354,7 @@ __global__ void unpatch_ln_prob_kernel(const float* __restrict__ u, const float*
 }
 
 
-// impl 0: tensor-core split-bf16 kernel (product path); impl 1: fp32 SIMT kernel (check kernel, tests only)
-static int run_attention(const float* qkv, float* o, __nv_bfloat16* split, int N, float scale_log2e, int impl, cudaStream_t s) {
-  if (impl == 1) {
-    attention_f32_kernel<<<dim3(cdiv(N, 128), 4), 128, 0, s>>>(qkv, o, N, scale_log2e);
-    MVSF_LAUNCH_CHECK("attention_f32");
-    return MVSF_OK;
-  }
+static int run_attention(const float* qkv, float* o, __half* split, int N, float scale_log2e, cudaStream_t s) {
   qkv_split_kernel<<<cdiv((long long)N * 48, 256), 256, 0, s>>>(qkv, split, N, scale_log2e);
   MVSF_LAUNCH_CHECK("qkv_split");
   attention_mma_kernel<<<dim3(cdiv(N, FA_BM), 4), 256, 0, s>>>(split, o, N);
@@ -447,7 +373,7 @@ int mvsf_costreg_tr_workspace_bytes(int C, int D, int H, int W, size_t* bytes) {
   MVSF_REQUIRE(D % 2 == 0 && H % 4 == 0 && W % 4 == 0 && D > 0 && H > 0 && W > 0,
                "costreg_tr: D %% 2, H %% 4, W %% 4 must be 0 (down_rate (2,4,4))");
   size_t N = (size_t)(D / 2) * (H / 4) * (W / 4);
-  // patches/u/h [N][256], x [N][64], y [N][64], o [N][64], qkv [N][192], split bf16 [6][4][N][16] (= 192 floats / token)
+  // patches/u/h [N][256], x [N][64], y [N][64], o [N][64], qkv [N][192], split fp16 [6][4][N][16] (= 192 floats / token)
   *bytes = N * (256 + 64 + 64 + 64 + 192 + 192) * sizeof(float);
   return MVSF_OK;
 }
@@ -470,7 +396,7 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, f
   float* y = x + (size_t)N * 64;           // [N][64]
   float* o = y + (size_t)N * 64;           // [N][64]
   float* qkv = o + (size_t)N * 64;         // [N][192]
-  __nv_bfloat16* split = reinterpret_cast<__nv_bfloat16*>(qkv + (size_t)N * 192);  // [6][4][N][16] bf16
+  __half* split = reinterpret_cast<__half*>(qkv + (size_t)N * 192);  // [6][4][N][16] fp16
 
   if (pos) {
     pe3d_add_kernel<<<cdiv((long long)nvox, 256), 256, 0, s>>>(volume, pos, wts + TR_PE, nvox);
@@ -490,7 +416,7 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, f
     LinArgs q{};
     q.A = x; q.lda = 64; q.W = lw + L_QKV; q.bias = nullptr; q.C = qkv; q.ldc = 192; q.M = N; q.N = 192; q.K = 64;
     if ((rc = launch_linear(q, LIN_BIAS, s))) return rc;
-    if ((rc = run_attention(qkv, o, split, N, scale_log2e, 0, s))) return rc;
+    if ((rc = run_attention(qkv, o, split, N, scale_log2e, s))) return rc;
     LinArgs p{};
     p.A = o; p.lda = 64; p.W = lw + L_PROJ_W; p.bias = lw + L_PROJ_B; p.C = y; p.ldc = 64; p.M = N; p.N = 64; p.K = 64;
     p.res = x; p.ldres = 64; p.gamma = lw + L_G1; p.ln_w = lw + L_N1W; p.ln_b = lw + L_N1B; p.ln_eps = 1e-5f;
@@ -512,13 +438,11 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, f
   return MVSF_OK;
 }
 
-/* Softmax attention alone (attention.py:141-170): qkv [N][3][4][16] fp32 -> out [N][64].  workspace >= N*768 bytes.
- * impl 0 = product tensor-core kernel, impl 1 = fp32 SIMT check kernel (used by tests to validate impl 0 at full size). */
+/* Softmax attention alone (attention.py:141-170): qkv [N][3][4][16] fp32 -> out [N][64].  workspace >= N*768 bytes. */
 int mvsf_attention_forward(const float* qkv, float* out, void* workspace, size_t workspace_bytes, int N,
-                           float softmax_scale, int impl, mvsf_stream_t stream) {
-  MVSF_REQUIRE(qkv && out && workspace && N > 0 && (impl == 0 || impl == 1), "attention_forward: bad arguments");
+                           float softmax_scale, mvsf_stream_t stream) {
+  MVSF_REQUIRE(qkv && out && workspace && N > 0, "attention_forward: bad arguments");
   if (workspace_bytes < (size_t)N * 768) return fail(MVSF_ERR_WORKSPACE, "attention_forward: workspace %zu < %zu bytes", workspace_bytes, (size_t)N * 768);
-  return run_attention(qkv, out, reinterpret_cast<__nv_bfloat16*>(workspace), N, softmax_scale * 1.4426950408889634f, impl,
-                       (cudaStream_t)stream);
+  return run_attention(qkv, out, reinterpret_cast<__half*>(workspace), N, softmax_scale * 1.4426950408889634f, (cudaStream_t)stream);
 }
 }

@@ -436,27 +436,24 @@ def test_identity_homography_property(dev, L):
 
 
 # ----------------------------------------------------------------------------------------------- tensor-core attention
-@pytest.mark.parametrize("N", [200, 1000, 27648])
-def test_attention_tensor_core_vs_fp32(dev, L, N):
-    """Product attention kernel (mma.sync, 3-term split-bf16) against (a) the fp32 SIMT check kernel on the GPU and
-    (b) for small N an fp64 softmax(QK^T*scale)V on the CPU.  Inputs have LayerNorm-like statistics."""
+@pytest.mark.parametrize("N", [200, 1000, 4000, 27648])
+def test_attention_tensor_core_vs_fp64(dev, L, N):
+    """Product attention kernel (mma.sync, 3-term split-fp16) against an fp64 softmax(QK^T*scale)V evaluated with torch
+    on the GPU (test-side ground truth, chunked over queries).
+    Inputs are deliberately harsher than LayerNorm-ed tokens (std 1.5 -> |score| up to ~14 in log2 units)."""
     g = torch.Generator().manual_seed(N)
     qkv = torch.randn(N, 192, generator=g) * 1.5
     scale = 16 ** -0.5 * math.log(N, 12185)
     qd = qkv.to(dev)
     ws = torch.empty(N * 192 + 16, device=dev)
     o0 = torch.empty(N, 64, device=dev)
-    o1 = torch.empty(N, 64, device=dev)
-    ck(L.mvsf_attention_forward(P(qd), P(o0), P(ws), ctypes.c_size_t(ws.numel() * 4), N, float(scale), 0, S()), "attention impl0")
-    ck(L.mvsf_attention_forward(P(qd), P(o1), P(ws), ctypes.c_size_t(ws.numel() * 4), N, float(scale), 1, S()), "attention impl1")
-    torch.cuda.synchronize()
-    e01 = max_abs(o0.cpu(), o1.cpu())
-    out = {"tc_vs_f32": e01, "scale": float(o1.abs().max())}
-    if N <= 1000:
-        q, k, v = [qkv[:, i * 64:(i + 1) * 64].double().view(N, 4, 16).transpose(0, 1) for i in range(3)]
-        want = (torch.softmax(q @ k.transpose(1, 2) * scale, -1) @ v).transpose(0, 1).reshape(N, 64)
-        out["tc_vs_f64"] = max_abs(o0.cpu(), want)
-        out["f32_vs_f64"] = max_abs(o1.cpu(), want)
-        assert out["tc_vs_f64"] < 2e-5
-    rec(f"attention_N{N}", **out)
-    assert e01 < 2e-5
+    ck(L.mvsf_attention_forward(P(qd), P(o0), P(ws), ctypes.c_size_t(ws.numel() * 4), N, float(scale), S()), "attention")
+    q, k, v = [qd[:, i * 64:(i + 1) * 64].double().view(N, 4, 16).transpose(0, 1) for i in range(3)]
+    want = torch.empty(4, N, 16, dtype=torch.float64, device=dev)
+    for s0 in range(0, N, 2048):
+        a = torch.softmax(q[:, s0:s0 + 2048] @ k.transpose(1, 2) * scale, -1)
+        want[:, s0:s0 + 2048] = a @ v
+    want = want.transpose(0, 1).reshape(N, 64)
+    e_tc, sc = max_abs(o0, want), float(want.abs().max())
+    rec(f"attention_N{N}", tc_vs_f64=e_tc, scale=sc)
+    assert e_tc < 2.5e-5 * sc  # r1: 1.1e-6 (N=200) .. 4.9e-5 (N=27648, scale 4.3); an fp32 one-thread-per-query kernel measured 4.3e-4
