@@ -5,7 +5,8 @@
 // Thread mapping: LPP = C/4 lanes cooperate on one reference pixel, each lane owning 4 consecutive channels
 // and loading them with one 128-bit LDG per corner; a warp therefore covers 32/LPP consecutive pixels and each
 // warp-wide load touches 512 contiguous bytes of the source map when neighbouring pixels map to neighbouring
-// source texels (the common case).  Partial dot products are combined across the LPP lanes with xor-shuffles.
+// source texels (the common case).  Tap coordinates are computed once per warp and shared through shared memory;
+// partial dot products are combined across the LPP lanes with a butterfly reduce-scatter.
 //
 //   pass A (warp_corr_entropy):   sim[d] = sum_g mean_{c in g} ref[c]*warp[c,d]  ->  softmax_D -> entropy
 //   pass B (warp_corr_aggregate): vol[g,d] = sum_v w_v * mean_{c in g} ref*warp_v / (sum_v w_v + 1e-6)
@@ -20,147 +21,240 @@ namespace mvsf {
 
 constexpr int kMaxGenericD = 512;
 
-template <int LPP>
-__device__ __forceinline__ float lanes_sum(float v) {
+// v2 organisation (r1 ncu: v1 was instruction-issue bound because all C/4 lanes of a pixel recomputed the exact-rounding
+// coordinate math: ~220 warp instructions per tap):
+//   A warp owns P = 32/LPP consecutive pixels (LPP = C/4 lanes per pixel) and works on chunks of DCH = 2*LPP
+//   hypotheses, i.e. always 64 (pixel, hypothesis) taps per chunk.
+//   phase 1: every lane computes exactly two of the 64 taps (coordinates -> 4 corner offsets + 4 weights) and parks them
+//            in a per-warp shared-memory table (2 KB);  phase 2: the LPP lanes of a pixel read each tap back with two
+//            broadcast LDS.128 and do the 4-corner gather + correlation for their 4 channels.
+// For the shipped stages DCH equals the stage's hypothesis count (C=64/32/16/8 <-> D=32/16/8/4): one chunk per view.
+template <int C>
+struct WC {
+  static constexpr int LPP = C / 4, P = 32 / LPP, DCH = 2 * LPP;
+};
+struct __align__(16) TapTable {
+  int4 off[64];
+  float4 wt[64];
+};
+
+// phase 1 for one (view, chunk): taps t = lane and lane+32, t = di*P + pi
+template <int C>
+__device__ __forceinline__ void build_taps(TapTable& tb, const float* __restrict__ depth, const Hom& m, float rx, float ry,
+                                           float rz, const CoordConst& cc, int p1, int d0, int D, int HW, int H, int W,
+                                           int lane) {
+  constexpr int P = WC<C>::P;
 #pragma unroll
-  for (int o = LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  for (int k = 0; k < 2; ++k) {
+    const int t = lane + 32 * k;
+    const int d = d0 + t / P;
+    const float dv = (d < D) ? __ldg(depth + (size_t)d * HW + p1) : 1.0f;
+    float ix, iy;
+    warp_coord_fast(rx, ry, rz, m, dv, cc, ix, iy);
+    int4 off;
+    float4 wt;
+    make_tap_fast(ix, iy, W, H, C, off, wt);
+    tb.off[t] = off;
+    tb.wt[t] = wt;
+  }
+}
+__device__ __forceinline__ float4 gather4(const float* __restrict__ base, const int4& o, const float4& w) {
+  float4 a = ldg4(base + o.x), b = ldg4(base + o.y), c = ldg4(base + o.z), d = ldg4(base + o.w);
+  float4 s;
+  s.x = fmaf(d.x, w.w, fmaf(c.x, w.z, fmaf(b.x, w.y, a.x * w.x)));
+  s.y = fmaf(d.y, w.w, fmaf(c.y, w.z, fmaf(b.y, w.y, a.y * w.x)));
+  s.z = fmaf(d.z, w.w, fmaf(c.z, w.z, fmaf(b.z, w.y, a.z * w.x)));
+  s.w = fmaf(d.w, w.w, fmaf(c.w, w.z, fmaf(b.w, w.y, a.w * w.x)));
+  return s;
 }
 
+// Butterfly reduce-scatter over the LPP lanes of a pixel: in: v[0..N) partial sums per lane; out: lane `lip` holds the
+// complete sums of elements [lip*N/LPP, (lip+1)*N/LPP) in v[0..N/LPP).
+template <int N, int LANES>
+struct ReduceScatter {
+  static __device__ __forceinline__ void run(float (&v)[N > 0 ? N : 1], int lip) {
+    if constexpr (LANES > 1) {
+      constexpr int H = N / 2, O = LANES / 2;
+      const bool upper = (lip & O) != 0;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        float send = upper ? v[i] : v[i + H];
+        float keep = upper ? v[i + H] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+      }
+      float (&lo)[H > 0 ? H : 1] = reinterpret_cast<float (&)[H > 0 ? H : 1]>(v);
+      ReduceScatter<H, O>::run(lo, lip);
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------- pass A
-template <int C, int DT>  // DT > 0: D == DT known at compile time (sims stay in registers); DT == 0: runtime D
+template <int C, bool GENERIC>
 __global__ void __launch_bounds__(256)
 warp_corr_entropy_kernel(const float* __restrict__ feat, const float* __restrict__ homs,
                          const float* __restrict__ depth, float* __restrict__ entropy, int G, int D, int H, int W) {
-  constexpr int LPP = C / 4;
+  constexpr int LPP = WC<C>::LPP, P = WC<C>::P, DCH = WC<C>::DCH;
+  constexpr int SPL = DCH / LPP;  // complete sims per lane per chunk (= 2)
+  constexpr int MAXCH = GENERIC ? (kMaxGenericD + DCH - 1) / DCH : 1;
+  __shared__ TapTable tables[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  TapTable& tb = tables[warp];
   const int HW = H * W;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lip = gtid % LPP;
-  const int pix = gtid / LPP;
-  const int v = blockIdx.y;  // source view index (0-based among sources)
-  const bool active = pix < HW;
-  const int p = active ? pix : HW - 1;  // keep every lane alive for the shuffles
-  const int y = p / W, x = p - y * W;
-
+  const int v = blockIdx.y;
+  const int pix0 = (blockIdx.x * 8 + warp) * P;
+  if (pix0 >= HW) return;  // whole warp exits together
+  // phase-1 pixel (lane % P) and phase-2 pixel (lane / LPP)
+  const int p1 = min(pix0 + lane % P, HW - 1);
+  const int p2raw = pix0 + lane / LPP;
+  const bool active = p2raw < HW;
+  const int p2 = active ? p2raw : HW - 1;
+  const int lip = lane % LPP;
   const Hom m = load_hom(homs + (size_t)v * 12);
-  const float4 r = ldg4(feat + (size_t)p * C + lip * 4);
-  const float* __restrict__ src = feat + (size_t)(v + 1) * HW * C + lip * 4;
-
-  const float fx = (float)x, fy = (float)y;
+  const CoordConst cc = make_coord_const(W, H);
+  const int y1 = p1 / W, x1 = p1 - y1 * W;
+  const float fx = (float)x1, fy = (float)y1;
   const float rx = __fadd_rn(fmaf(m.r01, fy, __fmul_rn(m.r00, fx)), m.r02);
   const float ry = __fadd_rn(fmaf(m.r11, fy, __fmul_rn(m.r10, fx)), m.r12);
   const float rz = __fadd_rn(fmaf(m.r21, fy, __fmul_rn(m.r20, fx)), m.r22);
-  const float half_w = (float)(W - 1) * 0.5f, half_h = (float)(H - 1) * 0.5f;
-  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-  const float gscale = (float)G / (float)C;  // 1/(C/G): mean over the channels of a group (power of two)
+  const float4 r = ldg4(feat + (size_t)p2 * C + lip * 4);
+  const float* __restrict__ src = feat + (size_t)(v + 1) * HW * C + lip * 4;
+  const float gscale = (float)G / (float)C;
 
-  float sims[DT > 0 ? DT : kMaxGenericD];
-  float mx = -FLT_MAX;
-  const int Dn = DT > 0 ? DT : D;
+  float sims[MAXCH * SPL];
+  const int nch = GENERIC ? (D + DCH - 1) / DCH : 1;
+  for (int ch = 0; ch < nch; ++ch) {
+    const int d0 = ch * DCH;
+    build_taps<C>(tb, depth, m, rx, ry, rz, cc, p1, d0, D, HW, H, W, lane);
+    __syncwarp();
+    float part[DCH];
+    const int pi = lane / LPP;
 #pragma unroll
-  for (int d = 0; d < Dn; ++d) {
-    float dv = __ldg(depth + (size_t)d * HW + p);
-    float ix, iy, z;
-    warp_coord(rx, ry, rz, m, dv, half_w, half_h, wm1, hm1, ix, iy, z);
-    Tap t = make_tap(ix, iy, W, H, C);
-    float4 s = tap4(src, t);
-    float part = fmaf(r.w, s.w, fmaf(r.z, s.z, fmaf(r.y, s.y, r.x * s.x)));
-    float sim = lanes_sum<LPP>(part) * gscale;
-    sims[d] = sim;
-    mx = fmaxf(mx, sim);
+    for (int di = 0; di < DCH; ++di) {
+      const int4 o = tb.off[di * P + pi];
+      const float4 w = tb.wt[di * P + pi];
+      const float4 s = gather4(src, o, w);
+      part[di] = fmaf(r.w, s.w, fmaf(r.z, s.z, fmaf(r.y, s.y, r.x * s.x)));
+    }
+    __syncwarp();
+    ReduceScatter<DCH, LPP>::run(part, lip);
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+      const int d = d0 + lip * SPL + i;
+      sims[ch * SPL + i] = (d < D) ? part[i] * gscale : -FLT_MAX;
+    }
   }
+  // softmax over D -> entropy; a pixel's sims are spread over its LPP lanes (nch*SPL each)
+  float mx = -FLT_MAX;
+  for (int i = 0; i < nch * SPL; ++i) mx = fmaxf(mx, sims[i]);
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float Z = 0.f;
+  for (int i = 0; i < nch * SPL; ++i) {
+    sims[i] = (sims[i] == -FLT_MAX) ? 0.f : expf(sims[i] - mx);
+    Z += sims[i];
+  }
 #pragma unroll
-  for (int d = 0; d < Dn; ++d) { sims[d] = expf(sims[d] - mx); Z += sims[d]; }
+  for (int o = LPP / 2; o > 0; o >>= 1) Z += __shfl_xor_sync(0xffffffffu, Z, o);
   float ent = 0.f;
-#pragma unroll
-  for (int d = 0; d < Dn; ++d) {
-    float pr = __fdiv_rn(sims[d], Z);
+  for (int i = 0; i < nch * SPL; ++i) {
+    float pr = __fdiv_rn(sims[i], Z);
     ent -= pr * logf(pr + 1e-7f);
   }
-  if (active && lip == 0) entropy[(size_t)v * HW + p] = ent;
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, o);
+  if (active && lip == 0) entropy[(size_t)v * HW + p2] = ent;
 }
 
 // ---------------------------------------------------------------------------------------------- pass B
-// CPG = C/G channels per group.  NGL = groups owned by one lane = max(1, 4/CPG).
-template <int C, int CPG, int DC>
+// CPG = C/G channels per group.  A lane owns NGL = max(1, 4/CPG) groups; for CPG = 8 two lanes share a group and their
+// partial sums are combined once at the end (the view reduction is linear).
+template <int C, int CPG>
 __global__ void __launch_bounds__(256)
 warp_corr_aggregate_kernel(const float* __restrict__ feat, const float* __restrict__ homs,
                            const float* __restrict__ depth, const float* __restrict__ vis,
                            float* __restrict__ volume, int V, int D, int H, int W) {
-  constexpr int LPP = C / 4;
+  constexpr int LPP = WC<C>::LPP, P = WC<C>::P, DCH = WC<C>::DCH;
   constexpr int G = C / CPG;
   constexpr int NGL = (CPG >= 4) ? 1 : 4 / CPG;
-  constexpr int LPG = (CPG >= 4) ? CPG / 4 : 1;  // lanes per group
+  constexpr int LPG = (CPG >= 4) ? CPG / 4 : 1;  // lanes per group (1 or 2)
+  static_assert(LPG == 1 || LPG == 2, "C/G must be 1, 2, 4 or 8");
+  __shared__ TapTable tables[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  TapTable& tb = tables[warp];
   const int HW = H * W;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lip = gtid % LPP;
-  const int pix = gtid / LPP;
-  const bool active = pix < HW;
-  const int p = active ? pix : HW - 1;
-  const int y = p / W, x = p - y * W;
-  const float4 r = ldg4(feat + (size_t)p * C + lip * 4);
-  const float fx = (float)x, fy = (float)y;
-  const float half_w = (float)(W - 1) * 0.5f, half_h = (float)(H - 1) * 0.5f;
-  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  const int pix0 = (blockIdx.x * 8 + warp) * P;
+  if (pix0 >= HW) return;
+  const int p1 = min(pix0 + lane % P, HW - 1);
+  const int p2raw = pix0 + lane / LPP;
+  const bool active = p2raw < HW;
+  const int p2 = active ? p2raw : HW - 1;
+  const int lip = lane % LPP, pi = lane / LPP;
+  const CoordConst cc = make_coord_const(W, H);
+  const int y1 = p1 / W, x1 = p1 - y1 * W;
+  const float fx = (float)x1, fy = (float)y1;
+  const float4 r = ldg4(feat + (size_t)p2 * C + lip * 4);
   constexpr float inv_cpg = 1.0f / (float)CPG;
 
-  for (int d0 = 0; d0 < D; d0 += DC) {
-    float acc[DC][NGL];
+  for (int d0 = 0; d0 < D; d0 += DCH) {
+    float acc[NGL][DCH];
 #pragma unroll
-    for (int i = 0; i < DC; ++i)
+    for (int g = 0; g < NGL; ++g)
 #pragma unroll
-      for (int g = 0; g < NGL; ++g) acc[i][g] = 0.f;
-    float dvs[DC];
-#pragma unroll
-    for (int i = 0; i < DC; ++i) dvs[i] = (d0 + i < D) ? __ldg(depth + (size_t)(d0 + i) * HW + p) : 1.0f;
+      for (int i = 0; i < DCH; ++i) acc[g][i] = 0.f;
     float wsum = 0.f;
     for (int v = 0; v < V - 1; ++v) {
       const Hom m = load_hom(homs + (size_t)v * 12);
       const float rx = __fadd_rn(fmaf(m.r01, fy, __fmul_rn(m.r00, fx)), m.r02);
       const float ry = __fadd_rn(fmaf(m.r11, fy, __fmul_rn(m.r10, fx)), m.r12);
       const float rz = __fadd_rn(fmaf(m.r21, fy, __fmul_rn(m.r20, fx)), m.r22);
+      build_taps<C>(tb, depth, m, rx, ry, rz, cc, p1, d0, D, HW, H, W, lane);
+      __syncwarp();
       const float* __restrict__ src = feat + (size_t)(v + 1) * HW * C + lip * 4;
-      const float w = __ldg(vis + (size_t)v * HW + p);
+      const float w = __ldg(vis + (size_t)v * HW + p2);
       wsum = __fadd_rn(wsum, w);
 #pragma unroll
-      for (int i = 0; i < DC; ++i) {
-        float ix, iy, z;
-        warp_coord(rx, ry, rz, m, dvs[i], half_w, half_h, wm1, hm1, ix, iy, z);
-        Tap t = make_tap(ix, iy, W, H, C);
-        float4 s = tap4(src, t);
+      for (int di = 0; di < DCH; ++di) {
+        const int4 o = tb.off[di * P + pi];
+        const float4 wt = tb.wt[di * P + pi];
+        const float4 s = gather4(src, o, wt);
         if (CPG >= 4) {
-          float part = fmaf(r.w, s.w, fmaf(r.z, s.z, fmaf(r.y, s.y, r.x * s.x)));
-          part = lanes_sum<LPG>(part) * inv_cpg;
-          acc[i][0] = fmaf(part, w, acc[i][0]);
+          float part = fmaf(r.w, s.w, fmaf(r.z, s.z, fmaf(r.y, s.y, r.x * s.x))) * inv_cpg;
+          acc[0][di] = fmaf(part, w, acc[0][di]);
         } else if (CPG == 2) {
-          float p0 = fmaf(r.y, s.y, r.x * s.x) * inv_cpg;
-          float p1 = fmaf(r.w, s.w, r.z * s.z) * inv_cpg;
-          acc[i][0] = fmaf(p0, w, acc[i][0]);
-          acc[i][NGL > 1 ? 1 : 0] = fmaf(p1, w, acc[i][NGL > 1 ? 1 : 0]);
+          acc[0][di] = fmaf(fmaf(r.y, s.y, r.x * s.x) * inv_cpg, w, acc[0][di]);
+          acc[NGL > 1 ? 1 : 0][di] = fmaf(fmaf(r.w, s.w, r.z * s.z) * inv_cpg, w, acc[NGL > 1 ? 1 : 0][di]);
         } else {  // CPG == 1: plain product (cost_volume.py:84-85)
-          acc[i][0] = fmaf(r.x * s.x, w, acc[i][0]);
-          acc[i][NGL > 1 ? 1 : 0] = fmaf(r.y * s.y, w, acc[i][NGL > 1 ? 1 : 0]);
-          acc[i][NGL > 2 ? 2 : 0] = fmaf(r.z * s.z, w, acc[i][NGL > 2 ? 2 : 0]);
-          acc[i][NGL > 3 ? 3 : 0] = fmaf(r.w * s.w, w, acc[i][NGL > 3 ? 3 : 0]);
+          acc[0][di] = fmaf(r.x * s.x, w, acc[0][di]);
+          acc[NGL > 1 ? 1 : 0][di] = fmaf(r.y * s.y, w, acc[NGL > 1 ? 1 : 0][di]);
+          acc[NGL > 2 ? 2 : 0][di] = fmaf(r.z * s.z, w, acc[NGL > 2 ? 2 : 0][di]);
+          acc[NGL > 3 ? 3 : 0][di] = fmaf(r.w * s.w, w, acc[NGL > 3 ? 3 : 0][di]);
         }
       }
+      __syncwarp();
     }
     const float den = __fadd_rn(wsum, 1e-6f);
-    if (active) {
+    if (LPG == 2) {
+      // the two lanes of a group exchange halves: even lane ends with hypotheses [0, DCH/2), odd lane with [DCH/2, DCH)
+      ReduceScatter<DCH, 2>::run(acc[0], lip & 1);
+      if (active) {
+        const int dbase = d0 + (lip & 1) * (DCH / 2);
 #pragma unroll
-      for (int i = 0; i < DC; ++i) {
-        if (d0 + i < D) {
-          float* o = volume + ((size_t)(d0 + i) * HW + p) * G;
-          if (CPG >= 4) {
-            if (lip % LPG == 0) o[lip / LPG] = __fdiv_rn(acc[i][0], den);
-          } else if (CPG == 2) {
-            float2 v2 = make_float2(__fdiv_rn(acc[i][0], den), __fdiv_rn(acc[i][NGL > 1 ? 1 : 0], den));
-            *reinterpret_cast<float2*>(o + lip * 2) = v2;
+        for (int i = 0; i < DCH / 2; ++i)
+          if (dbase + i < D) volume[((size_t)(dbase + i) * HW + p2) * G + (lip >> 1)] = __fdiv_rn(acc[0][i], den);
+      }
+    } else if (active) {
+#pragma unroll
+      for (int di = 0; di < DCH; ++di) {
+        if (d0 + di < D) {
+          float* o = volume + ((size_t)(d0 + di) * HW + p2) * G;
+          if (NGL == 1) {
+            o[lip] = __fdiv_rn(acc[0][di], den);
+          } else if (NGL == 2) {
+            *reinterpret_cast<float2*>(o + lip * 2) = make_float2(__fdiv_rn(acc[0][di], den), __fdiv_rn(acc[NGL > 1 ? 1 : 0][di], den));
           } else {
-            float4 v4 = make_float4(__fdiv_rn(acc[i][0], den), __fdiv_rn(acc[i][NGL > 1 ? 1 : 0], den),
-                                    __fdiv_rn(acc[i][NGL > 2 ? 2 : 0], den), __fdiv_rn(acc[i][NGL > 3 ? 3 : 0], den));
-            *reinterpret_cast<float4*>(o + lip * 4) = v4;
+            *reinterpret_cast<float4*>(o + lip * 4) =
+                make_float4(__fdiv_rn(acc[0][di], den), __fdiv_rn(acc[NGL > 1 ? 1 : 0][di], den),
+                            __fdiv_rn(acc[NGL > 2 ? 2 : 0][di], den), __fdiv_rn(acc[NGL > 3 ? 3 : 0][di], den));
           }
         }
       }
@@ -201,26 +295,21 @@ __global__ void homo_warp_kernel(const float* __restrict__ src, const float* __r
 template <int C>
 static int launch_entropy(const float* feat, const float* homs, const float* depth, float* entropy, int V, int G, int D,
                           int H, int W, cudaStream_t s) {
-  constexpr int LPP = C / 4;
-  long long threads = (long long)H * W * LPP;
-  dim3 grid(cdiv(threads, 256), V - 1);
-  switch (D) {
-    case 4: warp_corr_entropy_kernel<C, 4><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, G, D, H, W); break;
-    case 8: warp_corr_entropy_kernel<C, 8><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, G, D, H, W); break;
-    case 16: warp_corr_entropy_kernel<C, 16><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, G, D, H, W); break;
-    case 32: warp_corr_entropy_kernel<C, 32><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, G, D, H, W); break;
-    default: warp_corr_entropy_kernel<C, 0><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, G, D, H, W); break;
-  }
+  constexpr int P = WC<C>::P;
+  dim3 grid(cdiv((long long)H * W, 8 * P), V - 1);
+  if (D == WC<C>::DCH)
+    warp_corr_entropy_kernel<C, false><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, G, D, H, W);
+  else
+    warp_corr_entropy_kernel<C, true><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, G, D, H, W);
   return 0;
 }
 
 template <int C, int CPG>
 static int launch_aggregate(const float* feat, const float* homs, const float* depth, const float* vis, float* volume,
                             int V, int D, int H, int W, cudaStream_t s) {
-  constexpr int LPP = C / 4;
-  long long threads = (long long)H * W * LPP;
-  dim3 grid(cdiv(threads, 256));
-  warp_corr_aggregate_kernel<C, CPG, 4><<<grid, 256, 0, s>>>(feat, homs, depth, vis, volume, V, D, H, W);
+  constexpr int P = WC<C>::P;
+  dim3 grid(cdiv((long long)H * W, 8 * P));
+  warp_corr_aggregate_kernel<C, CPG><<<grid, 256, 0, s>>>(feat, homs, depth, vis, volume, V, D, H, W);
   return 0;
 }
 
