@@ -102,6 +102,12 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, f
 int mvsf_attention_forward(const float* qkv, float* out, void* workspace, size_t workspace_bytes, int N,
                            float softmax_scale, mvsf_stream_t stream);
 
+/* token-wise linear layer alone (nn.Linear, e.g. models/module.py:520-522 FFN.linear1): C[M,N] = act(A[M,K] W[N,K]^T + bias)
+ * on the tcgen05 tensor cores with fp16 hi/lo split operands (fp32-class accuracy).  N % 16 == 0, N <= 256, K % 64 == 0.
+ * workspace >= (M+N)*2K*2 + 256 bytes.  gelu != 0 applies the exact-erf GELU. */
+int mvsf_linear_tc_forward(const float* A, const float* W, const float* bias, float* C, void* workspace,
+                           size_t workspace_bytes, int M, int N, int K, int gelu, mvsf_stream_t stream);
+
 /* ---- S1: models/cost_volume.py:105-117 + models/module.py:649-655 (eval, depth_type 'ce').
  * logits [D][H][W], depth hypotheses [D][H][W] -> prob [D][H][W], depth [H][W], conf [H][W] */
 int mvsf_softargmax(const float* logits, const float* depth_hypo, float tmp, float* prob, float* depth, float* conf,

@@ -26,6 +26,7 @@ SIGNATURES = {
     "mvsf_costreg_tr_workspace_bytes": ([I, I, I, I, ctypes.POINTER(Z)], I),
     "mvsf_costreg_tr_forward": ([P, P, P, P, P, Z, I, I, I, I, I, F, P], I),
     "mvsf_attention_forward": ([P, P, P, Z, I, F, P], I),
+    "mvsf_linear_tc_forward": ([P, P, P, P, P, Z, I, I, I, I, P], I),
     "mvsf_softargmax": ([P, P, F, P, P, P, I, I, I, P], I),
     "mvsf_conf_accumulate": ([P, I, I, P, I, I, F, I, P], I),
     "mvsf_fmt_workspace_bytes": ([I, I, I, ctypes.POINTER(Z)], I),

@@ -7,14 +7,6 @@
 
 namespace mvsf {
 
-enum LinEpi {
-  LIN_BIAS = 0,    // C = acc + bias
-  LIN_GELU = 1,    // C = gelu(acc + bias)
-  LIN_ELU1 = 2,    // C = col < elu_cols ? elu(acc)+1 : acc            (attention.py:268-269)
-  LIN_RES = 3,     // C = res + gamma[col] * (acc + bias)               (block.py:344-345, pre-norm)
-  LIN_RES_LN = 4,  // C = LN(res + gamma[col] * (acc + bias))           (module.py:575-576, post-norm), N == 64
-  LIN_LN = 5       // C = LN(acc + bias)                                (module.py:615-618 down conv + LN3D), N == 64
-};
 
 struct LinArgs {
   const float* A; int lda;

@@ -1,0 +1,265 @@
+// Token-wise linear layers on the 5th-generation tensor cores:  C[M,N] = epi(A[M,K] * W[N,K]^T), fp32-class accuracy.
+//   * operands are split into fp16 hi + lo parts (hi+lo carries 22 mantissa bits); three tcgen05.mma.kind::f16 products
+//     per K-step (lo*hi, hi*lo, hi*hi) accumulate in fp32 in TMEM - a single-pass fp16/bf16/tf32 GEMM would move the
+//     depth probabilities by ~1e-3, the split stays at ~1e-6 relative;
+//   * CTA = 128 rows x all N columns (N <= 256): the accumulator is 128 TMEM lanes x N columns; K is streamed in blocks
+//     of 64 through a 2-stage cp.async ring into the canonical no-swizzle K-major layout (umma.cuh); one thread issues
+//     the MMAs, tcgen05.commit -> mbarrier releases a stage;
+//   * epilogue: each of the 128 threads owns one accumulator row (tcgen05.ld 32x32b), so bias / GELU / ELU+1 / residual /
+//     LayerNorm need no cross-thread traffic; optionally also emits the fp16 hi|lo split of the result for the next GEMM.
+// Used by the stage-1 transformer regulariser (module.py:507-646) and FMT (FMT.py, block.py:336-346).
+#include "linear_tc.cuh"
+
+#include "umma.cuh"
+
+namespace mvsf {
+
+using namespace umma;
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 2, TC_THREADS = 128;
+
+__global__ void split_f16_kernel(const float* __restrict__ x, int ldx, __half* __restrict__ out, int ldo, int M, int K) {
+  // out[m][k] = hi, out[m][K + k] = lo ; 4 elements per thread
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)M * (K / 4);
+  if (i >= total) return;
+  int m = (int)(i / (K / 4)), q = (int)(i % (K / 4));
+  float4 v = ldg4(x + (size_t)m * ldx + q * 4);
+  float f[4] = {v.x, v.y, v.z, v.w};
+  __half hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    hi[e] = __float2half_rn(f[e]);
+    lo[e] = __float2half_rn(f[e] - __half2float(hi[e]));
+  }
+  __half2* ph = reinterpret_cast<__half2*>(out + (size_t)m * ldo + q * 4);
+  __half2* pl = reinterpret_cast<__half2*>(out + (size_t)m * ldo + K + q * 4);
+  ph[0] = __halves2half2(hi[0], hi[1]); ph[1] = __halves2half2(hi[2], hi[3]);
+  pl[0] = __halves2half2(lo[0], lo[1]); pl[1] = __halves2half2(lo[2], lo[3]);
+}
+
+__device__ __forceinline__ void store_split16(__half* c2row, int N, int col, const float (&v)[16]) {
+  __align__(16) __half hi[16], lo[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    hi[e] = __float2half_rn(v[e]);
+    lo[e] = __float2half_rn(v[e] - __half2float(hi[e]));
+  }
+  uint4* dh = reinterpret_cast<uint4*>(c2row + col);
+  uint4* dl = reinterpret_cast<uint4*>(c2row + N + col);
+  dh[0] = reinterpret_cast<uint4*>(hi)[0]; dh[1] = reinterpret_cast<uint4*>(hi)[1];
+  dl[0] = reinterpret_cast<uint4*>(lo)[0]; dl[1] = reinterpret_cast<uint4*>(lo)[1];
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS)
+linear_tc_kernel(TcLinArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N, K = a.K;
+  const int m0 = blockIdx.x * TC_BM;
+  const int valid_rows = min(TC_BM, a.M - m0);
+  const uint32_t a_bytes = tile_bytes(TC_BM), b_bytes = tile_bytes(N);
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_base = sbase + TC_STAGES * stage_bytes;  // mbar_stage[0], mbar_stage[1], mbar_done (8 B each)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TC_STAGES * stage_bytes + 32);
+
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)N) ncols <<= 1;
+  if (tid == 0) {
+    mbar_init(bar_base + 0, 1);
+    mbar_init(bar_base + 8, 1);
+    mbar_init(bar_base + 16, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(sbase + TC_STAGES * stage_bytes + 32, ncols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nkb = K / TC_BK;
+  const __half* Ag = a.A2 + (size_t)m0 * a.lda2;
+  auto load_block = [&](int kb, int st) {
+    const uint32_t s0 = sbase + st * stage_bytes;
+    fill_tile<TC_THREADS>(s0, Ag + kb * TC_BK, a.lda2, TC_BM, valid_rows, tid);                       // A hi
+    fill_tile<TC_THREADS>(s0 + a_bytes, Ag + K + kb * TC_BK, a.lda2, TC_BM, valid_rows, tid);          // A lo
+    fill_tile<TC_THREADS>(s0 + 2 * a_bytes, a.B2 + kb * TC_BK, (size_t)2 * K, N, N, tid);              // B hi
+    fill_tile<TC_THREADS>(s0 + 2 * a_bytes + b_bytes, a.B2 + K + kb * TC_BK, (size_t)2 * K, N, N, tid);  // B lo
+    cp_async_commit_group();
+  };
+  const uint32_t idesc = make_idesc_f16(TC_BM, N);
+  const uint32_t lbo_a = tile_lbo(TC_BM), lbo_b = tile_lbo(N);
+
+  load_block(0, 0);
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int st = kb & 1;
+    if (kb + 1 < nkb) {
+      const int nst = (kb + 1) & 1;
+      if (kb >= 1) mbar_wait(bar_base + 8 * nst, (uint32_t)(((kb - 1) >> 1) & 1));  // MMAs of block kb-1 released stage nst
+      load_block(kb + 1, nst);
+      cp_async_wait_group<1>();
+    } else {
+      cp_async_wait_group<0>();
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+      const uint32_t s0 = sbase + st * stage_bytes;
+#pragma unroll
+      for (int i = 0; i < TC_BK / 16; ++i) {
+        const uint64_t ah = make_desc(s0 + 2 * i * lbo_a, lbo_a, 128);
+        const uint64_t al = make_desc(s0 + a_bytes + 2 * i * lbo_a, lbo_a, 128);
+        const uint64_t bh = make_desc(s0 + 2 * a_bytes + 2 * i * lbo_b, lbo_b, 128);
+        const uint64_t bl = make_desc(s0 + 2 * a_bytes + b_bytes + 2 * i * lbo_b, lbo_b, 128);
+        mma_f16_ss(tmem_base, al, bh, idesc, (kb > 0 || i > 0) ? 1u : 0u);
+        mma_f16_ss(tmem_base, ah, bl, idesc, 1u);
+        mma_f16_ss(tmem_base, ah, bh, idesc, 1u);
+      }
+      commit(bar_base + 8 * st);
+      if (kb == nkb - 1) commit(bar_base + 16);
+    }
+  }
+
+  // ---------------- epilogue: thread <-> accumulator row
+  mbar_wait(bar_base + 16, 0);
+  tc_fence_after_sync();
+  const int row = warp * 32 + lane;
+  const int m = m0 + row;
+  const bool mvalid = m < a.M;
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const float* resrow = (EPI == LIN_RES || EPI == LIN_RES_LN) ? a.res + (size_t)(mvalid ? m : 0) * a.ldres : nullptr;
+  float* crow = a.C ? a.C + (size_t)(mvalid ? m : 0) * a.ldc : nullptr;
+  __half* c2row = a.C2 ? a.C2 + (size_t)(mvalid ? m : 0) * a.ldc2 : nullptr;
+
+  if (EPI == LIN_RES_LN || EPI == LIN_LN) {  // N == 64: the whole row lives in this thread's registers
+    float x[64];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v[16];
+      tmem_ld16(trow + c * 16, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int col = c * 16 + e;
+        float t = v[e] + (a.bias ? __ldg(a.bias + col) : 0.f);
+        if (EPI == LIN_RES_LN) t = (mvalid ? resrow[col] : 0.f) + __ldg(a.gamma + col) * t;
+        x[col] = t;
+        s += t;
+      }
+    }
+    const float mean = s * (1.0f / 64.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int e = 0; e < 64; ++e) { float d = x[e] - mean; q = fmaf(d, d, q); }
+    const float sd = sqrtf(q * (1.0f / 64.0f) + a.ln_eps);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float o[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int col = c * 16 + e;
+        o[e] = __fdiv_rn(x[col] - mean, sd) * __ldg(a.ln_w + col) + __ldg(a.ln_b + col);
+      }
+      if (mvalid) {
+        if (crow) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            *reinterpret_cast<float4*>(crow + c * 16 + e * 4) = make_float4(o[e * 4], o[e * 4 + 1], o[e * 4 + 2], o[e * 4 + 3]);
+        }
+        if (c2row) store_split16(c2row, N, c * 16, o);
+      }
+    }
+  } else {
+    for (int c = 0; c < N / 16; ++c) {
+      float v[16];
+      tmem_ld16(trow + c * 16, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int col = c * 16 + e;
+        float t = v[e] + (a.bias ? __ldg(a.bias + col) : 0.f);
+        if (EPI == LIN_GELU) t = gelu_erf(t);
+        if (EPI == LIN_ELU1) t = (col < a.elu_cols) ? ((t > 0.f ? t : expm1f(t)) + 1.0f) : t;
+        if (EPI == LIN_RES) t = (mvalid ? resrow[col] : 0.f) + __ldg(a.gamma + col) * t;
+        v[e] = t;
+      }
+      if (mvalid) {
+        if (crow) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            *reinterpret_cast<float4*>(crow + c * 16 + e * 4) = make_float4(v[e * 4], v[e * 4 + 1], v[e * 4 + 2], v[e * 4 + 3]);
+        }
+        if (c2row) store_split16(c2row, N, c * 16, v);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+static size_t tc_smem_bytes(int N) { return (size_t)TC_STAGES * (2 * tile_bytes(TC_BM) + 2 * tile_bytes(N)) + 64; }
+
+int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
+  MVSF_REQUIRE(a.A2 && a.B2 && (a.C || a.C2) && a.M > 0, "linear_tc: bad arguments");
+  MVSF_REQUIRE(a.N % 16 == 0 && a.N >= 16 && a.N <= 256 && a.K % TC_BK == 0 && a.K >= TC_BK, "linear_tc: need N %% 16 == 0, 16 <= N <= 256, K %% 64 == 0");
+  MVSF_REQUIRE((a.lda2 % 8) == 0 && ((uintptr_t)a.A2 & 15) == 0 && ((uintptr_t)a.B2 & 15) == 0, "linear_tc: operands must be 16-byte aligned");
+  if (a.C) MVSF_REQUIRE((a.ldc % 4) == 0 && ((uintptr_t)a.C & 15) == 0, "linear_tc: C must be 16-byte aligned");
+  if (a.C2) MVSF_REQUIRE((a.ldc2 % 8) == 0 && ((uintptr_t)a.C2 & 15) == 0, "linear_tc: C2 must be 16-byte aligned");
+  if (epi == LIN_RES_LN || epi == LIN_LN) MVSF_REQUIRE(a.N == 64 && a.ln_w && a.ln_b, "linear_tc: LayerNorm epilogue needs N == 64");
+  if (epi == LIN_RES || epi == LIN_RES_LN) MVSF_REQUIRE(a.res && a.gamma, "linear_tc: residual epilogue needs res and gamma");
+  const size_t smem = tc_smem_bytes(a.N);
+  static bool configured = false;
+  if (!configured) {
+    const int maxs = (int)tc_smem_bytes(256);
+    MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_ELU1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_RES_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+    configured = true;
+  }
+  dim3 grid(cdiv(a.M, TC_BM));
+  switch (epi) {
+    case LIN_BIAS: linear_tc_kernel<LIN_BIAS><<<grid, TC_THREADS, smem, s>>>(a); break;
+    case LIN_GELU: linear_tc_kernel<LIN_GELU><<<grid, TC_THREADS, smem, s>>>(a); break;
+    case LIN_ELU1: linear_tc_kernel<LIN_ELU1><<<grid, TC_THREADS, smem, s>>>(a); break;
+    case LIN_RES: linear_tc_kernel<LIN_RES><<<grid, TC_THREADS, smem, s>>>(a); break;
+    case LIN_RES_LN: linear_tc_kernel<LIN_RES_LN><<<grid, TC_THREADS, smem, s>>>(a); break;
+    case LIN_LN: linear_tc_kernel<LIN_LN><<<grid, TC_THREADS, smem, s>>>(a); break;
+    default: return fail(MVSF_ERR_INVALID, "linear_tc: unknown epilogue %d", epi);
+  }
+  MVSF_LAUNCH_CHECK("linear_tc");
+  return MVSF_OK;
+}
+
+int launch_split_f16(const float* x, int ldx, __half* out, int ldo, int M, int K, cudaStream_t s) {
+  MVSF_REQUIRE(x && out && M > 0 && K % 4 == 0 && ldx % 4 == 0 && ldo % 2 == 0, "split_f16: bad arguments");
+  size_t total = (size_t)M * (K / 4);
+  split_f16_kernel<<<cdiv((long long)total, 256), 256, 0, s>>>(x, ldx, out, ldo, M, K);
+  MVSF_LAUNCH_CHECK("split_f16");
+  return MVSF_OK;
+}
+
+}  // namespace mvsf
+
+using namespace mvsf;
+
+extern "C" int mvsf_linear_tc_forward(const float* A, const float* W, const float* bias, float* C, void* workspace,
+                                      size_t workspace_bytes, int M, int N, int K, int gelu, mvsf_stream_t stream) {
+  MVSF_REQUIRE(A && W && C && workspace, "linear_tc_forward: null pointer");
+  const size_t need = ((size_t)M * 2 * K + (size_t)N * 2 * K) * sizeof(__half) + 256;
+  if (workspace_bytes < need) return fail(MVSF_ERR_WORKSPACE, "linear_tc_forward: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t s = (cudaStream_t)stream;
+  __half* A2 = reinterpret_cast<__half*>(workspace);
+  __half* B2 = A2 + align_up((size_t)M * 2 * K, 64);
+  int rc;
+  if ((rc = launch_split_f16(A, K, A2, 2 * K, M, K, s))) return rc;
+  if ((rc = launch_split_f16(W, K, B2, 2 * K, N, K, s))) return rc;
+  TcLinArgs a{};
+  a.A2 = A2; a.lda2 = 2 * K; a.B2 = B2; a.M = M; a.N = N; a.K = K; a.bias = bias; a.C = C; a.ldc = N;
+  return launch_linear_tc(a, gelu ? LIN_GELU : LIN_BIAS, s);
+}

@@ -1,0 +1,114 @@
+// tcgen05 (5th-gen tensor core) building blocks for sm_100a, hand-written PTX.
+//   - shared-memory operand descriptors for the canonical K-major, no-swizzle ("interleaved") layout:
+//       element (row m, k) of a tile lives at  base + (k/8)*LBO + (m/8)*SBO + (m%8)*16 + (k%8)*2   [fp16]
+//     i.e. 8x8 "core matrices" of 128 contiguous bytes (conflict-free for the tensor core's reads);
+//   - tcgen05.mma.cta_group::1.kind::f16 (fp16 x fp16 -> fp32 accumulators in TMEM), issued by one thread;
+//   - tcgen05.commit -> mbarrier, bounded mbarrier waits (trap instead of hanging the GPU);
+//   - TMEM alloc/dealloc and tcgen05.ld (32 lanes x 32 bit, one accumulator row per thread).
+// Field layouts follow the PTX ISA / CUTLASS cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace mvsf {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy shared-memory writes (st.shared / cp.async) -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a mis-programmed pipeline traps (sticky CUDA error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 24); ++it)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);              // start address            bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;    // leading byte offset       bits [16,30)  (between the 2 k-chunks)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;    // stride byte offset        bits [32,46)  (between 8-row groups)
+  d |= (uint64_t)1 << 46;                              // descriptor version 1 (Blackwell)
+  return d;                                            // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+// kind::f16 instruction descriptor: fp16 A/B (format 0), fp32 accumulate (c_format 1), both K-major, dense
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (count 1) on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// one full warp; writes the TMEM base address (lane 0, column c) to *dst_smem
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane (lane = 32*(warp%4) + laneid)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_addr, const void* gptr, bool valid) {
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// bytes of one K-block tile (64 fp16 = 8 chunks of 16 B per row) of `rows` rows in the padded canonical layout
+__host__ __device__ constexpr uint32_t tile_lbo(int rows) { return (uint32_t)(rows / 8) * 128u + 16u; }  // +16: bank-conflict-free fills
+__host__ __device__ constexpr uint32_t tile_bytes(int rows) { return 8u * tile_lbo(rows); }
+// cooperative fill of one tile from a row-major fp16 matrix: g points at (row 0, k 0) of the tile, ld in elements
+template <int NTHREADS>
+__device__ __forceinline__ void fill_tile(uint32_t tile_smem, const __half* g, size_t ld, int rows, int valid_rows, int tid) {
+  const uint32_t lbo = tile_lbo(rows);
+  for (int idx = tid; idx < rows * 8; idx += NTHREADS) {
+    int r = idx >> 3, c = idx & 7;
+    bool ok = r < valid_rows;
+    const __half* src = g + (size_t)(ok ? r : 0) * ld + c * 8;
+    cp_async16_zfill(tile_smem + c * lbo + (r >> 3) * 128 + (r & 7) * 16, src, ok);
+  }
+}
+
+}  // namespace umma
+}  // namespace mvsf
