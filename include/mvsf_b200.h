@@ -90,11 +90,14 @@ int mvsf_costreg_unet_forward(int kind, const float* volume, const float* wts, f
 
 /* ---- R1: models/module.py:602-646 PureTransformerCostReg (+ position_encoding.py:164-189 PositionEncoding3D).
  * volume [D][H][W][C] is modified in place by the PE add; pos [3][D][H][W] or NULL.
- * Fixed by the shipped config: down_rate (2,4,4), mid 64, heads 4, mlp 256.  softmax_scale = hd^-0.5*log_tal(N). */
+ * Fixed by the shipped config: down_rate (2,4,4), mid 64, heads 4, mlp 256.  softmax_scale = hd^-0.5*log_tal(N).
+ * wts16 = mvsf_split_weights_f16(wts) (fp16 hi|lo parts for the tcgen05 GEMMs), n_wts = number of floats in wts. */
 int mvsf_costreg_tr_workspace_bytes(int C, int D, int H, int W, size_t* bytes);
-int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, float* logits, void* workspace,
-                            size_t workspace_bytes, int C, int D, int H, int W, int layers, float softmax_scale,
-                            mvsf_stream_t stream);
+int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, const void* wts16, size_t n_wts,
+                            float* logits, void* workspace, size_t workspace_bytes, int C, int D, int H, int W,
+                            int layers, float softmax_scale, mvsf_stream_t stream);
+/* install-time helper: fp32 weight blob (n floats, n % 8 == 0) -> out16 = [n fp16 hi parts | n fp16 lo parts] (4n bytes) */
+int mvsf_split_weights_f16(const float* wts, void* out16, size_t n, mvsf_stream_t stream);
 
 /* softmax attention of R1 alone: models/dino/layers/attention.py:141-170 (FlashAttention2.forward after the qkv linear).
  * qkv [N][3][4][16] fp32 -> out [N][64]; workspace >= N*768 bytes.  Tensor cores (mma.sync), 3-term split-fp16 operands,
@@ -122,8 +125,8 @@ int mvsf_conf_accumulate(const float* conf, int h, int w, float* acc, int H, int
  * Outputs are channels-last: o1 [V][H1][W1][64] ... o4 [V][8H1][8W1][8].  wts: packing.pack_fmt. */
 int mvsf_fmt_workspace_bytes(int V, int H1, int W1, size_t* bytes);
 int mvsf_fmt_forward(const float* f1, const float* f2, const float* f3, const float* f4, const float* pe,
-                     const float* wts, float* o1, float* o2, float* o3, float* o4, void* workspace,
-                     size_t workspace_bytes, int V, int H1, int W1, mvsf_stream_t stream);
+                     const float* wts, const void* wts16, size_t n_wts, float* o1, float* o2, float* o3, float* o4,
+                     void* workspace, size_t workspace_bytes, int V, int H1, int W1, mvsf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -24,13 +24,14 @@ SIGNATURES = {
     "mvsf_costreg_unet_workspace_bytes": ([I, I, I, I, I, ctypes.POINTER(Z)], I),
     "mvsf_costreg_unet_forward": ([I, P, P, P, P, Z, I, I, I, I, P], I),
     "mvsf_costreg_tr_workspace_bytes": ([I, I, I, I, ctypes.POINTER(Z)], I),
-    "mvsf_costreg_tr_forward": ([P, P, P, P, P, Z, I, I, I, I, I, F, P], I),
+    "mvsf_costreg_tr_forward": ([P, P, P, P, Z, P, P, Z, I, I, I, I, I, F, P], I),
+    "mvsf_split_weights_f16": ([P, P, Z, P], I),
     "mvsf_attention_forward": ([P, P, P, Z, I, F, P], I),
     "mvsf_linear_tc_forward": ([P, P, P, P, P, Z, I, I, I, I, P], I),
     "mvsf_softargmax": ([P, P, F, P, P, P, I, I, I, P], I),
     "mvsf_conf_accumulate": ([P, I, I, P, I, I, F, I, P], I),
     "mvsf_fmt_workspace_bytes": ([I, I, I, ctypes.POINTER(Z)], I),
-    "mvsf_fmt_forward": ([P] * 11 + [Z, I, I, I, P], I),
+    "mvsf_fmt_forward": ([P] * 7 + [Z] + [P] * 5 + [Z, I, I, I, P], I),
 }
 
 

@@ -11,6 +11,7 @@
 #include <float.h>
 
 #include "linear.cuh"
+#include "linear_tc.cuh"
 
 namespace mvsf {
 
@@ -61,19 +62,22 @@ __global__ void pe3d_add_kernel(float* __restrict__ vol, const float* __restrict
   v[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
-// im2col for the (2,4,4)/(2,4,4) patchify conv: patches[t][((kd*4+kh)*4+kw)*8 + ci]
-__global__ void patch_gather_kernel(const float* __restrict__ vol, float* __restrict__ patches, int D, int H, int W) {
+// im2col for the (2,4,4)/(2,4,4) patchify conv, emitted as the fp16 hi|lo split the tensor-core GEMM consumes:
+// patches2[t] = [hi(256) | lo(256)], k = ((kd*4+kh)*4+kw)*8 + ci
+__global__ void patch_gather_kernel(const float* __restrict__ vol, __half* __restrict__ patches2, int D, int H, int W) {
   const int Hp = H / 4, Wp = W / 4;
-  size_t total = (size_t)(D / 2) * Hp * Wp * 32 * 2;  // float4 elements: token x 32 voxels x 2 halves
+  size_t total = (size_t)(D / 2) * Hp * Wp * 32;  // one thread per (token, voxel): 8 channels
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int half = (int)(i & 1);
-  int vox = (int)((i >> 1) & 31);
-  size_t t = i >> 6;
+  int vox = (int)(i & 31);
+  size_t t = i >> 5;
   int wp = (int)(t % Wp), hp = (int)((t / Wp) % Hp), dp = (int)(t / ((size_t)Wp * Hp));
   int kw = vox & 3, kh = (vox >> 2) & 3, kd = vox >> 4;
-  size_t src = (((size_t)(dp * 2 + kd) * H + hp * 4 + kh) * W + wp * 4 + kw) * 8 + half * 4;
-  reinterpret_cast<float4*>(patches)[i] = ldg4(vol + src);
+  const float* src = vol + (((size_t)(dp * 2 + kd) * H + hp * 4 + kh) * W + wp * 4 + kw) * 8;
+  float4 a = ldg4(src), b = ldg4(src + 4);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  __half* row = patches2 + t * 512 + vox * 8;
+  split_store8(row, row + 256, v);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -154,7 +158,7 @@ constexpr int FA_ARR_BYTES = FA_BN * 32, FA_STAGE_BYTES = 4 * FA_ARR_BYTES;
 __device__ __forceinline__ int fa_off(int r, int c) { return r * 32 + ((c ^ ((r >> 2) & 1)) << 4); }
 
 __global__ void __launch_bounds__(256)
-attention_mma_kernel(const __half* __restrict__ split, float* __restrict__ out, int N) {
+attention_mma_kernel(const __half* __restrict__ split, float* __restrict__ out, __half* __restrict__ out2, int N) {
   __shared__ __align__(128) unsigned char smem[FA_STAGES * FA_STAGE_BYTES];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -315,8 +319,24 @@ attention_mma_kernel(const __half* __restrict__ split, float* __restrict__ out, 
   const int r0 = q0 + g, r1 = q0 + g + 8;
 #pragma unroll
   for (int nd = 0; nd < 2; ++nd) {
-    if (r0 < N) *reinterpret_cast<float2*>(out + (size_t)r0 * 64 + h * 16 + nd * 8 + 2 * t) = make_float2(o[nd][0] * i0, o[nd][1] * i0);
-    if (r1 < N) *reinterpret_cast<float2*>(out + (size_t)r1 * 64 + h * 16 + nd * 8 + 2 * t) = make_float2(o[nd][2] * i1, o[nd][3] * i1);
+    const int col = h * 16 + nd * 8 + 2 * t;
+    const float a0 = o[nd][0] * i0, a1 = o[nd][1] * i0, b0 = o[nd][2] * i1, b1 = o[nd][3] * i1;
+    if (out) {
+      if (r0 < N) *reinterpret_cast<float2*>(out + (size_t)r0 * 64 + col) = make_float2(a0, a1);
+      if (r1 < N) *reinterpret_cast<float2*>(out + (size_t)r1 * 64 + col) = make_float2(b0, b1);
+    }
+    if (out2) {  // fp16 hi|lo split rows [hi(64) | lo(64)] for the projection GEMM
+      const __half2 ah = __floats2half2_rn(a0, a1), bh = __floats2half2_rn(b0, b1);
+      const float2 af = __half22float2(ah), bf = __half22float2(bh);
+      if (r0 < N) {
+        *reinterpret_cast<__half2*>(out2 + (size_t)r0 * 128 + col) = ah;
+        *reinterpret_cast<__half2*>(out2 + (size_t)r0 * 128 + 64 + col) = __floats2half2_rn(a0 - af.x, a1 - af.y);
+      }
+      if (r1 < N) {
+        *reinterpret_cast<__half2*>(out2 + (size_t)r1 * 128 + col) = bh;
+        *reinterpret_cast<__half2*>(out2 + (size_t)r1 * 128 + 64 + col) = __floats2half2_rn(b0 - bf.x, b1 - bf.y);
+      }
+    }
   }
 }
 
@@ -354,10 +374,10 @@ __global__ void unpatch_ln_prob_kernel(const float* __restrict__ u, const float*
 }
 
 
-static int run_attention(const float* qkv, float* o, __half* split, int N, float scale_log2e, cudaStream_t s) {
+static int run_attention(const float* qkv, float* o, __half* o2, __half* split, int N, float scale_log2e, cudaStream_t s) {
   qkv_split_kernel<<<cdiv((long long)N * 48, 256), 256, 0, s>>>(qkv, split, N, scale_log2e);
   MVSF_LAUNCH_CHECK("qkv_split");
-  attention_mma_kernel<<<dim3(cdiv(N, FA_BM), 4), 256, 0, s>>>(split, o, N);
+  attention_mma_kernel<<<dim3(cdiv(N, FA_BM), 4), 256, 0, s>>>(split, o, o2, N);
   MVSF_LAUNCH_CHECK("attention_mma");
   return MVSF_OK;
 }
@@ -373,67 +393,82 @@ int mvsf_costreg_tr_workspace_bytes(int C, int D, int H, int W, size_t* bytes) {
   MVSF_REQUIRE(D % 2 == 0 && H % 4 == 0 && W % 4 == 0 && D > 0 && H > 0 && W > 0,
                "costreg_tr: D %% 2, H %% 4, W %% 4 must be 0 (down_rate (2,4,4))");
   size_t N = (size_t)(D / 2) * (H / 4) * (W / 4);
-  // patches/u/h [N][256], x [N][64], y [N][64], o [N][64], qkv [N][192], split fp16 [6][4][N][16] (= 192 floats / token)
-  *bytes = N * (256 + 64 + 64 + 64 + 192 + 192) * sizeof(float);
+  // per token (in floats): big 256 (patches2 / ffn hidden split / un-patchify out), x 64, y 64, x2 64, y2 64, o2 64,
+  // qkv 192, attention operand split 192
+  *bytes = N * (256 + 64 + 64 + 64 + 64 + 64 + 192 + 192) * sizeof(float);
   return MVSF_OK;
 }
 
-int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, float* logits, void* workspace,
-                            size_t workspace_bytes, int C, int D, int H, int W, int layers, float softmax_scale,
-                            mvsf_stream_t stream) {
-  MVSF_REQUIRE(volume && wts && logits && workspace && layers >= 0, "costreg_tr: bad arguments");
+int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, const void* wts16, size_t n_wts,
+                            float* logits, void* workspace, size_t workspace_bytes, int C, int D, int H, int W,
+                            int layers, float softmax_scale, mvsf_stream_t stream) {
+  MVSF_REQUIRE(volume && wts && wts16 && logits && workspace && layers >= 0, "costreg_tr: bad arguments");
   size_t need = 0;
   int rc = mvsf_costreg_tr_workspace_bytes(C, D, H, W, &need);
   if (rc) return rc;
   if (workspace_bytes < need) return fail(MVSF_ERR_WORKSPACE, "costreg_tr: workspace %zu < %zu bytes", workspace_bytes, need);
-  MVSF_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)wts & 15) == 0 && ((uintptr_t)volume & 15) == 0,
+  MVSF_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)wts & 15) == 0 && ((uintptr_t)volume & 15) == 0 &&
+                   ((uintptr_t)wts16 & 15) == 0 && (n_wts % 8) == 0,
                "costreg_tr: pointers must be 16-byte aligned");
+  MVSF_REQUIRE(n_wts >= (size_t)TR_LAYER0 + (size_t)layers * TR_LAYER + U_PB + 1, "costreg_tr: weight blob too small");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t nvox = (size_t)D * H * W;
   const int N = (int)((size_t)(D / 2) * (H / 4) * (W / 4));
-  float* big = (float*)workspace;          // [N][256]: patches, then FFN hidden, then un-patchify output
-  float* x = big + (size_t)N * 256;        // [N][64]
-  float* y = x + (size_t)N * 64;           // [N][64]
-  float* o = y + (size_t)N * 64;           // [N][64]
-  float* qkv = o + (size_t)N * 64;         // [N][192]
+  const __half* wh = reinterpret_cast<const __half*>(wts16);  // fp16 hi parts, same indexing as wts
+  const __half* wl = wh + n_wts;                              // fp16 lo parts
+  float* big = (float*)workspace;                             // [N][256] floats
+  __half* big2 = reinterpret_cast<__half*>(big);             // [N][512] halves: row = [hi(256) | lo(256)]
+  float* x = big + (size_t)N * 256;                           // [N][64]
+  float* y = x + (size_t)N * 64;                              // [N][64]
+  __half* x2 = reinterpret_cast<__half*>(y + (size_t)N * 64);    // [N][128] = [hi(64) | lo(64)]
+  __half* y2 = x2 + (size_t)N * 128;
+  __half* o2 = y2 + (size_t)N * 128;
+  float* qkv = reinterpret_cast<float*>(o2 + (size_t)N * 128);   // [N][192]
   __half* split = reinterpret_cast<__half*>(qkv + (size_t)N * 192);  // [6][4][N][16] fp16
 
   if (pos) {
     pe3d_add_kernel<<<cdiv((long long)nvox, 256), 256, 0, s>>>(volume, pos, wts + TR_PE, nvox);
     MVSF_LAUNCH_CHECK("pe3d_add");
   }
-  patch_gather_kernel<<<cdiv((long long)N * 64, 256), 256, 0, s>>>(volume, big, D, H, W);
+  patch_gather_kernel<<<cdiv((long long)N * 32, 256), 256, 0, s>>>(volume, big2, D, H, W);
   MVSF_LAUNCH_CHECK("patch_gather");
 
-  LinArgs a{};
-  a.A = big; a.lda = 256; a.W = wts + TR_DOWN_W; a.bias = wts + TR_DOWN_B; a.C = x; a.ldc = 64;
-  a.M = N; a.N = 64; a.K = 256; a.ln_w = wts + TR_DOWN_LNW; a.ln_b = wts + TR_DOWN_LNB; a.ln_eps = 1e-6f;
-  if ((rc = launch_linear(a, LIN_LN, s))) return rc;
+  TcLinArgs a{};
+  a.Ah = big2; a.Al = big2 + 256; a.lda = 512; a.Bh = wh + TR_DOWN_W; a.Bl = wl + TR_DOWN_W; a.ldb = 256;
+  a.M = N; a.N = 64; a.K = 256; a.bias = wts + TR_DOWN_B; a.ln_w = wts + TR_DOWN_LNW; a.ln_b = wts + TR_DOWN_LNB; a.ln_eps = 1e-6f;
+  a.C = x; a.ldc = 64; a.C2 = x2; a.ldc2 = 128;
+  if ((rc = launch_linear_tc(a, LIN_LN, s))) return rc;
 
   const float scale_log2e = softmax_scale * 1.4426950408889634f;
   for (int l = 0; l < layers; ++l) {
-    const float* lw = wts + TR_LAYER0 + (size_t)l * TR_LAYER;
-    LinArgs q{};
-    q.A = x; q.lda = 64; q.W = lw + L_QKV; q.bias = nullptr; q.C = qkv; q.ldc = 192; q.M = N; q.N = 192; q.K = 64;
-    if ((rc = launch_linear(q, LIN_BIAS, s))) return rc;
-    if ((rc = run_attention(qkv, o, split, N, scale_log2e, s))) return rc;
-    LinArgs p{};
-    p.A = o; p.lda = 64; p.W = lw + L_PROJ_W; p.bias = lw + L_PROJ_B; p.C = y; p.ldc = 64; p.M = N; p.N = 64; p.K = 64;
-    p.res = x; p.ldres = 64; p.gamma = lw + L_G1; p.ln_w = lw + L_N1W; p.ln_b = lw + L_N1B; p.ln_eps = 1e-5f;
-    if ((rc = launch_linear(p, LIN_RES_LN, s))) return rc;
-    LinArgs f1{};
-    f1.A = y; f1.lda = 64; f1.W = lw + L_F1W; f1.bias = lw + L_F1B; f1.C = big; f1.ldc = 256; f1.M = N; f1.N = 256; f1.K = 64;
-    if ((rc = launch_linear(f1, LIN_GELU, s))) return rc;
-    LinArgs f2{};
-    f2.A = big; f2.lda = 256; f2.W = lw + L_F2W; f2.bias = lw + L_F2B; f2.C = x; f2.ldc = 64; f2.M = N; f2.N = 64; f2.K = 256;
-    f2.res = y; f2.ldres = 64; f2.gamma = lw + L_G2; f2.ln_w = lw + L_N2W; f2.ln_b = lw + L_N2B; f2.ln_eps = 1e-5f;
-    if ((rc = launch_linear(f2, LIN_RES_LN, s))) return rc;
+    const size_t lo = (size_t)TR_LAYER0 + (size_t)l * TR_LAYER;
+    const float* lw = wts + lo;
+    TcLinArgs q{};
+    q.Ah = x2; q.Al = x2 + 64; q.lda = 128; q.Bh = wh + lo + L_QKV; q.Bl = wl + lo + L_QKV; q.ldb = 64;
+    q.M = N; q.N = 192; q.K = 64; q.C = qkv; q.ldc = 192;
+    if ((rc = launch_linear_tc(q, LIN_BIAS, s))) return rc;
+    if ((rc = run_attention(qkv, nullptr, o2, split, N, scale_log2e, s))) return rc;
+    TcLinArgs p{};
+    p.Ah = o2; p.Al = o2 + 64; p.lda = 128; p.Bh = wh + lo + L_PROJ_W; p.Bl = wl + lo + L_PROJ_W; p.ldb = 64;
+    p.M = N; p.N = 64; p.K = 64; p.bias = lw + L_PROJ_B; p.res = x; p.ldres = 64; p.gamma = lw + L_G1;
+    p.ln_w = lw + L_N1W; p.ln_b = lw + L_N1B; p.ln_eps = 1e-5f; p.C = y; p.ldc = 64; p.C2 = y2; p.ldc2 = 128;
+    if ((rc = launch_linear_tc(p, LIN_RES_LN, s))) return rc;
+    TcLinArgs f1{};
+    f1.Ah = y2; f1.Al = y2 + 64; f1.lda = 128; f1.Bh = wh + lo + L_F1W; f1.Bl = wl + lo + L_F1W; f1.ldb = 64;
+    f1.M = N; f1.N = 256; f1.K = 64; f1.bias = lw + L_F1B; f1.C2 = big2; f1.ldc2 = 512;
+    if ((rc = launch_linear_tc(f1, LIN_GELU, s))) return rc;
+    TcLinArgs f2{};
+    f2.Ah = big2; f2.Al = big2 + 256; f2.lda = 512; f2.Bh = wh + lo + L_F2W; f2.Bl = wl + lo + L_F2W; f2.ldb = 256;
+    f2.M = N; f2.N = 64; f2.K = 256; f2.bias = lw + L_F2B; f2.res = y; f2.ldres = 64; f2.gamma = lw + L_G2;
+    f2.ln_w = lw + L_N2W; f2.ln_b = lw + L_N2B; f2.ln_eps = 1e-5f; f2.C = x; f2.ldc = 64; f2.C2 = x2; f2.ldc2 = 128;
+    if ((rc = launch_linear_tc(f2, LIN_RES_LN, s))) return rc;
   }
-  const float* uw = wts + TR_LAYER0 + (size_t)layers * TR_LAYER;
-  LinArgs u{};
-  u.A = x; u.lda = 64; u.W = uw + U_W; u.bias = uw + U_B; u.C = big; u.ldc = 256; u.M = N; u.N = 256; u.K = 64;
-  if ((rc = launch_linear(u, LIN_BIAS, s))) return rc;
-  unpatch_ln_prob_kernel<<<cdiv((long long)nvox, 256), 256, 0, s>>>(big, uw + U_LNW, logits, D, H, W);
+  const size_t uo = (size_t)TR_LAYER0 + (size_t)layers * TR_LAYER;
+  TcLinArgs u{};
+  u.Ah = x2; u.Al = x2 + 64; u.lda = 128; u.Bh = wh + uo + U_W; u.Bl = wl + uo + U_W; u.ldb = 64;
+  u.M = N; u.N = 256; u.K = 64; u.bias = wts + uo + U_B; u.C = big; u.ldc = 256;
+  if ((rc = launch_linear_tc(u, LIN_BIAS, s))) return rc;
+  unpatch_ln_prob_kernel<<<cdiv((long long)nvox, 256), 256, 0, s>>>(big, wts + uo + U_LNW, logits, D, H, W);
   MVSF_LAUNCH_CHECK("unpatch_ln_prob");
   return MVSF_OK;
 }
@@ -443,6 +478,6 @@ int mvsf_attention_forward(const float* qkv, float* out, void* workspace, size_t
                            float softmax_scale, mvsf_stream_t stream) {
   MVSF_REQUIRE(qkv && out && workspace && N > 0, "attention_forward: bad arguments");
   if (workspace_bytes < (size_t)N * 768) return fail(MVSF_ERR_WORKSPACE, "attention_forward: workspace %zu < %zu bytes", workspace_bytes, (size_t)N * 768);
-  return run_attention(qkv, out, reinterpret_cast<__half*>(workspace), N, softmax_scale * 1.4426950408889634f, (cudaStream_t)stream);
+  return run_attention(qkv, out, nullptr, reinterpret_cast<__half*>(workspace), N, softmax_scale * 1.4426950408889634f, (cudaStream_t)stream);
 }
 }

@@ -6,6 +6,7 @@
 // the [V][H][W][64] layout the warp kernels consume.  All source views are processed as one batch; the K/V
 // summaries of the two cross layers depend only on the reference view and are computed once.
 #include "linear.cuh"
+#include "linear_tc.cuh"
 
 namespace mvsf {
 
@@ -84,10 +85,34 @@ __global__ void kv_final_kernel(const float* __restrict__ partial, int nblk, flo
   fin[(size_t)view * KVSZ + i] = s;
 }
 
+// Row LayerNorm over 64 channels emitting the fp16 hi|lo split [hi(64) | lo(64)] the tensor-core GEMMs consume
+__global__ void __launch_bounds__(256)
+layernorm64_split_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                         __half* __restrict__ y2, int M, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float2 v = ldg2(x + (size_t)row * 64 + lane * 2);
+  float s = v.x + v.y;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / 64.0f);
+  float d0 = v.x - mean, d1 = v.y - mean;
+  float q = d0 * d0 + d1 * d1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float sd = sqrtf(q * (1.0f / 64.0f) + eps);
+  float2 ww = ldg2(w + lane * 2), bb = ldg2(b + lane * 2);
+  const float o0 = __fdiv_rn(d0, sd) * ww.x + bb.x, o1 = __fdiv_rn(d1, sd) * ww.y + bb.y;
+  const __half2 hh = __floats2half2_rn(o0, o1);
+  const float2 hf = __half22float2(hh);
+  *reinterpret_cast<__half2*>(y2 + (size_t)row * 128 + lane * 2) = hh;
+  *reinterpret_cast<__half2*>(y2 + (size_t)row * 128 + 64 + lane * 2) = __floats2half2_rn(o0 - hf.x, o1 - hf.y);
+}
+
 // out[s][h*16+m] = (sum_d q[s,h,d] KV[h][m][d]) / (q[s,h,:] . ksum[h,:] + 1e-6)     (attention.py:281-284)
 __global__ void __launch_bounds__(128)
 linattn_apply_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kvfin, size_t kv_view_stride,
-                     float* __restrict__ out, int L, int M) {
+                     __half* __restrict__ out2, int L, int M) {
   __shared__ __align__(16) float kvs[256 + 16];
   const int h = blockIdx.y;
   const int s = blockIdx.x * 128 + threadIdx.x;
@@ -108,7 +133,7 @@ linattn_apply_kernel(const float* __restrict__ q, int ldq, const float* __restri
 #pragma unroll
   for (int d = 0; d < 16; ++d) den = fmaf(qv[d], kvs[256 + d], den);
   const float z = __fdiv_rn(1.0f, den + 1e-6f);
-  float* op = out + (size_t)s * 64 + h * 16;
+  __half* op = out2 + (size_t)s * 128 + h * 16;  // fp16 hi|lo split rows [hi(64) | lo(64)]
 #pragma unroll
   for (int mq = 0; mq < 4; ++mq) {
     float r[4];
@@ -123,7 +148,12 @@ linattn_apply_kernel(const float* __restrict__ q, int ldq, const float* __restri
       t = fmaf(qv[12], e.x, t); t = fmaf(qv[13], e.y, t); t = fmaf(qv[14], e.z, t); t = fmaf(qv[15], e.w, t);
       r[mm] = t * z;
     }
-    *reinterpret_cast<float4*>(op + mq * 4) = make_float4(r[0], r[1], r[2], r[3]);
+    const __half2 h01 = __floats2half2_rn(r[0], r[1]), h23 = __floats2half2_rn(r[2], r[3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    *reinterpret_cast<__half2*>(op + mq * 4) = h01;
+    *reinterpret_cast<__half2*>(op + mq * 4 + 2) = h23;
+    *reinterpret_cast<__half2*>(op + 64 + mq * 4) = __floats2half2_rn(r[0] - f01.x, r[1] - f01.y);
+    *reinterpret_cast<__half2*>(op + 64 + mq * 4 + 2) = __floats2half2_rn(r[2] - f23.x, r[3] - f23.y);
   }
 }
 
@@ -242,23 +272,28 @@ conv2d_k3_kernel(const float* __restrict__ in, const float* __restrict__ wts, fl
 }
 
 struct FmtWs {
-  float *xn, *qkv, *att, *hid, *ref0, *kvpart, *kvfin, *kvc;
+  __half *xn2, *att2, *hid2;   // fp16 hi|lo split activations: [M][128], [M][128], [M][512]
+  float *qkv, *ref0, *kvpart, *kvfin, *kvc;
+  const __half *wh, *wl;       // fp16 hi / lo parts of the packed weight blob (same indexing as the fp32 blob)
 };
 
 // one CrossBlock over `M` tokens (nviews views of L tokens each) stored at x (in place).
 // self attention: kv_src == nullptr ; cross attention: kvc = precomputed K/V summary of the reference view.
-static int run_block(float* x, int nviews, int L, const float* bw, const float* kvc, const FmtWs& ws, cudaStream_t s) {
+static int run_block(float* x, int nviews, int L, const float* bw, size_t boff, const float* kvc, const FmtWs& ws,
+                     cudaStream_t s) {
   const int M = nviews * L;
   int rc;
-  layernorm64_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, bw + B_N1W, bw + B_N1B, ws.xn, M, 1e-5f);
+  layernorm64_split_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, bw + B_N1W, bw + B_N1B, ws.xn2, M, 1e-5f);
   MVSF_LAUNCH_CHECK("fmt_ln1");
   const float* kvsum;
   size_t kv_stride;
   int ldq;
+  TcLinArgs a{};
+  a.Ah = ws.xn2; a.Al = ws.xn2 + 64; a.lda = 128; a.Bh = ws.wh + boff + B_QKV; a.Bl = ws.wl + boff + B_QKV; a.ldb = 64;
+  a.M = M; a.K = 64; a.C = ws.qkv;
   if (!kvc) {
-    LinArgs a{};
-    a.A = ws.xn; a.lda = 64; a.W = bw + B_QKV; a.C = ws.qkv; a.ldc = 192; a.M = M; a.N = 192; a.K = 64; a.elu_cols = 128;
-    if ((rc = launch_linear(a, LIN_ELU1, s))) return rc;
+    a.N = 192; a.ldc = 192; a.elu_cols = 128;
+    if ((rc = launch_linear_tc(a, LIN_ELU1, s))) return rc;
     const int nblk = cdiv(L, KV_CHUNK);
     kv_partial_kernel<<<dim3(nblk, nviews), 256, 0, s>>>(ws.qkv, 192, 64, 128, L, ws.kvpart);
     MVSF_LAUNCH_CHECK("fmt_kv_partial");
@@ -266,46 +301,49 @@ static int run_block(float* x, int nviews, int L, const float* bw, const float* 
     MVSF_LAUNCH_CHECK("fmt_kv_final");
     kvsum = ws.kvfin; kv_stride = KVSZ; ldq = 192;
   } else {
-    LinArgs a{};
-    a.A = ws.xn; a.lda = 64; a.W = bw + B_QKV; a.C = ws.qkv; a.ldc = 64; a.M = M; a.N = 64; a.K = 64; a.elu_cols = 64;
-    if ((rc = launch_linear(a, LIN_ELU1, s))) return rc;
+    a.N = 64; a.ldc = 64; a.elu_cols = 64;
+    if ((rc = launch_linear_tc(a, LIN_ELU1, s))) return rc;
     kvsum = kvc; kv_stride = 0; ldq = 64;
   }
   if (L % 128 == 0 || nviews == 1) {
-    linattn_apply_kernel<<<dim3(cdiv(M, 128), 4), 128, 0, s>>>(ws.qkv, ldq, kvsum, kv_stride, ws.att, L, M);
+    linattn_apply_kernel<<<dim3(cdiv(M, 128), 4), 128, 0, s>>>(ws.qkv, ldq, kvsum, kv_stride, ws.att2, L, M);
     MVSF_LAUNCH_CHECK("fmt_linattn_apply");
   } else {
     for (int v = 0; v < nviews; ++v) {  // views do not align with 128-token blocks: one launch per view
       linattn_apply_kernel<<<dim3(cdiv(L, 128), 4), 128, 0, s>>>(ws.qkv + (size_t)v * L * ldq, ldq,
                                                                  kvsum + (size_t)v * kv_stride, 0,
-                                                                 ws.att + (size_t)v * L * 64, L, L);
+                                                                 ws.att2 + (size_t)v * L * 128, L, L);
       MVSF_LAUNCH_CHECK("fmt_linattn_apply");
     }
   }
-  LinArgs p{};
-  p.A = ws.att; p.lda = 64; p.W = bw + B_PW; p.bias = bw + B_PB; p.C = x; p.ldc = 64; p.M = M; p.N = 64; p.K = 64;
-  p.res = x; p.ldres = 64; p.gamma = bw + B_G1;
-  if ((rc = launch_linear(p, LIN_RES, s))) return rc;
-  layernorm64_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, bw + B_N2W, bw + B_N2B, ws.xn, M, 1e-5f);
+  TcLinArgs p{};
+  p.Ah = ws.att2; p.Al = ws.att2 + 64; p.lda = 128; p.Bh = ws.wh + boff + B_PW; p.Bl = ws.wl + boff + B_PW; p.ldb = 64;
+  p.M = M; p.N = 64; p.K = 64; p.bias = bw + B_PB; p.res = x; p.ldres = 64; p.gamma = bw + B_G1; p.C = x; p.ldc = 64;
+  if ((rc = launch_linear_tc(p, LIN_RES, s))) return rc;
+  layernorm64_split_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, bw + B_N2W, bw + B_N2B, ws.xn2, M, 1e-5f);
   MVSF_LAUNCH_CHECK("fmt_ln2");
-  LinArgs f1{};
-  f1.A = ws.xn; f1.lda = 64; f1.W = bw + B_F1W; f1.bias = bw + B_F1B; f1.C = ws.hid; f1.ldc = 256; f1.M = M; f1.N = 256; f1.K = 64;
-  if ((rc = launch_linear(f1, LIN_GELU, s))) return rc;
-  LinArgs f2{};
-  f2.A = ws.hid; f2.lda = 256; f2.W = bw + B_F2W; f2.bias = bw + B_F2B; f2.C = x; f2.ldc = 64; f2.M = M; f2.N = 64; f2.K = 256;
-  f2.res = x; f2.ldres = 64; f2.gamma = bw + B_G2;
-  if ((rc = launch_linear(f2, LIN_RES, s))) return rc;
+  TcLinArgs f1{};
+  f1.Ah = ws.xn2; f1.Al = ws.xn2 + 64; f1.lda = 128; f1.Bh = ws.wh + boff + B_F1W; f1.Bl = ws.wl + boff + B_F1W; f1.ldb = 64;
+  f1.M = M; f1.N = 256; f1.K = 64; f1.bias = bw + B_F1B; f1.C2 = ws.hid2; f1.ldc2 = 512;
+  if ((rc = launch_linear_tc(f1, LIN_GELU, s))) return rc;
+  TcLinArgs f2{};
+  f2.Ah = ws.hid2; f2.Al = ws.hid2 + 256; f2.lda = 512; f2.Bh = ws.wh + boff + B_F2W; f2.Bl = ws.wl + boff + B_F2W; f2.ldb = 256;
+  f2.M = M; f2.N = 64; f2.K = 256; f2.bias = bw + B_F2B; f2.res = x; f2.ldres = 64; f2.gamma = bw + B_G2; f2.C = x; f2.ldc = 64;
+  if ((rc = launch_linear_tc(f2, LIN_RES, s))) return rc;
   return MVSF_OK;
 }
 
 // K/V summary of a cross layer: key = value = norm1_layer(ref_feature)   (block.py:341-343, FMT.py:121-125)
-static int run_cross_kv(const float* ref_tok, int L, const float* bw, float* kvc_out, const FmtWs& ws, cudaStream_t s) {
+static int run_cross_kv(const float* ref_tok, int L, const float* bw, size_t boff, float* kvc_out, const FmtWs& ws,
+                        cudaStream_t s) {
   int rc;
-  layernorm64_kernel<<<cdiv(L, 8), 256, 0, s>>>(ref_tok, bw + B_N1W, bw + B_N1B, ws.xn, L, 1e-5f);
+  layernorm64_split_kernel<<<cdiv(L, 8), 256, 0, s>>>(ref_tok, bw + B_N1W, bw + B_N1B, ws.xn2, L, 1e-5f);
   MVSF_LAUNCH_CHECK("fmt_ln_key");
-  LinArgs a{};
-  a.A = ws.xn; a.lda = 64; a.W = bw + B_QKV + 64 * 64; a.C = ws.qkv; a.ldc = 128; a.M = L; a.N = 128; a.K = 64; a.elu_cols = 64;
-  if ((rc = launch_linear(a, LIN_ELU1, s))) return rc;
+  TcLinArgs a{};
+  a.Ah = ws.xn2; a.Al = ws.xn2 + 64; a.lda = 128;
+  a.Bh = ws.wh + boff + B_QKV + 64 * 64; a.Bl = ws.wl + boff + B_QKV + 64 * 64; a.ldb = 64;
+  a.M = L; a.N = 128; a.K = 64; a.C = ws.qkv; a.ldc = 128; a.elu_cols = 64;
+  if ((rc = launch_linear_tc(a, LIN_ELU1, s))) return rc;
   const int nblk = cdiv(L, KV_CHUNK);
   kv_partial_kernel<<<dim3(nblk, 1), 256, 0, s>>>(ws.qkv, 128, 0, 64, L, ws.kvpart);
   MVSF_LAUNCH_CHECK("fmt_kv_partial");
@@ -346,9 +384,10 @@ int mvsf_fmt_workspace_bytes(int V, int H1, int W1, size_t* bytes) {
 }
 
 int mvsf_fmt_forward(const float* f1, const float* f2, const float* f3, const float* f4, const float* pe,
-                     const float* wts, float* o1, float* o2, float* o3, float* o4, void* workspace,
-                     size_t workspace_bytes, int V, int H1, int W1, mvsf_stream_t stream) {
-  MVSF_REQUIRE(f1 && f2 && f3 && f4 && pe && wts && o1 && o2 && o3 && o4 && workspace, "fmt: null pointer");
+                     const float* wts, const void* wts16, size_t n_wts, float* o1, float* o2, float* o3, float* o4,
+                     void* workspace, size_t workspace_bytes, int V, int H1, int W1, mvsf_stream_t stream) {
+  MVSF_REQUIRE(f1 && f2 && f3 && f4 && pe && wts && wts16 && o1 && o2 && o3 && o4 && workspace, "fmt: null pointer");
+  MVSF_REQUIRE(n_wts >= (size_t)FMT_WTS && (n_wts % 8) == 0 && ((uintptr_t)wts16 & 15) == 0, "fmt: bad fp16 weight blob");
   size_t need = 0;
   int rc = mvsf_fmt_workspace_bytes(V, H1, W1, &need);
   if (rc) return rc;
@@ -359,10 +398,12 @@ int mvsf_fmt_forward(const float* f1, const float* f2, const float* f3, const fl
   const size_t VL = (size_t)V * L;
   float* base = (float*)workspace;
   FmtWs ws;
-  ws.xn = base;                       // [V*L][64]
-  ws.qkv = ws.xn + 64 * VL;           // [V*L][192]
-  ws.att = ws.qkv + 192 * VL;         // [V*L][64]
-  ws.hid = ws.att + 64 * VL;          // [V*L][256]   (xn..hid = 576 VL; the pathway reuses 640 VL from base)
+  ws.xn2 = reinterpret_cast<__half*>(base);                  // [V*L][128] halves (= 64 floats / token)
+  ws.qkv = base + 64 * VL;                                   // [V*L][192]
+  ws.att2 = reinterpret_cast<__half*>(ws.qkv + 192 * VL);    // [V*L][128] halves
+  ws.hid2 = ws.att2 + 128 * VL;                              // [V*L][512] halves  (576 VL floats in total; the pathway reuses 640 VL)
+  ws.wh = reinterpret_cast<const __half*>(wts16);
+  ws.wl = ws.wh + n_wts;
   ws.ref0 = base + 640 * VL;          // [L][64]
   const size_t nblk = (L + KV_CHUNK - 1) / KV_CHUNK;
   ws.kvpart = ws.ref0 + 64 * (size_t)L;
@@ -375,17 +416,17 @@ int mvsf_fmt_forward(const float* f1, const float* f2, const float* f3, const fl
 
   const float* b0 = wts; const float* b1 = wts + B_SIZE; const float* b2 = wts + 2 * B_SIZE; const float* b3 = wts + 3 * B_SIZE;
   // reference view: the two self layers (FMT.py:96-107); keep the output of the first one for cross layer 1
-  if ((rc = run_block(o1, 1, L, b0, nullptr, ws, s))) return rc;
+  if ((rc = run_block(o1, 1, L, b0, 0, nullptr, ws, s))) return rc;
   MVSF_CUDA_OK(cudaMemcpyAsync(ws.ref0, o1, (size_t)L * 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  if ((rc = run_block(o1, 1, L, b2, nullptr, ws, s))) return rc;
-  if ((rc = run_cross_kv(ws.ref0, L, b1, ws.kvc, ws, s))) return rc;
-  if ((rc = run_cross_kv(o1, L, b3, ws.kvc + KVSZ, ws, s))) return rc;
+  if ((rc = run_block(o1, 1, L, b2, 2 * (size_t)B_SIZE, nullptr, ws, s))) return rc;
+  if ((rc = run_cross_kv(ws.ref0, L, b1, (size_t)B_SIZE, ws.kvc, ws, s))) return rc;
+  if ((rc = run_cross_kv(o1, L, b3, 3 * (size_t)B_SIZE, ws.kvc + KVSZ, ws, s))) return rc;
   // source views as one batch: self, cross(ref_list[0]), self, cross(ref_list[1])   (FMT.py:119-135)
   float* xs = o1 + (size_t)L * 64;
-  if ((rc = run_block(xs, V - 1, L, b0, nullptr, ws, s))) return rc;
-  if ((rc = run_block(xs, V - 1, L, b1, ws.kvc, ws, s))) return rc;
-  if ((rc = run_block(xs, V - 1, L, b2, nullptr, ws, s))) return rc;
-  if ((rc = run_block(xs, V - 1, L, b3, ws.kvc + KVSZ, ws, s))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b0, 0, nullptr, ws, s))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b1, (size_t)B_SIZE, ws.kvc, ws, s))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b2, 2 * (size_t)B_SIZE, nullptr, ws, s))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b3, 3 * (size_t)B_SIZE, ws.kvc + KVSZ, ws, s))) return rc;
 
   // top-down pathway (FMT.py:195-197), all views batched
   float* red = base;                  // <= 128 VL floats

@@ -80,13 +80,14 @@ linear_tc_kernel(TcLinArgs a) {
   const uint32_t tmem_base = *tmem_slot;
 
   const int nkb = K / TC_BK;
-  const __half* Ag = a.A2 + (size_t)m0 * a.lda2;
+  const __half* Agh = a.Ah + (size_t)m0 * a.lda;
+  const __half* Agl = a.Al + (size_t)m0 * a.lda;
   auto load_block = [&](int kb, int st) {
     const uint32_t s0 = sbase + st * stage_bytes;
-    fill_tile<TC_THREADS>(s0, Ag + kb * TC_BK, a.lda2, TC_BM, valid_rows, tid);                       // A hi
-    fill_tile<TC_THREADS>(s0 + a_bytes, Ag + K + kb * TC_BK, a.lda2, TC_BM, valid_rows, tid);          // A lo
-    fill_tile<TC_THREADS>(s0 + 2 * a_bytes, a.B2 + kb * TC_BK, (size_t)2 * K, N, N, tid);              // B hi
-    fill_tile<TC_THREADS>(s0 + 2 * a_bytes + b_bytes, a.B2 + K + kb * TC_BK, (size_t)2 * K, N, N, tid);  // B lo
+    fill_tile<TC_THREADS>(s0, Agh + kb * TC_BK, a.lda, TC_BM, valid_rows, tid);                          // A hi
+    fill_tile<TC_THREADS>(s0 + a_bytes, Agl + kb * TC_BK, a.lda, TC_BM, valid_rows, tid);                // A lo
+    fill_tile<TC_THREADS>(s0 + 2 * a_bytes, a.Bh + kb * TC_BK, a.ldb, N, N, tid);                        // B hi
+    fill_tile<TC_THREADS>(s0 + 2 * a_bytes + b_bytes, a.Bl + kb * TC_BK, a.ldb, N, N, tid);              // B lo
     cp_async_commit_group();
   };
   const uint32_t idesc = make_idesc_f16(TC_BM, N);
@@ -203,9 +204,10 @@ linear_tc_kernel(TcLinArgs a) {
 static size_t tc_smem_bytes(int N) { return (size_t)TC_STAGES * (2 * tile_bytes(TC_BM) + 2 * tile_bytes(N)) + 64; }
 
 int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
-  MVSF_REQUIRE(a.A2 && a.B2 && (a.C || a.C2) && a.M > 0, "linear_tc: bad arguments");
+  MVSF_REQUIRE(a.Ah && a.Al && a.Bh && a.Bl && (a.C || a.C2) && a.M > 0, "linear_tc: bad arguments");
   MVSF_REQUIRE(a.N % 16 == 0 && a.N >= 16 && a.N <= 256 && a.K % TC_BK == 0 && a.K >= TC_BK, "linear_tc: need N %% 16 == 0, 16 <= N <= 256, K %% 64 == 0");
-  MVSF_REQUIRE((a.lda2 % 8) == 0 && ((uintptr_t)a.A2 & 15) == 0 && ((uintptr_t)a.B2 & 15) == 0, "linear_tc: operands must be 16-byte aligned");
+  MVSF_REQUIRE((a.lda % 8) == 0 && (a.ldb % 8) == 0 && ((uintptr_t)a.Ah & 15) == 0 && ((uintptr_t)a.Al & 15) == 0 &&
+                   ((uintptr_t)a.Bh & 15) == 0 && ((uintptr_t)a.Bl & 15) == 0, "linear_tc: operands must be 16-byte aligned");
   if (a.C) MVSF_REQUIRE((a.ldc % 4) == 0 && ((uintptr_t)a.C & 15) == 0, "linear_tc: C must be 16-byte aligned");
   if (a.C2) MVSF_REQUIRE((a.ldc2 % 8) == 0 && ((uintptr_t)a.C2 & 15) == 0, "linear_tc: C2 must be 16-byte aligned");
   if (epi == LIN_RES_LN || epi == LIN_LN) MVSF_REQUIRE(a.N == 64 && a.ln_w && a.ln_b, "linear_tc: LayerNorm epilogue needs N == 64");
@@ -236,6 +238,21 @@ int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
   return MVSF_OK;
 }
 
+__global__ void split_blob_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = x[i];
+  __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+int launch_split_blob_f16(const float* x, __half* hi, __half* lo, size_t n, cudaStream_t s) {
+  MVSF_REQUIRE(x && hi && lo && n > 0, "split_blob_f16: bad arguments");
+  split_blob_f16_kernel<<<cdiv((long long)n, 256), 256, 0, s>>>(x, hi, lo, n);
+  MVSF_LAUNCH_CHECK("split_blob_f16");
+  return MVSF_OK;
+}
+
 int launch_split_f16(const float* x, int ldx, __half* out, int ldo, int M, int K, cudaStream_t s) {
   MVSF_REQUIRE(x && out && M > 0 && K % 4 == 0 && ldx % 4 == 0 && ldo % 2 == 0, "split_f16: bad arguments");
   size_t total = (size_t)M * (K / 4);
@@ -260,6 +277,14 @@ extern "C" int mvsf_linear_tc_forward(const float* A, const float* W, const floa
   if ((rc = launch_split_f16(A, K, A2, 2 * K, M, K, s))) return rc;
   if ((rc = launch_split_f16(W, K, B2, 2 * K, N, K, s))) return rc;
   TcLinArgs a{};
-  a.A2 = A2; a.lda2 = 2 * K; a.B2 = B2; a.M = M; a.N = N; a.K = K; a.bias = bias; a.C = C; a.ldc = N;
+  a.Ah = A2; a.Al = A2 + K; a.lda = 2 * K; a.Bh = B2; a.Bl = B2 + K; a.ldb = 2 * K;
+  a.M = M; a.N = N; a.K = K; a.bias = bias; a.C = C; a.ldc = N;
   return launch_linear_tc(a, gelu ? LIN_GELU : LIN_BIAS, s);
+}
+
+/* fp32 weight blob -> fp16 hi / lo blobs with identical indexing (install time): out16 = [hi(n) | lo(n)] */
+extern "C" int mvsf_split_weights_f16(const float* wts, void* out16, size_t n, mvsf_stream_t stream) {
+  MVSF_REQUIRE(wts && out16 && n > 0 && (n % 8) == 0, "split_weights_f16: n must be a multiple of 8");
+  __half* hi = reinterpret_cast<__half*>(out16);
+  return launch_split_blob_f16(wts, hi, hi + n, n, (cudaStream_t)stream);
 }

@@ -7,8 +7,8 @@
 namespace mvsf {
 
 struct TcLinArgs {
-  const __half* A2; int lda2;   // activations, fp16 hi|lo split: row m = [hi(0..K) | lo(0..K)], lda2 >= 2K (elements)
-  const __half* B2;             // weights [N][2K] fp16 hi|lo split (nn.Linear weight [N][K])
+  const __half* Ah; const __half* Al; int lda;  // activations [M][K] as fp16 hi and lo parts (x ~= hi + lo), row stride lda
+  const __half* Bh; const __half* Bl; int ldb;  // weights [N][K] (nn.Linear layout) as fp16 hi and lo parts, row stride ldb
   int M, N, K;
   const float* bias;            // [N] or nullptr
   const float* res; int ldres;  // residual (LIN_RES / LIN_RES_LN)
@@ -20,6 +20,19 @@ struct TcLinArgs {
 };
 
 int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s);
+// out row m = [hi(0..K) | lo(0..K)] (ldo >= 2K)
 int launch_split_f16(const float* x, int ldx, __half* out, int ldo, int M, int K, cudaStream_t s);
+// element-wise split of a flat fp32 blob into two fp16 blobs with the same indexing (weights, done once at install time)
+int launch_split_blob_f16(const float* x, __half* hi, __half* lo, size_t n, cudaStream_t s);
+__device__ __forceinline__ void split_store8(__half* hi_dst, __half* lo_dst, const float (&v)[8]) {
+  __align__(16) __half h[8], l[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    h[e] = __float2half_rn(v[e]);
+    l[e] = __float2half_rn(v[e] - __half2float(h[e]));
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = *reinterpret_cast<uint4*>(h);
+  *reinterpret_cast<uint4*>(lo_dst) = *reinterpret_cast<uint4*>(l);
+}
 
 }  // namespace mvsf

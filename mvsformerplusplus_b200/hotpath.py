@@ -61,6 +61,16 @@ def to_nchw(x_nhwc):
     return out
 
 
+def split_weights_f16(flat):
+    """fp32 weight blob on the device -> fp16 [hi | lo] blob for the tcgen05 GEMMs (install time, once)."""
+    L = _lib.lib()
+    n = flat.numel()
+    assert n % 8 == 0
+    out = torch.empty(2 * n, device=flat.device, dtype=torch.float16)
+    _lib.check(L.mvsf_split_weights_f16(_ptr(flat), _ptr(out), ctypes.c_size_t(n), _stream()), "split_weights_f16")
+    return out
+
+
 class _PackedMixin:
     """Packs the module's parameters for the CUDA library on first use / after load_state_dict."""
 
@@ -110,6 +120,7 @@ class StageNet(_PackedMixin, nn.Module):
             pk["kind"] = "tr"
             pk["layers"] = tc["layer_num"]
             pk["reg"] = packing.pack_costreg_tr(sd, "cost_reg.", tc["layer_num"]).to(device)
+            pk["reg16"] = split_weights_f16(pk["reg"])
         else:
             kind, flat = packing.pack_costreg_unet(sd, "cost_reg.")
             pk["kind"] = kind
@@ -153,7 +164,8 @@ class StageNet(_PackedMixin, nn.Module):
             _lib.check(L.mvsf_costreg_tr_workspace_bytes(G, D, H, W, ctypes.byref(need)), "costreg_tr_workspace_bytes")
             ws = torch.empty(need.value // 4 + 4, **f32)
             n_tok = (D // 2) * (H // 4) * (W // 4)
-            _lib.check(L.mvsf_costreg_tr_forward(_ptr(volume), _ptr(position3d), _ptr(pk["reg"]), _ptr(logits),
+            _lib.check(L.mvsf_costreg_tr_forward(_ptr(volume), _ptr(position3d), _ptr(pk["reg"]), _ptr(pk["reg16"]),
+                                                 ctypes.c_size_t(pk["reg"].numel()), _ptr(logits),
                                                  _ptr(ws), ctypes.c_size_t(ws.numel() * 4), G, D, H, W, pk["layers"],
                                                  float(self._softmax_scale(n_tok)), st), "costreg_tr_forward")
         else:
@@ -225,7 +237,8 @@ class FMT_with_pathway(_PackedMixin, nn.Module):
     def _pack(self, device):
         if self._packed is None or self._packed["device"] != device:
             sd = {"FMT_module." + k: v for k, v in self.state_dict().items()}
-            self._packed = {"device": device, "w": packing.pack_fmt(sd).to(device)}
+            w = packing.pack_fmt(sd).to(device)
+            self._packed = {"device": device, "w": w, "w16": split_weights_f16(w)}
         return self._packed
 
     def _pe(self, H, W, device):
@@ -266,6 +279,7 @@ class FMT_with_pathway(_PackedMixin, nn.Module):
                     raise AssertionError(f"stage{k + 1} features must be [V,{c},{H1 * sc},{W1 * sc}], got {tuple(ins[k].shape)}")
             o = [torch.empty((V, H1 * sc, W1 * sc, c), **f32) for c, sc in ((64, 1), (32, 2), (16, 4), (8, 8))]
             _lib.check(L.mvsf_fmt_forward(_ptr(ins[0]), _ptr(ins[1]), _ptr(ins[2]), _ptr(ins[3]), _ptr(pe), _ptr(pk["w"]),
+                                          _ptr(pk["w16"]), ctypes.c_size_t(pk["w"].numel()),
                                           _ptr(o[0]), _ptr(o[1]), _ptr(o[2]), _ptr(o[3]), _ptr(ws),
                                           ctypes.c_size_t(ws.numel() * 4), V, H1, W1, _stream()), "fmt_forward")
             for k in range(4):

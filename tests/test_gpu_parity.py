@@ -266,8 +266,11 @@ def test_costreg_transformer(dev, L, D, H, W):
     n_tok = (D // 2) * (H // 4) * (W // 4)
     scale = 16 ** -0.5 * math.log(n_tok, cfg["train_avg_length"])
     pos_d = pos[0].contiguous().to(dev)
-    ck(L.mvsf_costreg_tr_forward(P(v), P(pos_d), P(flat), P(logits), P(ws), ctypes.c_size_t(ws.numel() * 4),
-                                 8, D, H, W, cfg["layer_num"], float(scale), S()), "costreg_tr_forward")
+    from mvsformerplusplus_b200.hotpath import split_weights_f16
+    flat16 = split_weights_f16(flat)
+    ck(L.mvsf_costreg_tr_forward(P(v), P(pos_d), P(flat), P(flat16), ctypes.c_size_t(flat.numel()), P(logits), P(ws),
+                                 ctypes.c_size_t(ws.numel() * 4), 8, D, H, W, cfg["layer_num"], float(scale), S()),
+       "costreg_tr_forward")
     e = max_abs(logits.cpu(), want)
     rec(f"costreg_tr_{D}x{H}x{W}", abs=e, scale=float(want.abs().max()), tokens=n_tok)
     assert e < 2e-4 * max(1.0, float(want.abs().max()))
