@@ -84,7 +84,7 @@ def pack_costreg_tr(sd, p, layers):
     parts += [wu.permute(2, 3, 4, 1, 0).reshape(256, 64), _d(sd[p + "up.0.bias"]).repeat(32),
               _d(sd[p + "up.1.weight"]), _d(sd[p + "up.1.bias"]),
               _d(sd[p + "prob.weight"]).reshape(8), _d(sd[p + "prob.bias"]).reshape(1)]
-    return _cat(parts)
+    return _cat(parts, pad_to=8)  # multiple of 8 floats: the fp16 hi/lo copies stay 16-byte aligned
 
 
 def pack_fmt(sd, p="FMT_module."):
@@ -105,4 +105,4 @@ def pack_fmt(sd, p="FMT_module."):
     for k in (1, 2, 3):
         w = _d(sd[f"{p}smooth_{k}.weight"])  # [co, ci, 3, 3] -> [tap][ci][co]
         parts.append(w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]))
-    return _cat(parts)
+    return _cat(parts, pad_to=8)

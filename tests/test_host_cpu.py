@@ -84,7 +84,7 @@ def test_packing_layout_sizes_and_bn_folding():
     k0, f0 = packing.pack_costreg_unet(sd, "fusions.1.cost_reg.")
     k1, f1 = packing.pack_costreg_unet(sd, "fusions.3.cost_reg.")
     assert (k0, k1) == (0, 1) and f0.numel() == 290800 and f1.numel() == 290596
-    assert packing.pack_costreg_tr(sd, "fusions.0.cost_reg.", 6).numel() == 332956
+    assert packing.pack_costreg_tr(sd, "fusions.0.cost_reg.", 6).numel() == 332960
     assert packing.pack_fmt(sd).numel() == 214464
     # folded conv+bias reproduces conv -> BatchNorm(eval)
     x = torch.randn(1, 1, 9, 9)
