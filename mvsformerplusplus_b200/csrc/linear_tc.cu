@@ -2,9 +2,10 @@
 //   * operands are split into fp16 hi + lo parts (hi+lo carries 22 mantissa bits); three tcgen05.mma.kind::f16 products
 //     per K-step (lo*hi, hi*lo, hi*hi) accumulate in fp32 in TMEM - a single-pass fp16/bf16/tf32 GEMM would move the
 //     depth probabilities by ~1e-3, the split stays at ~1e-6 relative;
-//   * CTA = 128 rows x all N columns (N <= 256): the accumulator is 128 TMEM lanes x N columns; K is streamed in blocks
-//     of 64 through a 2-stage cp.async ring into the canonical no-swizzle K-major layout (umma.cuh); one thread issues
-//     the MMAs, tcgen05.commit -> mbarrier releases a stage;
+//   * tile = 128 rows x all N columns (N <= 256): the accumulator is 128 TMEM lanes x N columns; persistent CTAs (one per
+//     SM) keep the weights resident in shared memory and stream A in K-blocks of 64 through a 3-stage cp.async ring in the
+//     canonical no-swizzle K-major layout (umma.cuh); one thread issues the MMAs, tcgen05.commit -> mbarrier releases a
+//     stage; accumulators are double-buffered in TMEM so epilogue and MMA overlap;
 //   * epilogue: each of the 128 threads owns one accumulator row (tcgen05.ld 32x32b), so bias / GELU / ELU+1 / residual /
 //     LayerNorm need no cross-thread traffic; optionally also emits the fp16 hi|lo split of the result for the next GEMM.
 // Used by the stage-1 transformer regulariser (module.py:507-646) and FMT (FMT.py, block.py:336-346).
@@ -16,7 +17,7 @@ namespace mvsf {
 
 using namespace umma;
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_STAGES = 2, TC_THREADS = 128;
+constexpr int TC_BM = 128, TC_BK = 64;
 
 __global__ void split_f16_kernel(const float* __restrict__ x, int ldx, __half* __restrict__ out, int ldo, int M, int K) {
   // out[m][k] = hi, out[m][K + k] = lo ; 4 elements per thread
@@ -51,90 +52,24 @@ __device__ __forceinline__ void store_split16(__half* c2row, int N, int col, con
   dl[0] = reinterpret_cast<uint4*>(lo)[0]; dl[1] = reinterpret_cast<uint4*>(lo)[1];
 }
 
+// Persistent, warp-specialised kernel.  256 threads:
+//   warps 0-3  producers: cp.async-fill the A ring (one K-block of 128 rows, hi+lo, per stage); thread 0 issues the MMAs
+//   warps 4-7  epilogue : TMEM -> registers -> global, one accumulator row per thread
+// The weight tiles of all K-blocks stay resident in shared memory for the CTA's lifetime; accumulators are double
+// buffered in TMEM (2 x N columns) so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+// mbarriers: empty[s] (MMAs that read stage s finished -> refill), acc_full[b] / acc_empty[b] (accumulator hand-over).
+constexpr int TC_NPROD = 128, TC_NEPI = 128;
+
 template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS)
-linear_tc_kernel(TcLinArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = a.N, K = a.K;
-  const int m0 = blockIdx.x * TC_BM;
-  const int valid_rows = min(TC_BM, a.M - m0);
-  const uint32_t a_bytes = tile_bytes(TC_BM), b_bytes = tile_bytes(N);
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_base = sbase + TC_STAGES * stage_bytes;  // mbar_stage[0], mbar_stage[1], mbar_done (8 B each)
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TC_STAGES * stage_bytes + 32);
-
-  uint32_t ncols = 32;
-  while (ncols < (uint32_t)N) ncols <<= 1;
-  if (tid == 0) {
-    mbar_init(bar_base + 0, 1);
-    mbar_init(bar_base + 8, 1);
-    mbar_init(bar_base + 16, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(sbase + TC_STAGES * stage_bytes + 32, ncols);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int nkb = K / TC_BK;
-  const __half* Agh = a.Ah + (size_t)m0 * a.lda;
-  const __half* Agl = a.Al + (size_t)m0 * a.lda;
-  auto load_block = [&](int kb, int st) {
-    const uint32_t s0 = sbase + st * stage_bytes;
-    fill_tile<TC_THREADS>(s0, Agh + kb * TC_BK, a.lda, TC_BM, valid_rows, tid);                          // A hi
-    fill_tile<TC_THREADS>(s0 + a_bytes, Agl + kb * TC_BK, a.lda, TC_BM, valid_rows, tid);                // A lo
-    fill_tile<TC_THREADS>(s0 + 2 * a_bytes, a.Bh + kb * TC_BK, a.ldb, N, N, tid);                        // B hi
-    fill_tile<TC_THREADS>(s0 + 2 * a_bytes + b_bytes, a.Bl + kb * TC_BK, a.ldb, N, N, tid);              // B lo
-    cp_async_commit_group();
-  };
-  const uint32_t idesc = make_idesc_f16(TC_BM, N);
-  const uint32_t lbo_a = tile_lbo(TC_BM), lbo_b = tile_lbo(N);
-
-  load_block(0, 0);
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int st = kb & 1;
-    if (kb + 1 < nkb) {
-      const int nst = (kb + 1) & 1;
-      if (kb >= 1) mbar_wait(bar_base + 8 * nst, (uint32_t)(((kb - 1) >> 1) & 1));  // MMAs of block kb-1 released stage nst
-      load_block(kb + 1, nst);
-      cp_async_wait_group<1>();
-    } else {
-      cp_async_wait_group<0>();
-    }
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after_sync();
-      const uint32_t s0 = sbase + st * stage_bytes;
-#pragma unroll
-      for (int i = 0; i < TC_BK / 16; ++i) {
-        const uint64_t ah = make_desc(s0 + 2 * i * lbo_a, lbo_a, 128);
-        const uint64_t al = make_desc(s0 + a_bytes + 2 * i * lbo_a, lbo_a, 128);
-        const uint64_t bh = make_desc(s0 + 2 * a_bytes + 2 * i * lbo_b, lbo_b, 128);
-        const uint64_t bl = make_desc(s0 + 2 * a_bytes + b_bytes + 2 * i * lbo_b, lbo_b, 128);
-        mma_f16_ss(tmem_base, al, bh, idesc, (kb > 0 || i > 0) ? 1u : 0u);
-        mma_f16_ss(tmem_base, ah, bl, idesc, 1u);
-        mma_f16_ss(tmem_base, ah, bh, idesc, 1u);
-      }
-      commit(bar_base + 8 * st);
-      if (kb == nkb - 1) commit(bar_base + 16);
-    }
-  }
-
-  // ---------------- epilogue: thread <-> accumulator row
-  mbar_wait(bar_base + 16, 0);
-  tc_fence_after_sync();
-  const int row = warp * 32 + lane;
+__device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t tacc, int m0, int warp4, int lane) {
+  const int N = a.N;
+  const int row = warp4 * 32 + lane;
   const int m = m0 + row;
   const bool mvalid = m < a.M;
-  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t trow = tacc + ((uint32_t)(warp4 * 32) << 16);
   const float* resrow = (EPI == LIN_RES || EPI == LIN_RES_LN) ? a.res + (size_t)(mvalid ? m : 0) * a.ldres : nullptr;
   float* crow = a.C ? a.C + (size_t)(mvalid ? m : 0) * a.ldc : nullptr;
   __half* c2row = a.C2 ? a.C2 + (size_t)(mvalid ? m : 0) * a.ldc2 : nullptr;
-
   if (EPI == LIN_RES_LN || EPI == LIN_LN) {  // N == 64: the whole row lives in this thread's registers
     float x[64];
     float s = 0.f;
@@ -196,12 +131,125 @@ linear_tc_kernel(TcLinArgs a) {
       }
     }
   }
+}
+
+constexpr int TC_RING = 3;
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_NPROD + TC_NEPI, 1)
+linear_tc_kernel(TcLinArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N, K = a.K;
+  const int nkb = K / TC_BK;
+  const uint32_t a_bytes = tile_bytes(TC_BM), b_bytes = tile_bytes(N);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t sB = sbase;                                   // [nkb][hi tile | lo tile]
+  const uint32_t sA = sB + nkb * 2 * b_bytes;                  // ring [TC_RING][hi tile | lo tile]
+  const uint32_t bars = sA + TC_RING * 2 * a_bytes;            // empty[3] | acc_full[2] | acc_empty[2]  (8 B each)
+  const uint32_t bar_empty = bars, bar_accf = bars + 8 * TC_RING, bar_acce = bar_accf + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (sA - sbase) + TC_RING * 2 * a_bytes + 64);
+
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)(2 * N)) ncols <<= 1;
+  if (tid == 0) {
+    for (int i = 0; i < TC_RING; ++i) mbar_init(bar_empty + 8 * i, 1);
+    mbar_init(bar_accf + 0, 1); mbar_init(bar_accf + 8, 1);
+    mbar_init(bar_acce + 0, TC_NEPI); mbar_init(bar_acce + 8, TC_NEPI);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), ncols);
+  // resident weights: all K-blocks, hi and lo
+  for (int kb = 0; kb < nkb; ++kb) {
+    fill_tile<TC_NPROD + TC_NEPI>(sB + (2 * kb) * b_bytes, a.Bh + kb * TC_BK, a.ldb, N, N, tid);
+    fill_tile<TC_NPROD + TC_NEPI>(sB + (2 * kb + 1) * b_bytes, a.Bl + kb * TC_BK, a.ldb, N, N, tid);
+  }
+  cp_async_commit_group();
+  cp_async_wait_group<0>();
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ntiles = (a.M + TC_BM - 1) / TC_BM;
+  const uint32_t idesc = make_idesc_f16(TC_BM, N);
+  const uint32_t lbo_a = tile_lbo(TC_BM), lbo_b = tile_lbo(N);
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers + MMA issue (thread 0)
+    // global block counter g enumerates (tile, kb) pairs of this CTA; the MMAs of block g-1 are issued after the
+    // fill of block g has been launched (one block of prefetch skew, two cp.async groups in flight).
+    int g = 0;
+    int pend_tile_it = -1, pend_kb = 0, pend_stage = 0;  // block whose MMAs are still to be issued
+    auto issue_pending = [&]() {
+      if (pend_tile_it < 0) return;
+      if (tid == 0) {
+        const int buf = pend_tile_it & 1;
+        if (pend_kb == 0) {  // first block of a tile: the epilogue must have drained this accumulator buffer
+          mbar_wait(bar_acce + 8 * buf, (uint32_t)(((pend_tile_it >> 1) & 1) ^ 1));
+        }
+        tc_fence_after_sync();
+        const uint32_t sa = sA + pend_stage * 2 * a_bytes;
+        const uint32_t sb = sB + pend_kb * 2 * b_bytes;
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * N);
+#pragma unroll
+        for (int i = 0; i < TC_BK / 16; ++i) {
+          const uint64_t ah = make_desc(sa + 2 * i * lbo_a, lbo_a, 128);
+          const uint64_t al = make_desc(sa + a_bytes + 2 * i * lbo_a, lbo_a, 128);
+          const uint64_t bh = make_desc(sb + 2 * i * lbo_b, lbo_b, 128);
+          const uint64_t bl = make_desc(sb + b_bytes + 2 * i * lbo_b, lbo_b, 128);
+          mma_f16_ss(tacc, al, bh, idesc, (pend_kb > 0 || i > 0) ? 1u : 0u);
+          mma_f16_ss(tacc, ah, bl, idesc, 1u);
+          mma_f16_ss(tacc, ah, bh, idesc, 1u);
+        }
+        commit(bar_empty + 8 * pend_stage);
+        if (pend_kb == nkb - 1) commit(bar_accf + 8 * buf);
+      }
+    };
+    int tile_it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+      const int m0 = tile * TC_BM;
+      const int valid_rows = min(TC_BM, a.M - m0);
+      for (int kb = 0; kb < nkb; ++kb, ++g) {
+        const int st = g % TC_RING;
+        mbar_wait(bar_empty + 8 * st, (uint32_t)((((g / TC_RING) & 1)) ^ 1));  // stage free (first use passes)
+        const uint32_t s0 = sA + st * 2 * a_bytes;
+        fill_tile<TC_NPROD>(s0, a.Ah + (size_t)m0 * a.lda + kb * TC_BK, a.lda, TC_BM, valid_rows, tid);
+        fill_tile<TC_NPROD>(s0 + a_bytes, a.Al + (size_t)m0 * a.lda + kb * TC_BK, a.lda, TC_BM, valid_rows, tid);
+        cp_async_commit_group();
+        cp_async_wait_group<1>();       // the previous block's copies (of this thread) have landed
+        fence_proxy_async();
+        named_bar_sync(1, TC_NPROD);    // ... and everybody else's
+        issue_pending();
+        pend_tile_it = tile_it; pend_kb = kb; pend_stage = st;
+      }
+    }
+    cp_async_wait_group<0>();
+    fence_proxy_async();
+    named_bar_sync(1, TC_NPROD);
+    issue_pending();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int warp4 = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    int tile_it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+      const int buf = tile_it & 1;
+      mbar_wait(bar_accf + 8 * buf, (uint32_t)((tile_it >> 1) & 1));
+      tc_fence_after_sync();
+      tc_epilogue_tile<EPI>(a, tmem_base + (uint32_t)(buf * N), tile * TC_BM, warp4, lane);
+      tc_fence_before_sync();
+      mbar_arrive(bar_acce + 8 * buf);
+    }
+  }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, ncols);
 }
 
-static size_t tc_smem_bytes(int N) { return (size_t)TC_STAGES * (2 * tile_bytes(TC_BM) + 2 * tile_bytes(N)) + 64; }
+static size_t tc_smem_bytes(int N, int K) {
+  return (size_t)(K / TC_BK) * 2 * tile_bytes(N) + (size_t)TC_RING * 2 * tile_bytes(TC_BM) + 128;
+}
 
 int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
   MVSF_REQUIRE(a.Ah && a.Al && a.Bh && a.Bl && (a.C || a.C2) && a.M > 0, "linear_tc: bad arguments");
@@ -212,10 +260,15 @@ int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
   if (a.C2) MVSF_REQUIRE((a.ldc2 % 8) == 0 && ((uintptr_t)a.C2 & 15) == 0, "linear_tc: C2 must be 16-byte aligned");
   if (epi == LIN_RES_LN || epi == LIN_LN) MVSF_REQUIRE(a.N == 64 && a.ln_w && a.ln_b, "linear_tc: LayerNorm epilogue needs N == 64");
   if (epi == LIN_RES || epi == LIN_RES_LN) MVSF_REQUIRE(a.res && a.gamma, "linear_tc: residual epilogue needs res and gamma");
-  const size_t smem = tc_smem_bytes(a.N);
+  const size_t smem = tc_smem_bytes(a.N, a.K);
+  MVSF_REQUIRE(smem <= 227 * 1024, "linear_tc: N*K too large for resident weights (%zu bytes of shared memory)", smem);
   static bool configured = false;
+  static int num_sms = 148;
   if (!configured) {
-    const int maxs = (int)tc_smem_bytes(256);
+    int dev = 0;
+    MVSF_CUDA_OK(cudaGetDevice(&dev));
+    MVSF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const int maxs = 227 * 1024;
     MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_ELU1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
@@ -224,14 +277,16 @@ int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
     MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     configured = true;
   }
-  dim3 grid(cdiv(a.M, TC_BM));
+  const int ntiles = cdiv(a.M, TC_BM);
+  dim3 grid(ntiles < num_sms ? ntiles : num_sms);  // persistent: one CTA per SM, tiles strided by gridDim.x
+  constexpr int TC_THREADS2 = TC_NPROD + TC_NEPI;
   switch (epi) {
-    case LIN_BIAS: linear_tc_kernel<LIN_BIAS><<<grid, TC_THREADS, smem, s>>>(a); break;
-    case LIN_GELU: linear_tc_kernel<LIN_GELU><<<grid, TC_THREADS, smem, s>>>(a); break;
-    case LIN_ELU1: linear_tc_kernel<LIN_ELU1><<<grid, TC_THREADS, smem, s>>>(a); break;
-    case LIN_RES: linear_tc_kernel<LIN_RES><<<grid, TC_THREADS, smem, s>>>(a); break;
-    case LIN_RES_LN: linear_tc_kernel<LIN_RES_LN><<<grid, TC_THREADS, smem, s>>>(a); break;
-    case LIN_LN: linear_tc_kernel<LIN_LN><<<grid, TC_THREADS, smem, s>>>(a); break;
+    case LIN_BIAS: linear_tc_kernel<LIN_BIAS><<<grid, TC_THREADS2, smem, s>>>(a); break;
+    case LIN_GELU: linear_tc_kernel<LIN_GELU><<<grid, TC_THREADS2, smem, s>>>(a); break;
+    case LIN_ELU1: linear_tc_kernel<LIN_ELU1><<<grid, TC_THREADS2, smem, s>>>(a); break;
+    case LIN_RES: linear_tc_kernel<LIN_RES><<<grid, TC_THREADS2, smem, s>>>(a); break;
+    case LIN_RES_LN: linear_tc_kernel<LIN_RES_LN><<<grid, TC_THREADS2, smem, s>>>(a); break;
+    case LIN_LN: linear_tc_kernel<LIN_LN><<<grid, TC_THREADS2, smem, s>>>(a); break;
     default: return fail(MVSF_ERR_INVALID, "linear_tc: unknown epilogue %d", epi);
   }
   MVSF_LAUNCH_CHECK("linear_tc");
