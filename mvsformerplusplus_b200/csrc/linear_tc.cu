@@ -54,11 +54,11 @@ __device__ __forceinline__ void store_split16(__half* c2row, int N, int col, con
 
 // Persistent, warp-specialised kernel.  256 threads:
 //   warps 0-3  producers: cp.async-fill the A ring (one K-block of 128 rows, hi+lo, per stage); thread 0 issues the MMAs
-//   warps 4-7  epilogue : TMEM -> registers -> global, one accumulator row per thread
+//   warps 4-7 / 8-11  epilogue warpgroups for even / odd tiles: TMEM -> registers -> global, one accumulator row per thread
 // The weight tiles of all K-blocks stay resident in shared memory for the CTA's lifetime; accumulators are double
 // buffered in TMEM (2 x N columns) so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 // mbarriers: empty[s] (MMAs that read stage s finished -> refill), acc_full[b] / acc_empty[b] (accumulator hand-over).
-constexpr int TC_NPROD = 128, TC_NEPI = 128;
+constexpr int TC_NPROD = 128, TC_NEPI = 256;  // two epilogue warpgroups: even / odd tiles (= the two TMEM buffers)
 
 template <int EPI>
 __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t tacc, int m0, int warp4, int lane) {
@@ -155,7 +155,7 @@ linear_tc_kernel(TcLinArgs a) {
   if (tid == 0) {
     for (int i = 0; i < TC_RING; ++i) mbar_init(bar_empty + 8 * i, 1);
     mbar_init(bar_accf + 0, 1); mbar_init(bar_accf + 8, 1);
-    mbar_init(bar_acce + 0, TC_NEPI); mbar_init(bar_acce + 8, TC_NEPI);
+    mbar_init(bar_acce + 0, 128); mbar_init(bar_acce + 8, 128);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), ncols);
@@ -231,10 +231,12 @@ linear_tc_kernel(TcLinArgs a) {
     issue_pending();
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int warp4 = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int warp4 = warp & 3;         // the TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;    // epilogue warpgroup 0 drains buffer 0 (even tiles), group 1 buffer 1 (odd tiles)
     int tile_it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
       const int buf = tile_it & 1;
+      if (buf != grp) continue;
       mbar_wait(bar_accf + 8 * buf, (uint32_t)((tile_it >> 1) & 1));
       tc_fence_after_sync();
       tc_epilogue_tile<EPI>(a, tmem_base + (uint32_t)(buf * N), tile * TC_BM, warp4, lane);
