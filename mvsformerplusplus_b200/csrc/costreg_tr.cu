@@ -12,6 +12,7 @@
 
 #include "linear.cuh"
 #include "linear_tc.cuh"
+#include "umma.cuh"
 
 namespace mvsf {
 
@@ -80,18 +81,6 @@ __global__ void patch_gather_kernel(const float* __restrict__ vol, __half* __res
   split_store8(row, row + 256, v);
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Tensor-core softmax attention (product path).  head_dim 16 makes QK^T a single k16 MMA step and PV an n16 tile, so
-// the kernel is bound by the SIMT softmax work, not by the tensor pipe; it is written FlashAttention-2 style on
-// mma.sync.m16n8k16 (fp16 in, fp32 accumulate) with every operand split into hi + lo fp16 parts and three MMAs per
-// product (lo*hi + hi*lo + hi*hi; hi+lo carries 22 mantissa bits, the dropped lo*lo term is 2^-22 relative) so the
-// result stays within the fp32 parity budget.  A single bf16/tf32 pass moves probabilities by ~1e-3
-// and a bf16 split (2^-17 per product) still left 4e-4 at N = 27648 where |score| reaches 14 in log2 units.
-// Range assumption: |q*scale|, |k|, |v| < 65504 (LayerNorm-ed tokens through 64x64 linears: O(10)).
-//   split kernel : qkv [N][3][4][16] fp32 -> Qh,Ql,Kh,Kl,Vh,Vl [4][N][16] fp16   (q pre-scaled by scale*log2(e))
-//   main kernel  : CTA = 8 warps x 16 queries, 64-key tiles of K/V streamed with cp.async (3 stages), swizzled rows
-//                  so ldmatrix is bank-conflict free; S/P live in registers (C-fragment == A-fragment layout).
-// ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
@@ -105,239 +94,252 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
 }
-__global__ void qkv_split_kernel(const float* __restrict__ qkv, __half* __restrict__ split, int N, float qscale) {
-  // split layout: [6][4 heads][N][16]  (0 Qh, 1 Ql, 2 Kh, 3 Kl, 4 Vh, 5 Vl)
+__global__ void qkv_split_kernel(const float* __restrict__ qkv, __half* __restrict__ split, int N, int Np, float qscale) {
+  // split layout, planes of 4*Np*16 halves (Np = N rounded up to 8): 0 Qh, 1 Ql, 2 Kh, 3 Kl as [4 heads][Np][16];
+  // 4 Vh, 5 Vl TRANSPOSED per head as [4 heads][16 dims][Np] (keys contiguous: K-major B operand of the tcgen05 P*V
+  // product); the pad keys [N, Np) of V are written as zeros.
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // (token, which(q/k/v), head, quad of 4 dims)
-  int total = N * 3 * 4 * 4;
+  int total = Np * 3 * 4 * 4;
   if (i >= total) return;
   int quad = i & 3, h = (i >> 2) & 3, which = (i >> 4) % 3, tok = i / 48;
+  const size_t plane = (size_t)4 * Np * 16;
+  if (tok >= N) {
+    if (which == 2) {
+      __half* th = split + (size_t)4 * plane + ((size_t)h * 16 + quad * 4) * Np + tok;
+      __half* tl = split + (size_t)5 * plane + ((size_t)h * 16 + quad * 4) * Np + tok;
+      for (int e = 0; e < 4; ++e) { th[(size_t)e * Np] = __float2half_rn(0.f); tl[(size_t)e * Np] = __float2half_rn(0.f); }
+    }
+    return;
+  }
   float4 v = ldg4(qkv + (size_t)tok * 192 + which * 64 + h * 16 + quad * 4);
   if (which == 0) { v.x *= qscale; v.y *= qscale; v.z *= qscale; v.w *= qscale; }
   __half hi[4], lo[4];
   split_f16(v.x, hi[0], lo[0]); split_f16(v.y, hi[1], lo[1]); split_f16(v.z, hi[2], lo[2]); split_f16(v.w, hi[3], lo[3]);
-  size_t plane = (size_t)4 * N * 16;
-  size_t off = ((size_t)h * N + tok) * 16 + quad * 4;
-  __half* ph = split + (size_t)(which * 2) * plane + off;
-  __half* pl = split + (size_t)(which * 2 + 1) * plane + off;
-  *reinterpret_cast<uint2*>(ph) = *reinterpret_cast<uint2*>(hi);
-  *reinterpret_cast<uint2*>(pl) = *reinterpret_cast<uint2*>(lo);
+  if (which == 2) {
+    __half* th = split + (size_t)4 * plane + ((size_t)h * 16 + quad * 4) * Np + tok;
+    __half* tl = split + (size_t)5 * plane + ((size_t)h * 16 + quad * 4) * Np + tok;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { th[(size_t)e * Np] = hi[e]; tl[(size_t)e * Np] = lo[e]; }
+    return;
+  }
+  size_t off = ((size_t)h * Np + tok) * 16 + quad * 4;
+  __half2* ph = reinterpret_cast<__half2*>(split + (size_t)(which * 2) * plane + off);
+  __half2* pl = reinterpret_cast<__half2*>(split + (size_t)(which * 2 + 1) * plane + off);
+  ph[0] = __halves2half2(hi[0], hi[1]); ph[1] = __halves2half2(hi[2], hi[3]);
+  pl[0] = __halves2half2(lo[0], lo[1]); pl[1] = __halves2half2(lo[2], lo[3]);
 }
 
-__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr, bool valid) {
-  int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(sz));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N_>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_)); }
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-constexpr int FA_BM = 128, FA_BN = 64, FA_STAGES = 3;
-// one stage = 4 arrays (Kh, Kl, Vh, Vl) x 64 keys x 32 bytes
-constexpr int FA_ARR_BYTES = FA_BN * 32, FA_STAGE_BYTES = 4 * FA_ARR_BYTES;
+// ------------------------------------------------------------------------------------------------------------------
+// tcgen05 softmax attention (product path).  CTA = 128 queries x one head, 128 threads, thread t owns query row t
+// (TMEM lane t), so row max / row sum need no cross-thread traffic.  Per 128-key tile:
+//   S[128x128] = Q K^T      : 3 split-fp16 tcgen05.mma (lo*hi, hi*lo, hi*hi), K = 16, fp32 accumulators in TMEM
+//   softmax                  : tcgen05.ld the row, online max, P = exp2(S - m), split P into fp16 hi/lo, store both in the
+//                              canonical K-major A-operand layout in shared memory
+//   Otile[128x16] = P V      : 8 k-steps x 3 split products = 24 tcgen05.mma (N = 16), V^T tiles are K-major B operands
+//   O = O * corr + Otile     : round-to-nearest FMA in registers (tensor-core accumulation truncates; chaining all
+//                              tiles on one accumulator biases the result, see profiles/)
+// Two CTAs per SM (<= 113 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's MMAs.
+// ------------------------------------------------------------------------------------------------------------------
+namespace fa5 {
+using namespace umma;
+constexpr int BM = 128, BN = 128;
+constexpr uint32_t LBO_QK = 16 * 128 + 16;   // 2 chunks (hd = 16) x 128 rows
+constexpr uint32_t QK_TILE = 2 * LBO_QK;
+constexpr uint32_t LBO_P = 16 * 128;         // 16 chunks (128 keys) x 128 rows
+constexpr uint32_t P_TILE = 16 * LBO_P;      // 32 KB
+constexpr uint32_t LBO_V = 2 * 128 + 16;     // 16 chunks (128 keys) x 16 rows (dims)
+constexpr uint32_t V_TILE = 16 * LBO_V;
+constexpr uint32_t KV_STAGE = 2 * QK_TILE + 2 * V_TILE;  // Kh, Kl, Vth, Vtl
+constexpr uint32_t OFF_Q = 0, OFF_KV = 2 * QK_TILE, OFF_P = OFF_KV + 2 * KV_STAGE, OFF_BAR = OFF_P + 2 * P_TILE;
+constexpr uint32_t SMEM = OFF_BAR + 64;
+}  // namespace fa5
 
-// byte offset of (key row r, 16-byte chunk c) inside one 64x32B array, XOR-swizzled so that the 8 rows an ldmatrix
-// 8x8 tile touches fall into 8 distinct 16-byte bank groups
-__device__ __forceinline__ int fa_off(int r, int c) { return r * 32 + ((c ^ ((r >> 2) & 1)) << 4); }
-
-__global__ void __launch_bounds__(256)
-attention_mma_kernel(const __half* __restrict__ split, float* __restrict__ out, __half* __restrict__ out2, int N) {
-  __shared__ __align__(128) unsigned char smem[FA_STAGES * FA_STAGE_BYTES];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
+__global__ void __launch_bounds__(128, 2)
+attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, __half* __restrict__ out2, int N, int Np) {
+  using namespace fa5;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.y;
-  const int q0 = blockIdx.x * FA_BM + warp * 16;
-  const size_t plane = (size_t)4 * N * 16;
-  const __half* Qh = split + 0 * plane + (size_t)h * N * 16;
-  const __half* Ql = split + 1 * plane + (size_t)h * N * 16;
-  const __half* KV[4] = {split + 2 * plane + (size_t)h * N * 16, split + 3 * plane + (size_t)h * N * 16,
-                                split + 4 * plane + (size_t)h * N * 16, split + 5 * plane + (size_t)h * N * 16};
-  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  const int q0 = blockIdx.x * BM;
+  const size_t plane = (size_t)4 * Np * 16;
+  const __half* Qg[2] = {split + 0 * plane + (size_t)h * Np * 16, split + 1 * plane + (size_t)h * Np * 16};
+  const __half* Kg[2] = {split + 2 * plane + (size_t)h * Np * 16, split + 3 * plane + (size_t)h * Np * 16};
+  const __half* Vg[2] = {split + 4 * plane + (size_t)h * 16 * Np, split + 5 * plane + (size_t)h * 16 * Np};  // [16][Np]
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar_s = sb + OFF_BAR, bar_o = sb + OFF_BAR + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 32);
 
-  // Q fragments (A operand, 16 queries x 16 dims), hi and lo
-  uint32_t qh[4], ql[4];
-  {
-    int r0 = min(q0 + g, N - 1), r1 = min(q0 + g + 8, N - 1);
-    qh[0] = *reinterpret_cast<const uint32_t*>(Qh + (size_t)r0 * 16 + 2 * t);
-    qh[1] = *reinterpret_cast<const uint32_t*>(Qh + (size_t)r1 * 16 + 2 * t);
-    qh[2] = *reinterpret_cast<const uint32_t*>(Qh + (size_t)r0 * 16 + 2 * t + 8);
-    qh[3] = *reinterpret_cast<const uint32_t*>(Qh + (size_t)r1 * 16 + 2 * t + 8);
-    ql[0] = *reinterpret_cast<const uint32_t*>(Ql + (size_t)r0 * 16 + 2 * t);
-    ql[1] = *reinterpret_cast<const uint32_t*>(Ql + (size_t)r1 * 16 + 2 * t);
-    ql[2] = *reinterpret_cast<const uint32_t*>(Ql + (size_t)r0 * 16 + 2 * t + 8);
-    ql[3] = *reinterpret_cast<const uint32_t*>(Ql + (size_t)r1 * 16 + 2 * t + 8);
+  if (tid == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
   }
+  if (warp == 0) tmem_alloc(sb + OFF_BAR + 32, 256);
 
-  const int ntiles = (N + FA_BN - 1) / FA_BN;
-  auto issue_tile = [&](int tile, int stage) {
-    // 4 arrays x 64 rows x 2 chunks = 512 16-byte copies, 2 per thread
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      int idx = tid + i * 256;
-      int arr = idx >> 7, rem = idx & 127;
-      int r = rem >> 1, c = rem & 1;
-      int key = tile * FA_BN + r;
-      bool valid = key < N;
-      const __half* src = KV[arr] + (size_t)(valid ? key : 0) * 16 + c * 8;
-      cp_async16(smem_base + stage * FA_STAGE_BYTES + arr * FA_ARR_BYTES + fa_off(r, c), src, valid);
+  // ---- loads: Q once, K / V^T tiles through a 2-stage ring (cp.async, zero fill beyond N)
+  auto load_qk_tile = [&](uint32_t dst, const __half* g, int row0) {  // 128 rows x 2 chunks
+    for (int idx = tid; idx < 256; idx += 128) {
+      int r = idx >> 1, c = idx & 1;
+      bool ok = row0 + r < N;
+      cp_async16_zfill(dst + c * LBO_QK + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)(ok ? row0 + r : 0) * 16 + c * 8, ok);
     }
   };
-#pragma unroll
-  for (int s = 0; s < FA_STAGES - 1; ++s) {
-    if (s < ntiles) issue_tile(s, s);
-    cp_async_commit();
-  }
+  auto load_v_tile = [&](uint32_t dst, const __half* g, int key0) {   // 16 rows (dims) x 16 chunks of 8 keys
+    for (int idx = tid; idx < 256; idx += 128) {
+      int r = idx >> 4, c = idx & 15;
+      bool ok = key0 + c * 8 < Np;  // rows are padded to Np (multiple of 8) with zeros: chunks are whole
+      cp_async16_zfill(dst + c * LBO_V + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)r * Np + (ok ? key0 + c * 8 : 0), ok);
+    }
+  };
+  auto load_kv = [&](int tile, int st) {
+    const uint32_t s0 = sb + OFF_KV + st * KV_STAGE;
+    load_qk_tile(s0, Kg[0], tile * BN);
+    load_qk_tile(s0 + QK_TILE, Kg[1], tile * BN);
+    load_v_tile(s0 + 2 * QK_TILE, Vg[0], tile * BN);
+    load_v_tile(s0 + 2 * QK_TILE + V_TILE, Vg[1], tile * BN);
+    cp_async_commit_group();
+  };
+  load_qk_tile(sb + OFF_Q, Qg[0], q0);
+  load_qk_tile(sb + OFF_Q + QK_TILE, Qg[1], q0);
+  const int ntiles = (N + BN - 1) / BN;
+  load_kv(0, 0);  // (same cp.async group as Q)
 
-  float o[2][4];
-#pragma unroll
-  for (int nd = 0; nd < 2; ++nd)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
-  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t trow = ((uint32_t)(warp * 32)) << 16;
+  const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 16);
+  const uint32_t prow = sb + OFF_P + (tid >> 3) * 128 + (tid & 7) * 16;  // this thread's row inside every P chunk
 
-  for (int tile = 0; tile < ntiles; ++tile) {
-    cp_async_wait<FA_STAGES - 2>();
+  float o[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+  float m = -1e30f, l = 0.f;
+
+  for (int j = 0; j < ntiles; ++j) {
+    const int st = j & 1;
+    if (j + 1 < ntiles) { load_kv(j + 1, st ^ 1); cp_async_wait_group<1>(); }
+    else cp_async_wait_group<0>();
+    fence_proxy_async();
+    tc_fence_before_sync();
     __syncthreads();
-    {  // prefetch tile + STAGES-1 into the stage that was consumed in the previous iteration
-      int nt = tile + FA_STAGES - 1;
-      if (nt < ntiles) issue_tile(nt, nt % FA_STAGES);
-      cp_async_commit();
+    const uint32_t sK = sb + OFF_KV + st * KV_STAGE, sV = sK + 2 * QK_TILE;
+    if (tid == 0) {
+      tc_fence_after_sync();
+      const uint64_t qh = make_desc(sb + OFF_Q, LBO_QK, 128), ql = make_desc(sb + OFF_Q + QK_TILE, LBO_QK, 128);
+      const uint64_t kh = make_desc(sK, LBO_QK, 128), kl = make_desc(sK + QK_TILE, LBO_QK, 128);
+      mma_f16_ss(tS, ql, kh, idesc_s, 0u);
+      mma_f16_ss(tS, qh, kl, idesc_s, 1u);
+      mma_f16_ss(tS, qh, kh, idesc_s, 1u);
+      commit(bar_s);
     }
-    const uint32_t sb = smem_base + (tile % FA_STAGES) * FA_STAGE_BYTES;
-    const uint32_t sKh = sb, sKl = sb + FA_ARR_BYTES, sVh = sb + 2 * FA_ARR_BYTES, sVl = sb + 3 * FA_ARR_BYTES;
+    mbar_wait(bar_s, (uint32_t)(j & 1));
+    tc_fence_after_sync();
 
-    // ---- S = Q K^T  (8 n-tiles of 8 keys)
-    float sacc[8][4];
+    // ---- pass 1: row maximum
+    const int kbase = j * BN;
+    const bool tail = (kbase + BN > N);
+    float mx = m;
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      float v[16];
+      tmem_ld16(tS + trow + c * 16, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) sacc[j][i] = 0.f;
-#pragma unroll
-    for (int jp = 0; jp < 4; ++jp) {
-      // ldmatrix.x4: matrices (ntile 2jp, k 0-7), (2jp, k 8-15), (2jp+1, k 0-7), (2jp+1, k 8-15)
-      int mtx = lane >> 3, row = (2 * jp + (mtx >> 1)) * 8 + (lane & 7), chunk = mtx & 1;
-      uint32_t off = fa_off(row, chunk);
-      uint32_t bh[4], bl[4];
-      ldsm_x4(bh, sKh + off);
-      ldsm_x4(bl, sKl + off);
-      mma_f16_16816(sacc[2 * jp], ql, bh[0], bh[1]);
-      mma_f16_16816(sacc[2 * jp], qh, bl[0], bl[1]);
-      mma_f16_16816(sacc[2 * jp], qh, bh[0], bh[1]);
-      mma_f16_16816(sacc[2 * jp + 1], ql, bh[2], bh[3]);
-      mma_f16_16816(sacc[2 * jp + 1], qh, bl[2], bl[3]);
-      mma_f16_16816(sacc[2 * jp + 1], qh, bh[2], bh[3]);
-    }
-    // ---- mask keys beyond N (last tile only)
-    if (tile == ntiles - 1 && (N % FA_BN) != 0) {
-      int kbase = tile * FA_BN;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        int k0 = kbase + j * 8 + 2 * t;
-        if (k0 >= N) { sacc[j][0] = -1e30f; sacc[j][2] = -1e30f; }
-        if (k0 + 1 >= N) { sacc[j][1] = -1e30f; sacc[j][3] = -1e30f; }
+      for (int e = 0; e < 16; ++e) {
+        float sv = (tail && kbase + c * 16 + e >= N) ? -1e30f : v[e];
+        mx = fmaxf(mx, sv);
       }
     }
-    // ---- online softmax (rows g and g+8; a row is spread over the 4 lanes of a quad)
-    float mx0 = m0, mx1 = m1;
+    const float corr = ex2f(m - mx);
+    m = mx;
+    l *= corr;
+    // ---- pass 2: P = exp2(S - m), hi/lo split -> shared memory (A operand of P*V)
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      float v[16];
+      tmem_ld16(tS + trow + c * 16, v);
+      __align__(16) __half2 ph[8], pl[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mx0 = fmaxf(mx0, fmaxf(sacc[j][0], sacc[j][1]));
-      mx1 = fmaxf(mx1, fmaxf(sacc[j][2], sacc[j][3]));
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float c0 = ex2f(m0 - mx0), c1 = ex2f(m1 - mx1);
-    m0 = mx0; m1 = mx1;
-    l0 *= c0; l1 *= c1;
-    // Tensor-core fp32 accumulation truncates; chaining all 5k MMAs of a row on one accumulator biases the result by
-    // ~1e-4 relative.  Each tile therefore accumulates into fresh registers (12 chained MMAs) that are folded into the
-    // running output with a round-to-nearest FMA below.
-    float ot[2][4];
-#pragma unroll
-    for (int nd = 0; nd < 2; ++nd)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) ot[nd][i] = 0.f;
-
-    // ---- P = exp2(S - m), split into hi/lo fp16 A-fragments; O += P V
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      uint32_t ah[4], al[4];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int j = 2 * ks + half;
-        float p0 = ex2f(sacc[j][0] - m0), p1 = ex2f(sacc[j][1] - m0);
-        float p2 = ex2f(sacc[j][2] - m1), p3 = ex2f(sacc[j][3] - m1);
-        l0 += p0 + p1;
-        l1 += p2 + p3;
-        uint32_t h01 = pack_f16x2(p0, p1), h23 = pack_f16x2(p2, p3);
-        float2 f01 = unpack_f16x2(h01), f23 = unpack_f16x2(h23);
-        ah[half * 2 + 0] = h01; ah[half * 2 + 1] = h23;
-        al[half * 2 + 0] = pack_f16x2(p0 - f01.x, p1 - f01.y); al[half * 2 + 1] = pack_f16x2(p2 - f23.x, p3 - f23.y);
+      for (int e = 0; e < 8; ++e) {
+        float s0 = v[2 * e], s1 = v[2 * e + 1];
+        if (tail) {
+          if (kbase + c * 16 + 2 * e >= N) s0 = -1e30f;
+          if (kbase + c * 16 + 2 * e + 1 >= N) s1 = -1e30f;
+        }
+        const float p0 = ex2f(s0 - m), p1 = ex2f(s1 - m);
+        l += p0 + p1;
+        const __half2 hh = __floats2half2_rn(p0, p1);
+        const float2 hf = __half22float2(hh);
+        ph[e] = hh;
+        pl[e] = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
       }
-      // ldmatrix.x4.trans on V[key][dim]: matrices (keys lo, dims 0-7), (keys hi, dims 0-7), (keys lo, 8-15), (keys hi, 8-15)
-      int mtx = lane >> 3, row = ks * 16 + (mtx & 1) * 8 + (lane & 7), chunk = mtx >> 1;
-      uint32_t off = fa_off(row, chunk);
-      uint32_t vh[4], vl[4];
-      ldsm_x4_trans(vh, sVh + off);
-      ldsm_x4_trans(vl, sVl + off);
-      mma_f16_16816(ot[0], al, vh[0], vh[1]);
-      mma_f16_16816(ot[0], ah, vl[0], vl[1]);
-      mma_f16_16816(ot[0], ah, vh[0], vh[1]);
-      mma_f16_16816(ot[1], al, vh[2], vh[3]);
-      mma_f16_16816(ot[1], ah, vl[2], vl[3]);
-      mma_f16_16816(ot[1], ah, vh[2], vh[3]);
+      // 16 keys = chunks 2c and 2c+1 of this row
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (2 * c) * LBO_P), "r"(*reinterpret_cast<uint32_t*>(&ph[0])),
+                   "r"(*reinterpret_cast<uint32_t*>(&ph[1])), "r"(*reinterpret_cast<uint32_t*>(&ph[2])), "r"(*reinterpret_cast<uint32_t*>(&ph[3])) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (2 * c + 1) * LBO_P), "r"(*reinterpret_cast<uint32_t*>(&ph[4])),
+                   "r"(*reinterpret_cast<uint32_t*>(&ph[5])), "r"(*reinterpret_cast<uint32_t*>(&ph[6])), "r"(*reinterpret_cast<uint32_t*>(&ph[7])) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + P_TILE + (2 * c) * LBO_P), "r"(*reinterpret_cast<uint32_t*>(&pl[0])),
+                   "r"(*reinterpret_cast<uint32_t*>(&pl[1])), "r"(*reinterpret_cast<uint32_t*>(&pl[2])), "r"(*reinterpret_cast<uint32_t*>(&pl[3])) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + P_TILE + (2 * c + 1) * LBO_P), "r"(*reinterpret_cast<uint32_t*>(&pl[4])),
+                   "r"(*reinterpret_cast<uint32_t*>(&pl[5])), "r"(*reinterpret_cast<uint32_t*>(&pl[6])), "r"(*reinterpret_cast<uint32_t*>(&pl[7])) : "memory");
     }
+    fence_proxy_async();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
 #pragma unroll
-    for (int nd = 0; nd < 2; ++nd) {
-      o[nd][0] = fmaf(o[nd][0], c0, ot[nd][0]); o[nd][1] = fmaf(o[nd][1], c0, ot[nd][1]);
-      o[nd][2] = fmaf(o[nd][2], c1, ot[nd][2]); o[nd][3] = fmaf(o[nd][3], c1, ot[nd][3]);
+      for (int i = 0; i < 8; ++i) {
+        const uint64_t pH = make_desc(sb + OFF_P + 2 * i * LBO_P, LBO_P, 128);
+        const uint64_t pL = make_desc(sb + OFF_P + P_TILE + 2 * i * LBO_P, LBO_P, 128);
+        const uint64_t vH = make_desc(sV + 2 * i * LBO_V, LBO_V, 128);
+        const uint64_t vL = make_desc(sV + V_TILE + 2 * i * LBO_V, LBO_V, 128);
+        mma_f16_ss(tO, pL, vH, idesc_o, i > 0 ? 1u : 0u);
+        mma_f16_ss(tO, pH, vL, idesc_o, 1u);
+        mma_f16_ss(tO, pH, vH, idesc_o, 1u);
+      }
+      commit(bar_o);
+    }
+    mbar_wait(bar_o, (uint32_t)(j & 1));
+    tc_fence_after_sync();
+    {
+      float ot[16];
+      tmem_ld16(tO + trow, ot);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], corr, ot[d]);
     }
   }
-  cp_async_wait<0>();
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = __fdiv_rn(1.0f, l0), i1 = __fdiv_rn(1.0f, l1);
-  const int r0 = q0 + g, r1 = q0 + g + 8;
+
+  const int r = q0 + tid;
+  if (r < N) {
+    const float inv = __fdiv_rn(1.0f, l);
+    float res[16];
 #pragma unroll
-  for (int nd = 0; nd < 2; ++nd) {
-    const int col = h * 16 + nd * 8 + 2 * t;
-    const float a0 = o[nd][0] * i0, a1 = o[nd][1] * i0, b0 = o[nd][2] * i1, b1 = o[nd][3] * i1;
+    for (int d = 0; d < 16; ++d) res[d] = o[d] * inv;
     if (out) {
-      if (r0 < N) *reinterpret_cast<float2*>(out + (size_t)r0 * 64 + col) = make_float2(a0, a1);
-      if (r1 < N) *reinterpret_cast<float2*>(out + (size_t)r1 * 64 + col) = make_float2(b0, b1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(out + (size_t)r * 64 + h * 16 + c * 4) = make_float4(res[c * 4], res[c * 4 + 1], res[c * 4 + 2], res[c * 4 + 3]);
     }
-    if (out2) {  // fp16 hi|lo split rows [hi(64) | lo(64)] for the projection GEMM
-      const __half2 ah = __floats2half2_rn(a0, a1), bh = __floats2half2_rn(b0, b1);
-      const float2 af = __half22float2(ah), bf = __half22float2(bh);
-      if (r0 < N) {
-        *reinterpret_cast<__half2*>(out2 + (size_t)r0 * 128 + col) = ah;
-        *reinterpret_cast<__half2*>(out2 + (size_t)r0 * 128 + 64 + col) = __floats2half2_rn(a0 - af.x, a1 - af.y);
-      }
-      if (r1 < N) {
-        *reinterpret_cast<__half2*>(out2 + (size_t)r1 * 128 + col) = bh;
-        *reinterpret_cast<__half2*>(out2 + (size_t)r1 * 128 + 64 + col) = __floats2half2_rn(b0 - bf.x, b1 - bf.y);
-      }
+    if (out2) {
+      float v0[8], v1[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v0[e] = res[e]; v1[e] = res[8 + e]; }
+      split_store8(out2 + (size_t)r * 128 + h * 16, out2 + (size_t)r * 128 + 64 + h * 16, v0);
+      split_store8(out2 + (size_t)r * 128 + h * 16 + 8, out2 + (size_t)r * 128 + 64 + h * 16 + 8, v1);
     }
   }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // un-patchify epilogue: u [N][256] (n = vox*8+co) -> LayerNorm3D over the 8 channels of each voxel (eps 1e-6)
@@ -375,10 +377,16 @@ __global__ void unpatch_ln_prob_kernel(const float* __restrict__ u, const float*
 
 
 static int run_attention(const float* qkv, float* o, __half* o2, __half* split, int N, float scale_log2e, cudaStream_t s) {
-  qkv_split_kernel<<<cdiv((long long)N * 48, 256), 256, 0, s>>>(qkv, split, N, scale_log2e);
+  const int Np = (N + 7) & ~7;
+  qkv_split_kernel<<<cdiv((long long)Np * 48, 256), 256, 0, s>>>(qkv, split, N, Np, scale_log2e);
   MVSF_LAUNCH_CHECK("qkv_split");
-  attention_mma_kernel<<<dim3(cdiv(N, FA_BM), 4), 256, 0, s>>>(split, o, o2, N);
-  MVSF_LAUNCH_CHECK("attention_mma");
+  static bool configured = false;
+  if (!configured) {
+    MVSF_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa5::SMEM));
+    configured = true;
+  }
+  attention_tc_kernel<<<dim3(cdiv(N, fa5::BM), 4), 128, fa5::SMEM, s>>>(split, o, o2, N, Np);
+  MVSF_LAUNCH_CHECK("attention_tc");
   return MVSF_OK;
 }
 
@@ -395,7 +403,7 @@ int mvsf_costreg_tr_workspace_bytes(int C, int D, int H, int W, size_t* bytes) {
   size_t N = (size_t)(D / 2) * (H / 4) * (W / 4);
   // per token (in floats): big 256 (patches2 / ffn hidden split / un-patchify out), x 64, y 64, x2 64, y2 64, o2 64,
   // qkv 192, attention operand split 192
-  *bytes = N * (256 + 64 + 64 + 64 + 64 + 64 + 192 + 192) * sizeof(float);
+  *bytes = (N * (256 + 64 + 64 + 64 + 64 + 64 + 192) + (N + 8) * 192) * sizeof(float);
   return MVSF_OK;
 }
 
@@ -477,7 +485,7 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, c
 int mvsf_attention_forward(const float* qkv, float* out, void* workspace, size_t workspace_bytes, int N,
                            float softmax_scale, mvsf_stream_t stream) {
   MVSF_REQUIRE(qkv && out && workspace && N > 0, "attention_forward: bad arguments");
-  if (workspace_bytes < (size_t)N * 768) return fail(MVSF_ERR_WORKSPACE, "attention_forward: workspace %zu < %zu bytes", workspace_bytes, (size_t)N * 768);
+  if (workspace_bytes < (size_t)(N + 8) * 768) return fail(MVSF_ERR_WORKSPACE, "attention_forward: workspace %zu < %zu bytes", workspace_bytes, (size_t)(N + 8) * 768);
   return run_attention(qkv, out, nullptr, reinterpret_cast<__half*>(workspace), N, softmax_scale * 1.4426950408889634f, (cudaStream_t)stream);
 }
 }
