@@ -155,8 +155,9 @@ constexpr uint32_t LBO_P = 16 * 128;         // 16 chunks (128 keys) x 128 rows
 constexpr uint32_t P_TILE = 16 * LBO_P;      // 32 KB
 constexpr uint32_t LBO_V = 2 * 128 + 16;     // 16 chunks (128 keys) x 16 rows (dims)
 constexpr uint32_t V_TILE = 16 * LBO_V;
-constexpr uint32_t KV_STAGE = 2 * QK_TILE + 2 * V_TILE;  // Kh, Kl, Vth, Vtl
-constexpr uint32_t OFF_Q = 0, OFF_KV = 2 * QK_TILE, OFF_P = OFF_KV + 2 * KV_STAGE, OFF_BAR = OFF_P + 2 * P_TILE;
+// Q (hi,lo) | K ring 2 x (hi,lo) | V^T ring 2 x (hi,lo) | P (hi,lo) | barriers
+constexpr uint32_t OFF_Q = 0, OFF_K = 2 * QK_TILE, OFF_V = OFF_K + 4 * QK_TILE, OFF_P = OFF_V + 4 * V_TILE,
+                   OFF_BAR = OFF_P + 2 * P_TILE;
 constexpr uint32_t SMEM = OFF_BAR + 64;
 }  // namespace fa5
 
@@ -182,8 +183,7 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
   }
   if (warp == 0) tmem_alloc(sb + OFF_BAR + 32, 256);
 
-  // ---- loads: Q once, K / V^T tiles through a 2-stage ring (cp.async, zero fill beyond N)
-  auto load_qk_tile = [&](uint32_t dst, const __half* g, int row0) {  // 128 rows x 2 chunks
+  auto load_qk_tile = [&](uint32_t dst, const __half* g, int row0) {  // 128 rows x 2 chunks, zero fill beyond N
     for (int idx = tid; idx < 256; idx += 128) {
       int r = idx >> 1, c = idx & 1;
       bool ok = row0 + r < N;
@@ -197,105 +197,121 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
       cp_async16_zfill(dst + c * LBO_V + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)r * Np + (ok ? key0 + c * 8 : 0), ok);
     }
   };
-  auto load_kv = [&](int tile, int st) {
-    const uint32_t s0 = sb + OFF_KV + st * KV_STAGE;
-    load_qk_tile(s0, Kg[0], tile * BN);
-    load_qk_tile(s0 + QK_TILE, Kg[1], tile * BN);
-    load_v_tile(s0 + 2 * QK_TILE, Vg[0], tile * BN);
-    load_v_tile(s0 + 2 * QK_TILE + V_TILE, Vg[1], tile * BN);
+  const int ntiles = (N + BN - 1) / BN;
+  auto load_k = [&](int tile) {  // always commits a group (possibly empty) to keep the group accounting uniform
+    if (tile < ntiles) {
+      const uint32_t s0 = sb + OFF_K + (tile & 1) * 2 * QK_TILE;
+      load_qk_tile(s0, Kg[0], tile * BN);
+      load_qk_tile(s0 + QK_TILE, Kg[1], tile * BN);
+    }
     cp_async_commit_group();
   };
+  auto load_v = [&](int tile) {
+    if (tile < ntiles) {
+      const uint32_t s0 = sb + OFF_V + (tile & 1) * 2 * V_TILE;
+      load_v_tile(s0, Vg[0], tile * BN);
+      load_v_tile(s0 + V_TILE, Vg[1], tile * BN);
+    }
+    cp_async_commit_group();
+  };
+  const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 16);
+  auto issue_s = [&](uint32_t tS, int tile) {  // thread 0 only
+    const uint32_t sK = sb + OFF_K + (tile & 1) * 2 * QK_TILE;
+    const uint64_t qh = make_desc(sb + OFF_Q, LBO_QK, 128), ql = make_desc(sb + OFF_Q + QK_TILE, LBO_QK, 128);
+    const uint64_t kh = make_desc(sK, LBO_QK, 128), kl = make_desc(sK + QK_TILE, LBO_QK, 128);
+    mma_f16_ss(tS, ql, kh, idesc_s, 0u);
+    mma_f16_ss(tS, qh, kl, idesc_s, 1u);
+    mma_f16_ss(tS, qh, kh, idesc_s, 1u);
+    commit(bar_s);
+  };
+
   load_qk_tile(sb + OFF_Q, Qg[0], q0);
   load_qk_tile(sb + OFF_Q + QK_TILE, Qg[1], q0);
-  const int ntiles = (N + BN - 1) / BN;
-  load_kv(0, 0);  // (same cp.async group as Q)
-
+  load_k(0);   // group: Q + K(0)
+  load_v(0);
+  load_k(1);
+  cp_async_wait_group<0>();
+  fence_proxy_async();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
   const uint32_t trow = ((uint32_t)(warp * 32)) << 16;
-  const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 16);
   const uint32_t prow = sb + OFF_P + (tid >> 3) * 128 + (tid & 7) * 16;  // this thread's row inside every P chunk
+  if (tid == 0) issue_s(tS, 0);
 
   float o[16];
 #pragma unroll
   for (int d = 0; d < 16; ++d) o[d] = 0.f;
-  float m = -1e30f, l = 0.f;
+  float m = -1e30f, l = 0.f, corr_prev = 1.0f;
 
   for (int j = 0; j < ntiles; ++j) {
-    const int st = j & 1;
-    if (j + 1 < ntiles) { load_kv(j + 1, st ^ 1); cp_async_wait_group<1>(); }
-    else cp_async_wait_group<0>();
+    // ---- 1. S(j) -> registers (single wait)
+    mbar_wait(bar_s, (uint32_t)(j & 1));
+    tc_fence_after_sync();
+    uint32_t sr[4][32];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld32_nowait(tS + trow + c * 32, sr[c]);
+    tmem_ld_wait();
+    // ---- 2. K(j+2) prefetch; S(j+1) starts as soon as everybody has S(j) in registers
+    load_k(j + 2);
+    cp_async_wait_group<1>();   // K(j+1) and V(j) have landed
     fence_proxy_async();
     tc_fence_before_sync();
     __syncthreads();
-    const uint32_t sK = sb + OFF_KV + st * KV_STAGE, sV = sK + 2 * QK_TILE;
-    if (tid == 0) {
-      tc_fence_after_sync();
-      const uint64_t qh = make_desc(sb + OFF_Q, LBO_QK, 128), ql = make_desc(sb + OFF_Q + QK_TILE, LBO_QK, 128);
-      const uint64_t kh = make_desc(sK, LBO_QK, 128), kl = make_desc(sK + QK_TILE, LBO_QK, 128);
-      mma_f16_ss(tS, ql, kh, idesc_s, 0u);
-      mma_f16_ss(tS, qh, kl, idesc_s, 1u);
-      mma_f16_ss(tS, qh, kh, idesc_s, 1u);
-      commit(bar_s);
-    }
-    mbar_wait(bar_s, (uint32_t)(j & 1));
-    tc_fence_after_sync();
-
-    // ---- pass 1: row maximum
+    if (tid == 0 && j + 1 < ntiles) { tc_fence_after_sync(); issue_s(tS, j + 1); }
+    // ---- 3. row maximum, fold O_tile(j-1)
     const int kbase = j * BN;
     const bool tail = (kbase + BN > N);
     float mx = m;
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      float v[16];
-      tmem_ld16(tS + trow + c * 16, v);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        float sv = (tail && kbase + c * 16 + e >= N) ? -1e30f : v[e];
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        float sv = __uint_as_float(sr[c][e]);
+        if (tail && kbase + c * 32 + e >= N) { sv = -1e30f; sr[c][e] = __float_as_uint(sv); }
         mx = fmaxf(mx, sv);
       }
-    }
     const float corr = ex2f(m - mx);
     m = mx;
     l *= corr;
-    // ---- pass 2: P = exp2(S - m), hi/lo split -> shared memory (A operand of P*V)
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      float v[16];
-      tmem_ld16(tS + trow + c * 16, v);
-      __align__(16) __half2 ph[8], pl[8];
+    if (j > 0) {
+      mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
+      tc_fence_after_sync();
+      float ot[16];
+      tmem_ld16(tO + trow, ot);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float s0 = v[2 * e], s1 = v[2 * e + 1];
-        if (tail) {
-          if (kbase + c * 16 + 2 * e >= N) s0 = -1e30f;
-          if (kbase + c * 16 + 2 * e + 1 >= N) s1 = -1e30f;
-        }
-        const float p0 = ex2f(s0 - m), p1 = ex2f(s1 - m);
+      for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], corr_prev, ot[d]);
+    }
+    corr_prev = corr;
+    load_v(j + 1);   // its stage held V(j-1), released by the P*V product we just waited for
+    // ---- 4. P = exp2(S - m), hi/lo split -> shared memory (A operand of P*V); chunk = 8 keys
+#pragma unroll
+    for (int c8 = 0; c8 < 16; ++c8) {
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = c8 * 8 + 2 * e;
+        const float p0 = ex2f(__uint_as_float(sr[col >> 5][col & 31]) - m);
+        const float p1 = ex2f(__uint_as_float(sr[(col + 1) >> 5][(col + 1) & 31]) - m);
         l += p0 + p1;
         const __half2 hh = __floats2half2_rn(p0, p1);
         const float2 hf = __half22float2(hh);
-        ph[e] = hh;
-        pl[e] = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+        const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+        ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
       }
-      // 16 keys = chunks 2c and 2c+1 of this row
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (2 * c) * LBO_P), "r"(*reinterpret_cast<uint32_t*>(&ph[0])),
-                   "r"(*reinterpret_cast<uint32_t*>(&ph[1])), "r"(*reinterpret_cast<uint32_t*>(&ph[2])), "r"(*reinterpret_cast<uint32_t*>(&ph[3])) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (2 * c + 1) * LBO_P), "r"(*reinterpret_cast<uint32_t*>(&ph[4])),
-                   "r"(*reinterpret_cast<uint32_t*>(&ph[5])), "r"(*reinterpret_cast<uint32_t*>(&ph[6])), "r"(*reinterpret_cast<uint32_t*>(&ph[7])) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + P_TILE + (2 * c) * LBO_P), "r"(*reinterpret_cast<uint32_t*>(&pl[0])),
-                   "r"(*reinterpret_cast<uint32_t*>(&pl[1])), "r"(*reinterpret_cast<uint32_t*>(&pl[2])), "r"(*reinterpret_cast<uint32_t*>(&pl[3])) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + P_TILE + (2 * c + 1) * LBO_P), "r"(*reinterpret_cast<uint32_t*>(&pl[4])),
-                   "r"(*reinterpret_cast<uint32_t*>(&pl[5])), "r"(*reinterpret_cast<uint32_t*>(&pl[6])), "r"(*reinterpret_cast<uint32_t*>(&pl[7])) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + c8 * LBO_P), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + P_TILE + c8 * LBO_P), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
     }
+    // ---- 5. O_tile(j) = P(j) V(j)
     fence_proxy_async();
     tc_fence_before_sync();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after_sync();
+      const uint32_t sV = sb + OFF_V + (j & 1) * 2 * V_TILE;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint64_t pH = make_desc(sb + OFF_P + 2 * i * LBO_P, LBO_P, 128);
@@ -308,15 +324,16 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
       }
       commit(bar_o);
     }
-    mbar_wait(bar_o, (uint32_t)(j & 1));
-    tc_fence_after_sync();
-    {
-      float ot[16];
-      tmem_ld16(tO + trow, ot);
-#pragma unroll
-      for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], corr, ot[d]);
-    }
   }
+  {  // fold the last tile
+    mbar_wait(bar_o, (uint32_t)((ntiles - 1) & 1));
+    tc_fence_after_sync();
+    float ot[16];
+    tmem_ld16(tO + trow, ot);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], corr_prev, ot[d]);
+  }
+  cp_async_wait_group<0>();
 
   const int r = q0 + tid;
   if (r < N) {
