@@ -94,15 +94,15 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
 }
+// split layout: 6 planes of 4*16*Np halves (Np = N rounded up to 8): 0 Qh, 1 Ql, 2 Kh, 3 Kl as [4 heads][Np][16];
+// 4 Vh, 5 Vl TRANSPOSED per head as [4 heads][16 dims][Np] (keys contiguous: K-major B operand of the tcgen05 P*V
+// product).  Pad keys [N, Np) of V are zero.
 __global__ void qkv_split_kernel(const float* __restrict__ qkv, __half* __restrict__ split, int N, int Np, float qscale) {
-  // split layout, planes of 4*Np*16 halves (Np = N rounded up to 8): 0 Qh, 1 Ql, 2 Kh, 3 Kl as [4 heads][Np][16];
-  // 4 Vh, 5 Vl TRANSPOSED per head as [4 heads][16 dims][Np] (keys contiguous: K-major B operand of the tcgen05 P*V
-  // product); the pad keys [N, Np) of V are written as zeros.
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // (token, which(q/k/v), head, quad of 4 dims)
   int total = Np * 3 * 4 * 4;
   if (i >= total) return;
   int quad = i & 3, h = (i >> 2) & 3, which = (i >> 4) % 3, tok = i / 48;
-  const size_t plane = (size_t)4 * Np * 16;
+  const size_t plane = (size_t)4 * 16 * Np;
   if (tok >= N) {
     if (which == 2) {
       __half* th = split + (size_t)4 * plane + ((size_t)h * 16 + quad * 4) * Np + tok;
@@ -128,7 +128,6 @@ __global__ void qkv_split_kernel(const float* __restrict__ qkv, __half* __restri
   ph[0] = __halves2half2(hi[0], hi[1]); ph[1] = __halves2half2(hi[2], hi[3]);
   pl[0] = __halves2half2(lo[0], lo[1]); pl[1] = __halves2half2(lo[2], lo[3]);
 }
-
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -148,33 +147,39 @@ __device__ __forceinline__ float ex2f(float x) {
 // ------------------------------------------------------------------------------------------------------------------
 namespace fa5 {
 using namespace umma;
-constexpr int BM = 128, BN = 128;
+constexpr int BM = 128, BN = 128, THREADS = 256;
 constexpr uint32_t LBO_QK = 16 * 128 + 16;   // 2 chunks (hd = 16) x 128 rows
 constexpr uint32_t QK_TILE = 2 * LBO_QK;
 constexpr uint32_t LBO_P = 16 * 128;         // 16 chunks (128 keys) x 128 rows
 constexpr uint32_t P_TILE = 16 * LBO_P;      // 32 KB
-constexpr uint32_t LBO_V = 2 * 128 + 16;     // 16 chunks (128 keys) x 16 rows (dims)
+constexpr uint32_t LBO_V = 2 * 128 + 16;     // 16 chunks (128 keys) x 16 rows (head dims)
 constexpr uint32_t V_TILE = 16 * LBO_V;
-// Q (hi,lo) | K ring 2 x (hi,lo) | V^T ring 2 x (hi,lo) | P (hi,lo) | barriers
+// Q (hi,lo) | K ring 2 x (hi,lo) | V^T ring 2 x (hi,lo) | P (hi,lo) | row-max exchange [2][128] | barriers
 constexpr uint32_t OFF_Q = 0, OFF_K = 2 * QK_TILE, OFF_V = OFF_K + 4 * QK_TILE, OFF_P = OFF_V + 4 * V_TILE,
-                   OFF_BAR = OFF_P + 2 * P_TILE;
+                   OFF_X = OFF_P + 2 * P_TILE, OFF_BAR = OFF_X + 1024;
 constexpr uint32_t SMEM = OFF_BAR + 64;
 }  // namespace fa5
 
-__global__ void __launch_bounds__(128, 2)
+// 256 threads: thread (warp w, lane) owns query row (w%4)*32+lane and the key columns [64*(w/4), 64*(w/4)+64) of each
+// tile; the two threads of a row exchange their partial row maxima through shared memory.  The normaliser l is summed
+// per tile and folded like the outputs (l = l*corr + tile_sum): a single running fp32 sum over 27k keys is 5x noisier.
+__global__ void __launch_bounds__(256, 2)
 attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, __half* __restrict__ out2, int N, int Np) {
   using namespace fa5;
   extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;                       // which 64 key columns of a tile
+  const int row = (warp & 3) * 32 + lane;           // query row == TMEM lane
   const int h = blockIdx.y;
   const int q0 = blockIdx.x * BM;
-  const size_t plane = (size_t)4 * Np * 16;
+  const size_t plane = (size_t)4 * 16 * Np;
   const __half* Qg[2] = {split + 0 * plane + (size_t)h * Np * 16, split + 1 * plane + (size_t)h * Np * 16};
   const __half* Kg[2] = {split + 2 * plane + (size_t)h * Np * 16, split + 3 * plane + (size_t)h * Np * 16};
   const __half* Vg[2] = {split + 4 * plane + (size_t)h * 16 * Np, split + 5 * plane + (size_t)h * 16 * Np};  // [16][Np]
   const uint32_t sb = smem_u32(smem);
   const uint32_t bar_s = sb + OFF_BAR, bar_o = sb + OFF_BAR + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 32);
+  volatile float* xchg = reinterpret_cast<volatile float*>(smem + OFF_X);  // [2][128]
 
   if (tid == 0) {
     mbar_init(bar_s, 1);
@@ -184,15 +189,13 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
   if (warp == 0) tmem_alloc(sb + OFF_BAR + 32, 256);
 
   auto load_qk_tile = [&](uint32_t dst, const __half* g, int row0) {  // 128 rows x 2 chunks, zero fill beyond N
-    for (int idx = tid; idx < 256; idx += 128) {
-      int r = idx >> 1, c = idx & 1;
-      bool ok = row0 + r < N;
-      cp_async16_zfill(dst + c * LBO_QK + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)(ok ? row0 + r : 0) * 16 + c * 8, ok);
-    }
+    int r = tid >> 1, c = tid & 1;
+    bool ok = row0 + r < N;
+    cp_async16_zfill(dst + c * LBO_QK + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)(ok ? row0 + r : 0) * 16 + c * 8, ok);
   };
   auto load_v_tile = [&](uint32_t dst, const __half* g, int key0) {   // 16 rows (dims) x 16 chunks of 8 keys
-    for (int idx = tid; idx < 256; idx += 128) {
-      int r = idx >> 4, c = idx & 15;
+    {
+      int r = tid >> 4, c = tid & 15;
       bool ok = key0 + c * 8 < Np;  // rows are padded to Np (multiple of 8) with zeros: chunks are whole
       cp_async16_zfill(dst + c * LBO_V + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)r * Np + (ok ? key0 + c * 8 : 0), ok);
     }
@@ -237,23 +240,35 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
-  const uint32_t trow = ((uint32_t)(warp * 32)) << 16;
-  const uint32_t prow = sb + OFF_P + (tid >> 3) * 128 + (tid & 7) * 16;  // this thread's row inside every P chunk
+  const uint32_t trow = ((uint32_t)((warp & 3) * 32)) << 16;
+  const uint32_t prow = sb + OFF_P + (row >> 3) * 128 + (row & 7) * 16;  // this thread's row inside every P chunk
   if (tid == 0) issue_s(tS, 0);
 
-  float o[16];
+  float o[8];   // this thread's 8 of the 16 head dims: dims [8*half, 8*half+8)
 #pragma unroll
-  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+  for (int d = 0; d < 8; ++d) o[d] = 0.f;
   float m = -1e30f, l = 0.f, corr_prev = 1.0f;
 
   for (int j = 0; j < ntiles; ++j) {
-    // ---- 1. S(j) -> registers (single wait)
+    // ---- 1. this thread's 64 columns of S(j) -> registers (single wait), partial row maximum -> exchange buffer
     mbar_wait(bar_s, (uint32_t)(j & 1));
     tc_fence_after_sync();
-    uint32_t sr[4][32];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld32_nowait(tS + trow + c * 32, sr[c]);
+    uint32_t sr[2][32];
+    tmem_ld32_nowait(tS + trow + half * 64, sr[0]);
+    tmem_ld32_nowait(tS + trow + half * 64 + 32, sr[1]);
     tmem_ld_wait();
+    const int kbase = j * BN + half * 64;
+    const bool tail = (j * BN + BN > N);
+    float pmax = -1e30f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        float sv = __uint_as_float(sr[c][e]);
+        if (tail && kbase + c * 32 + e >= N) { sv = -1e30f; sr[c][e] = __float_as_uint(sv); }
+        pmax = fmaxf(pmax, sv);
+      }
+    xchg[half * 128 + row] = pmax;
     // ---- 2. K(j+2) prefetch; S(j+1) starts as soon as everybody has S(j) in registers
     load_k(j + 2);
     cp_async_wait_group<1>();   // K(j+1) and V(j) have landed
@@ -262,49 +277,41 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
     __syncthreads();
     if (tid == 0 && j + 1 < ntiles) { tc_fence_after_sync(); issue_s(tS, j + 1); }
     // ---- 3. row maximum, fold O_tile(j-1)
-    const int kbase = j * BN;
-    const bool tail = (kbase + BN > N);
-    float mx = m;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        float sv = __uint_as_float(sr[c][e]);
-        if (tail && kbase + c * 32 + e >= N) { sv = -1e30f; sr[c][e] = __float_as_uint(sv); }
-        mx = fmaxf(mx, sv);
-      }
+    const float mx = fmaxf(m, fmaxf(pmax, xchg[(half ^ 1) * 128 + row]));
     const float corr = ex2f(m - mx);
     m = mx;
-    l *= corr;
     if (j > 0) {
       mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
       tc_fence_after_sync();
       float ot[16];
       tmem_ld16(tO + trow, ot);
 #pragma unroll
-      for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], corr_prev, ot[d]);
+      for (int d = 0; d < 8; ++d) o[d] = fmaf(o[d], corr_prev, half ? ot[8 + d] : ot[d]);
     }
     corr_prev = corr;
+    float tsum = 0.f;
     load_v(j + 1);   // its stage held V(j-1), released by the P*V product we just waited for
     // ---- 4. P = exp2(S - m), hi/lo split -> shared memory (A operand of P*V); chunk = 8 keys
 #pragma unroll
-    for (int c8 = 0; c8 < 16; ++c8) {
+    for (int c8 = 0; c8 < 8; ++c8) {
       uint32_t ph[4], pl[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int col = c8 * 8 + 2 * e;
         const float p0 = ex2f(__uint_as_float(sr[col >> 5][col & 31]) - m);
         const float p1 = ex2f(__uint_as_float(sr[(col + 1) >> 5][(col + 1) & 31]) - m);
-        l += p0 + p1;
+        tsum += p0 + p1;
         const __half2 hh = __floats2half2_rn(p0, p1);
         const float2 hf = __half22float2(hh);
         const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
         ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
         pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
       }
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + c8 * LBO_P), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + P_TILE + c8 * LBO_P), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+      const uint32_t dst = prow + (half * 8 + c8) * LBO_P;
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + P_TILE), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
     }
+    l = fmaf(l, corr, tsum);
     // ---- 5. O_tile(j) = P(j) V(j)
     fence_proxy_async();
     tc_fence_before_sync();
@@ -331,28 +338,26 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
     float ot[16];
     tmem_ld16(tO + trow, ot);
 #pragma unroll
-    for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], corr_prev, ot[d]);
+    for (int d = 0; d < 8; ++d) o[d] = fmaf(o[d], corr_prev, half ? ot[8 + d] : ot[d]);
   }
   cp_async_wait_group<0>();
+  // the two threads of a row summed disjoint key columns: combine the normalisers
+  xchg[half * 128 + row] = l;
+  __syncthreads();
+  l += xchg[(half ^ 1) * 128 + row];
 
-  const int r = q0 + tid;
+  const int r = q0 + row;
   if (r < N) {
     const float inv = __fdiv_rn(1.0f, l);
-    float res[16];
+    float res[8];
 #pragma unroll
-    for (int d = 0; d < 16; ++d) res[d] = o[d] * inv;
+    for (int d = 0; d < 8; ++d) res[d] = o[d] * inv;
+    const int col = h * 16 + half * 8;
     if (out) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(out + (size_t)r * 64 + h * 16 + c * 4) = make_float4(res[c * 4], res[c * 4 + 1], res[c * 4 + 2], res[c * 4 + 3]);
+      *reinterpret_cast<float4*>(out + (size_t)r * 64 + col) = make_float4(res[0], res[1], res[2], res[3]);
+      *reinterpret_cast<float4*>(out + (size_t)r * 64 + col + 4) = make_float4(res[4], res[5], res[6], res[7]);
     }
-    if (out2) {
-      float v0[8], v1[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { v0[e] = res[e]; v1[e] = res[8 + e]; }
-      split_store8(out2 + (size_t)r * 128 + h * 16, out2 + (size_t)r * 128 + 64 + h * 16, v0);
-      split_store8(out2 + (size_t)r * 128 + h * 16 + 8, out2 + (size_t)r * 128 + 64 + h * 16 + 8, v1);
-    }
+    if (out2) split_store8(out2 + (size_t)r * 128 + col, out2 + (size_t)r * 128 + 64 + col, res);
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -402,7 +407,7 @@ static int run_attention(const float* qkv, float* o, __half* o2, __half* split, 
     MVSF_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa5::SMEM));
     configured = true;
   }
-  attention_tc_kernel<<<dim3(cdiv(N, fa5::BM), 4), 128, fa5::SMEM, s>>>(split, o, o2, N, Np);
+  attention_tc_kernel<<<dim3(cdiv(N, fa5::BM), 4), fa5::THREADS, fa5::SMEM, s>>>(split, o, o2, N, Np);
   MVSF_LAUNCH_CHECK("attention_tc");
   return MVSF_OK;
 }
