@@ -257,17 +257,19 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
     tmem_ld32_nowait(tS + trow + half * 64, sr[0]);
     tmem_ld32_nowait(tS + trow + half * 64 + 32, sr[1]);
     tmem_ld_wait();
-    const int kbase = j * BN + half * 64;
-    const bool tail = (j * BN + BN > N);
+    if (j * BN + BN > N) {  // last, partial tile only (uniform branch): keys >= N never win the max and get P = 0
+      const int kbase = j * BN + half * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (kbase + c * 32 + e >= N) sr[c][e] = 0xf149f2caU;  // -1e30f
+    }
     float pmax = -1e30f;
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        float sv = __uint_as_float(sr[c][e]);
-        if (tail && kbase + c * 32 + e >= N) { sv = -1e30f; sr[c][e] = __float_as_uint(sv); }
-        pmax = fmaxf(pmax, sv);
-      }
+      for (int e = 0; e < 32; ++e) pmax = fmaxf(pmax, __uint_as_float(sr[c][e]));
     xchg[half * 128 + row] = pmax;
     // ---- 2. K(j+2) prefetch; S(j+1) starts as soon as everybody has S(j) in registers
     load_k(j + 2);
