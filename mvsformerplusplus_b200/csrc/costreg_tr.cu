@@ -147,249 +147,223 @@ __device__ __forceinline__ float ex2f(float x) {
 // ------------------------------------------------------------------------------------------------------------------
 namespace fa5 {
 using namespace umma;
-constexpr int BM = 128, BN = 128, NSOFT = 256, THREADS = NSOFT + 32;
+constexpr int BM = 128, BN = 128, THREADS = 256;
 constexpr uint32_t LBO_QK = 16 * 128 + 16;   // 2 chunks (hd = 16) x 128 rows
 constexpr uint32_t QK_TILE = 2 * LBO_QK;
 constexpr uint32_t LBO_P = 16 * 128;         // 16 chunks (128 keys) x 128 rows
 constexpr uint32_t P_TILE = 16 * LBO_P;      // 32 KB
 constexpr uint32_t LBO_V = 2 * 128 + 16;     // 16 chunks (128 keys) x 16 rows (head dims)
 constexpr uint32_t V_TILE = 16 * LBO_V;
-// Q (hi,lo) | K ring 2 x (hi,lo) | V^T ring 2 x (hi,lo) | P (hi,lo) | row-max exchange [2 tiles][2][128] | barriers
+// Q (hi,lo) | K ring 2 x (hi,lo) | V^T ring 2 x (hi,lo) | P (hi,lo) | row-max exchange [2][128] | barriers
 constexpr uint32_t OFF_Q = 0, OFF_K = 2 * QK_TILE, OFF_V = OFF_K + 4 * QK_TILE, OFF_P = OFF_V + 4 * V_TILE,
-                   OFF_X = OFF_P + 2 * P_TILE, OFF_BAR = OFF_X + 2048;
+                   OFF_X = OFF_P + 2 * P_TILE, OFF_BAR = OFF_X + 1024;
 constexpr uint32_t SMEM = OFF_BAR + 64;
 }  // namespace fa5
 
-// Warp roles (288 threads, 2 CTAs per SM):
-//   warps 0-7  softmax: thread (w, lane) owns query row (w%4)*32+lane (= TMEM lane) and key columns [64*(w/4), +64) of
-//              every tile; the two threads of a row exchange partial row maxima through shared memory;
-//   warp 8     K / V^T tile loads (cp.async) and all tcgen05.mma issue (lane 0).
-// mbarriers:  bar_s  (tcgen05.commit) S(j) ready            bar_sfree (256 arrivals) S(j) copied to registers
-//             bar_p  (256 arrivals)  P(j) written + fenced   bar_o     (tcgen05.commit) O_tile(j) = P(j) V(j) ready
-// The normaliser l is summed per tile and folded like the outputs (l = l*corr + tile_sum): one running fp32 sum over
-// 27k keys is 5x noisier.  Tensor-core accumulators truncate, hence per-tile accumulators + round-to-nearest folds.
-__global__ void __launch_bounds__(288, 2)
+// 256 threads: thread (warp w, lane) owns query row (w%4)*32+lane and the key columns [64*(w/4), 64*(w/4)+64) of each
+// tile; the two threads of a row exchange their partial row maxima through shared memory.  The normaliser l is summed
+// per tile and folded like the outputs (l = l*corr + tile_sum): a single running fp32 sum over 27k keys is 5x noisier.
+__global__ void __launch_bounds__(256, 2)
 attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, __half* __restrict__ out2, int N, int Np) {
   using namespace fa5;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;                       // which 64 key columns of a tile
+  const int row = (warp & 3) * 32 + lane;           // query row == TMEM lane
   const int h = blockIdx.y;
   const int q0 = blockIdx.x * BM;
   const size_t plane = (size_t)4 * 16 * Np;
+  const __half* Qg[2] = {split + 0 * plane + (size_t)h * Np * 16, split + 1 * plane + (size_t)h * Np * 16};
+  const __half* Kg[2] = {split + 2 * plane + (size_t)h * Np * 16, split + 3 * plane + (size_t)h * Np * 16};
+  const __half* Vg[2] = {split + 4 * plane + (size_t)h * 16 * Np, split + 5 * plane + (size_t)h * 16 * Np};  // [16][Np]
   const uint32_t sb = smem_u32(smem);
-  const uint32_t bar_s = sb + OFF_BAR, bar_o = sb + OFF_BAR + 8, bar_sfree = sb + OFF_BAR + 16, bar_p = sb + OFF_BAR + 24;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 48);
-  const int ntiles = (N + BN - 1) / BN;
+  const uint32_t bar_s = sb + OFF_BAR, bar_o = sb + OFF_BAR + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 32);
+  volatile float* xchg = reinterpret_cast<volatile float*>(smem + OFF_X);  // [2][128]
 
   if (tid == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
-    mbar_init(bar_sfree, NSOFT);
-    mbar_init(bar_p, NSOFT);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(sb + OFF_BAR + 48, 256);
+  if (warp == 0) tmem_alloc(sb + OFF_BAR + 32, 256);
+
+  auto load_qk_tile = [&](uint32_t dst, const __half* g, int row0) {  // 128 rows x 2 chunks, zero fill beyond N
+    int r = tid >> 1, c = tid & 1;
+    bool ok = row0 + r < N;
+    cp_async16_zfill(dst + c * LBO_QK + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)(ok ? row0 + r : 0) * 16 + c * 8, ok);
+  };
+  auto load_v_tile = [&](uint32_t dst, const __half* g, int key0) {   // 16 rows (dims) x 16 chunks of 8 keys
+    {
+      int r = tid >> 4, c = tid & 15;
+      bool ok = key0 + c * 8 < Np;  // rows are padded to Np (multiple of 8) with zeros: chunks are whole
+      cp_async16_zfill(dst + c * LBO_V + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)r * Np + (ok ? key0 + c * 8 : 0), ok);
+    }
+  };
+  const int ntiles = (N + BN - 1) / BN;
+  auto load_k = [&](int tile) {  // always commits a group (possibly empty) to keep the group accounting uniform
+    if (tile < ntiles) {
+      const uint32_t s0 = sb + OFF_K + (tile & 1) * 2 * QK_TILE;
+      load_qk_tile(s0, Kg[0], tile * BN);
+      load_qk_tile(s0 + QK_TILE, Kg[1], tile * BN);
+    }
+    cp_async_commit_group();
+  };
+  auto load_v = [&](int tile) {
+    if (tile < ntiles) {
+      const uint32_t s0 = sb + OFF_V + (tile & 1) * 2 * V_TILE;
+      load_v_tile(s0, Vg[0], tile * BN);
+      load_v_tile(s0 + V_TILE, Vg[1], tile * BN);
+    }
+    cp_async_commit_group();
+  };
+  const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 16);
+  auto issue_s = [&](uint32_t tS, int tile) {  // thread 0 only
+    const uint32_t sK = sb + OFF_K + (tile & 1) * 2 * QK_TILE;
+    const uint64_t qh = make_desc(sb + OFF_Q, LBO_QK, 128), ql = make_desc(sb + OFF_Q + QK_TILE, LBO_QK, 128);
+    const uint64_t kh = make_desc(sK, LBO_QK, 128), kl = make_desc(sK + QK_TILE, LBO_QK, 128);
+    mma_f16_ss(tS, ql, kh, idesc_s, 0u);
+    mma_f16_ss(tS, qh, kl, idesc_s, 1u);
+    mma_f16_ss(tS, qh, kh, idesc_s, 1u);
+    commit(bar_s);
+  };
+
+  load_qk_tile(sb + OFF_Q, Qg[0], q0);
+  load_qk_tile(sb + OFF_Q + QK_TILE, Qg[1], q0);
+  load_k(0);   // group: Q + K(0)
+  load_v(0);
+  load_k(1);
+  cp_async_wait_group<0>();
+  fence_proxy_async();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t trow = ((uint32_t)((warp & 3) * 32)) << 16;
+  const uint32_t prow = sb + OFF_P + (row >> 3) * 128 + (row & 7) * 16;  // this thread's row inside every P chunk
+  if (tid == 0) issue_s(tS, 0);
 
-  if (warp == 8) {
-    // ------------------------------------------------------------------ loader + MMA warp
-    const __half* Qg[2] = {split + 0 * plane + (size_t)h * Np * 16, split + 1 * plane + (size_t)h * Np * 16};
-    const __half* Kg[2] = {split + 2 * plane + (size_t)h * Np * 16, split + 3 * plane + (size_t)h * Np * 16};
-    const __half* Vg[2] = {split + 4 * plane + (size_t)h * 16 * Np, split + 5 * plane + (size_t)h * 16 * Np};  // [16][Np]
-    auto load_qk_tile = [&](uint32_t dst, const __half* g, int row0) {  // 128 rows x 2 chunks, zero fill beyond N
-      for (int idx = lane; idx < 256; idx += 32) {
-        int r = idx >> 1, c = idx & 1;
-        bool ok = row0 + r < N;
-        cp_async16_zfill(dst + c * LBO_QK + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)(ok ? row0 + r : 0) * 16 + c * 8, ok);
-      }
-    };
-    auto load_v_tile = [&](uint32_t dst, const __half* g, int key0) {   // 16 rows (dims) x 16 chunks of 8 keys
-      for (int idx = lane; idx < 256; idx += 32) {
-        int r = idx >> 4, c = idx & 15;
-        bool ok = key0 + c * 8 < Np;  // rows are padded to Np (multiple of 8) with zeros: chunks are whole
-        cp_async16_zfill(dst + c * LBO_V + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)r * Np + (ok ? key0 + c * 8 : 0), ok);
-      }
-    };
-    auto load_k = [&](int tile) {  // always commits a group (possibly empty): uniform group accounting
-      if (tile < ntiles) {
-        const uint32_t s0 = sb + OFF_K + (tile & 1) * 2 * QK_TILE;
-        load_qk_tile(s0, Kg[0], tile * BN);
-        load_qk_tile(s0 + QK_TILE, Kg[1], tile * BN);
-      }
-      cp_async_commit_group();
-    };
-    auto load_v = [&](int tile) {
-      if (tile < ntiles) {
-        const uint32_t s0 = sb + OFF_V + (tile & 1) * 2 * V_TILE;
-        load_v_tile(s0, Vg[0], tile * BN);
-        load_v_tile(s0 + V_TILE, Vg[1], tile * BN);
-      }
-      cp_async_commit_group();
-    };
-    const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 16);
-    auto issue_s = [&](int tile) {  // lane 0
-      const uint32_t sK = sb + OFF_K + (tile & 1) * 2 * QK_TILE;
-      const uint64_t qh = make_desc(sb + OFF_Q, LBO_QK, 128), ql = make_desc(sb + OFF_Q + QK_TILE, LBO_QK, 128);
-      const uint64_t kh = make_desc(sK, LBO_QK, 128), kl = make_desc(sK + QK_TILE, LBO_QK, 128);
-      mma_f16_ss(tS, ql, kh, idesc_s, 0u);
-      mma_f16_ss(tS, qh, kl, idesc_s, 1u);
-      mma_f16_ss(tS, qh, kh, idesc_s, 1u);
-      commit(bar_s);
-    };
-    load_qk_tile(sb + OFF_Q, Qg[0], q0);
-    load_qk_tile(sb + OFF_Q + QK_TILE, Qg[1], q0);
-    load_k(0);   // group 0: Q + K(0)
-    load_v(0);   // group 1
-    load_k(1);   // group 2
-    cp_async_wait_group<0>();
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) issue_s(0);
-    for (int j = 0; j < ntiles; ++j) {
-      // S(j+1): needs K(j+1) (landed: waited below / prologue) and S(j) copied out of TMEM by every softmax thread
-      mbar_wait(bar_sfree, (uint32_t)(j & 1));
-      if (j + 1 < ntiles) {
-        tc_fence_after_sync();
-        if (lane == 0) issue_s(j + 1);
-      }
-      __syncwarp();
-      // P(j) V(j): needs V(j) (landed) and P(j) in shared memory
-      mbar_wait(bar_p, (uint32_t)(j & 1));
-      tc_fence_after_sync();
-      if (lane == 0) {
-        const uint32_t sV = sb + OFF_V + (j & 1) * 2 * V_TILE;
+  float o[8];   // this thread's 8 of the 16 head dims: dims [8*half, 8*half+8)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint64_t pH = make_desc(sb + OFF_P + 2 * i * LBO_P, LBO_P, 128);
-          const uint64_t pL = make_desc(sb + OFF_P + P_TILE + 2 * i * LBO_P, LBO_P, 128);
-          const uint64_t vH = make_desc(sV + 2 * i * LBO_V, LBO_V, 128);
-          const uint64_t vL = make_desc(sV + V_TILE + 2 * i * LBO_V, LBO_V, 128);
-          mma_f16_ss(tO, pL, vH, idesc_o, i > 0 ? 1u : 0u);
-          mma_f16_ss(tO, pH, vL, idesc_o, 1u);
-          mma_f16_ss(tO, pH, vH, idesc_o, 1u);
-        }
-        commit(bar_o);
-      }
-      __syncwarp();
-      // refill: K(j+2) -> stage of K(j) (S(j) finished: its result was already consumed);
-      //         V(j+1) -> stage of V(j-1), free once P(j-1) V(j-1) has completed
-      load_k(j + 2);
-      load_v(j + 1);   // P(j) arrived => every softmax thread has already seen P(j-1) V(j-1) complete: the stage is free
-      cp_async_wait_group<0>();   // K(j+2), V(j+1) landed (needed one iteration from now)
-      fence_proxy_async();
-      __syncwarp();
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax warps
-    const int half = warp >> 2;                       // which 64 key columns of a tile
-    const int row = (warp & 3) * 32 + lane;           // query row == TMEM lane
-    const uint32_t trow = ((uint32_t)((warp & 3) * 32)) << 16;
-    const uint32_t prow = sb + OFF_P + (row >> 3) * 128 + (row & 7) * 16;  // this thread's row inside every P chunk
-    volatile float* xchg = reinterpret_cast<volatile float*>(smem + OFF_X);  // [2][2][128]
-    float o[8];   // this thread's 8 of the 16 head dims: dims [8*half, 8*half+8)
-#pragma unroll
-    for (int d = 0; d < 8; ++d) o[d] = 0.f;
-    float m = -1e30f, l = 0.f, corr_prev = 1.0f;
+  for (int d = 0; d < 8; ++d) o[d] = 0.f;
+  float m = -1e30f, l = 0.f, corr_prev = 1.0f;
 
-    for (int j = 0; j < ntiles; ++j) {
-      // ---- 1. this thread's 64 columns of S(j) -> registers (single wait), partial row maximum -> exchange buffer
-      mbar_wait(bar_s, (uint32_t)(j & 1));
-      tc_fence_after_sync();
-      uint32_t sr[2][32];
-      tmem_ld32_nowait(tS + trow + half * 64, sr[0]);
-      tmem_ld32_nowait(tS + trow + half * 64 + 32, sr[1]);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      mbar_arrive(bar_sfree);   // S(j+1) may overwrite the TMEM tile
-      if (j * BN + BN > N) {  // last, partial tile only (uniform branch): keys >= N never win the max and get P = 0
-        const int kbase = j * BN + half * 64;
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (kbase + c * 32 + e >= N) sr[c][e] = 0xf149f2caU;  // -1e30f
-      }
-      float pmax = -1e30f;
+  for (int j = 0; j < ntiles; ++j) {
+    // ---- 1. this thread's 64 columns of S(j) -> registers (single wait), partial row maximum -> exchange buffer
+    mbar_wait(bar_s, (uint32_t)(j & 1));
+    tc_fence_after_sync();
+    uint32_t sr[2][32];
+    tmem_ld32_nowait(tS + trow + half * 64, sr[0]);
+    tmem_ld32_nowait(tS + trow + half * 64 + 32, sr[1]);
+    tmem_ld_wait();
+    if (j * BN + BN > N) {  // last, partial tile only (uniform branch): keys >= N never win the max and get P = 0
+      const int kbase = j * BN + half * 64;
 #pragma unroll
       for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int e = 0; e < 32; ++e) pmax = fmaxf(pmax, __uint_as_float(sr[c][e]));
-      xchg[(j & 1) * 256 + half * 128 + row] = pmax;   // double buffered: the partner may still be reading tile j-1's
-      named_bar_sync(1, NSOFT);
-      const float mx = fmaxf(m, fmaxf(pmax, xchg[(j & 1) * 256 + (half ^ 1) * 128 + row]));
-      const float corr = ex2f(m - mx);
-      m = mx;
-      // ---- 2. fold O_tile(j-1); after this wait the P buffer is free again
-      if (j > 0) {
-        mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
-        tc_fence_after_sync();
-        float ot[16];
-        tmem_ld16(tO + trow, ot);
-#pragma unroll
-        for (int d = 0; d < 8; ++d) o[d] = fmaf(o[d], corr_prev, half ? ot[8 + d] : ot[d]);
-      }
-      corr_prev = corr;
-      // ---- 3. P = exp2(S - m), hi/lo split -> shared memory (A operand of P*V); chunk = 8 keys
-      float tsum = 0.f;
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        uint32_t ph[4], pl[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = c8 * 8 + 2 * e;
-          const float p0 = ex2f(__uint_as_float(sr[col >> 5][col & 31]) - m);
-          const float p1 = ex2f(__uint_as_float(sr[(col + 1) >> 5][(col + 1) & 31]) - m);
-          tsum += p0 + p1;
-          const __half2 hh = __floats2half2_rn(p0, p1);
-          const float2 hf = __half22float2(hh);
-          const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
-          ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
-          pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
-        }
-        const uint32_t dst = prow + (half * 8 + c8) * LBO_P;
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + P_TILE), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
-      }
-      l = fmaf(l, corr, tsum);
-      fence_proxy_async();
-      tc_fence_before_sync();   // orders this thread's O_tile(j-1) read before the MMA warp's next P*V
-      mbar_arrive(bar_p);
+        for (int e = 0; e < 32; ++e)
+          if (kbase + c * 32 + e >= N) sr[c][e] = 0xf149f2caU;  // -1e30f
     }
-    {  // fold the last tile
-      mbar_wait(bar_o, (uint32_t)((ntiles - 1) & 1));
+    float pmax = -1e30f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int e = 0; e < 32; ++e) pmax = fmaxf(pmax, __uint_as_float(sr[c][e]));
+    xchg[half * 128 + row] = pmax;
+    // ---- 2. K(j+2) prefetch; S(j+1) starts as soon as everybody has S(j) in registers
+    load_k(j + 2);
+    cp_async_wait_group<1>();   // K(j+1) and V(j) have landed
+    fence_proxy_async();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0 && j + 1 < ntiles) { tc_fence_after_sync(); issue_s(tS, j + 1); }
+    // ---- 3. row maximum, fold O_tile(j-1)
+    const float mx = fmaxf(m, fmaxf(pmax, xchg[(half ^ 1) * 128 + row]));
+    const float corr = ex2f(m - mx);
+    m = mx;
+    if (j > 0) {
+      mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
       tc_fence_after_sync();
       float ot[16];
       tmem_ld16(tO + trow, ot);
 #pragma unroll
       for (int d = 0; d < 8; ++d) o[d] = fmaf(o[d], corr_prev, half ? ot[8 + d] : ot[d]);
     }
-    // the two threads of a row summed disjoint key columns: combine the normalisers
-    named_bar_sync(1, NSOFT);   // everybody is done with the exchange buffer
-    xchg[half * 128 + row] = l;
-    named_bar_sync(1, NSOFT);
-    l += xchg[(half ^ 1) * 128 + row];
-
-    const int r = q0 + row;
-    if (r < N) {
-      const float inv = __fdiv_rn(1.0f, l);
-      float res[8];
+    corr_prev = corr;
+    float tsum = 0.f;
+    load_v(j + 1);   // its stage held V(j-1), released by the P*V product we just waited for
+    // ---- 4. P = exp2(S - m), hi/lo split -> shared memory (A operand of P*V); chunk = 8 keys
 #pragma unroll
-      for (int d = 0; d < 8; ++d) res[d] = o[d] * inv;
-      const int col = h * 16 + half * 8;
-      if (out) {
-        *reinterpret_cast<float4*>(out + (size_t)r * 64 + col) = make_float4(res[0], res[1], res[2], res[3]);
-        *reinterpret_cast<float4*>(out + (size_t)r * 64 + col + 4) = make_float4(res[4], res[5], res[6], res[7]);
+    for (int c8 = 0; c8 < 8; ++c8) {
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = c8 * 8 + 2 * e;
+        const float p0 = ex2f(__uint_as_float(sr[col >> 5][col & 31]) - m);
+        const float p1 = ex2f(__uint_as_float(sr[(col + 1) >> 5][(col + 1) & 31]) - m);
+        tsum += p0 + p1;
+        const __half2 hh = __floats2half2_rn(p0, p1);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+        ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
       }
-      if (out2) split_store8(out2 + (size_t)r * 128 + col, out2 + (size_t)r * 128 + 64 + col, res);
+      const uint32_t dst = prow + (half * 8 + c8) * LBO_P;
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + P_TILE), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
     }
+    l = fmaf(l, corr, tsum);
+    // ---- 5. O_tile(j) = P(j) V(j)
+    fence_proxy_async();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+      const uint32_t sV = sb + OFF_V + (j & 1) * 2 * V_TILE;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint64_t pH = make_desc(sb + OFF_P + 2 * i * LBO_P, LBO_P, 128);
+        const uint64_t pL = make_desc(sb + OFF_P + P_TILE + 2 * i * LBO_P, LBO_P, 128);
+        const uint64_t vH = make_desc(sV + 2 * i * LBO_V, LBO_V, 128);
+        const uint64_t vL = make_desc(sV + V_TILE + 2 * i * LBO_V, LBO_V, 128);
+        mma_f16_ss(tO, pL, vH, idesc_o, i > 0 ? 1u : 0u);
+        mma_f16_ss(tO, pH, vL, idesc_o, 1u);
+        mma_f16_ss(tO, pH, vH, idesc_o, 1u);
+      }
+      commit(bar_o);
+    }
+  }
+  {  // fold the last tile
+    mbar_wait(bar_o, (uint32_t)((ntiles - 1) & 1));
+    tc_fence_after_sync();
+    float ot[16];
+    tmem_ld16(tO + trow, ot);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) o[d] = fmaf(o[d], corr_prev, half ? ot[8 + d] : ot[d]);
+  }
+  cp_async_wait_group<0>();
+  // the two threads of a row summed disjoint key columns: combine the normalisers
+  xchg[half * 128 + row] = l;
+  __syncthreads();
+  l += xchg[(half ^ 1) * 128 + row];
+
+  const int r = q0 + row;
+  if (r < N) {
+    const float inv = __fdiv_rn(1.0f, l);
+    float res[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) res[d] = o[d] * inv;
+    const int col = h * 16 + half * 8;
+    if (out) {
+      *reinterpret_cast<float4*>(out + (size_t)r * 64 + col) = make_float4(res[0], res[1], res[2], res[3]);
+      *reinterpret_cast<float4*>(out + (size_t)r * 64 + col + 4) = make_float4(res[4], res[5], res[6], res[7]);
+    }
+    if (out2) split_store8(out2 + (size_t)r * 128 + col, out2 + (size_t)r * 128 + 64 + col, res);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // un-patchify epilogue: u [N][256] (n = vox*8+co) -> LayerNorm3D over the 8 channels of each voxel (eps 1e-6)
