@@ -85,8 +85,11 @@ int mvsf_warp_corr_aggregate(const float* feat, const float* homs, const float* 
  *      :453-504 (kind 1: CostRegNet3D, stride (1,2,2), 1^3 prob + bias).  volume [D][H][W][C] -> logits [D][H][W].
  * wts: packed by packing.pack_costreg_unet (per layer [27][Cin][Cout] with BN scale folded, then bias[Cout]). */
 int mvsf_costreg_unet_workspace_bytes(int kind, int C, int D, int H, int W, size_t* bytes);
-int mvsf_costreg_unet_forward(int kind, const float* volume, const float* wts, float* logits, void* workspace,
-                              size_t workspace_bytes, int C, int D, int H, int W, mvsf_stream_t stream);
+/* install time: wts -> wts_tc, the fp16 hi/lo weight slabs of the tcgen05 implicit-GEMM convolutions (csrc/conv3d_tc.cu) */
+int mvsf_costreg_unet_tc_bytes(size_t* bytes);
+int mvsf_costreg_unet_pack_tc(const float* wts, void* wts_tc, size_t wts_tc_bytes, mvsf_stream_t stream);
+int mvsf_costreg_unet_forward(int kind, const float* volume, const float* wts, const void* wts_tc, float* logits,
+                              void* workspace, size_t workspace_bytes, int C, int D, int H, int W, mvsf_stream_t stream);
 
 /* ---- R1: models/module.py:602-646 PureTransformerCostReg (+ position_encoding.py:164-189 PositionEncoding3D).
  * volume [D][H][W][C] is modified in place by the PE add; pos [3][D][H][W] or NULL.

@@ -1,0 +1,429 @@
+// 3x3x3 convolutions of the U-Net cost regularisers (models/module.py:367-408 CostRegNet, :453-504 CostRegNet3D) as
+// implicit GEMMs on the 5th-generation tensor cores, fp32-class accuracy.
+//
+//   * activations live in HBM as two fp16 tensors (hi, lo; x ~= hi + lo carries 22 mantissa bits), NDHWC.  A CTA owns a
+//     tile of 16 (h) x 8*NT (w) cells of one depth slice.  Per (input depth slice, channel octet) "unit" the producers
+//     cp.async the halo of the tile into shared memory as PLANES of voxel octets: plane[row][col] = 8 channels = 16 bytes.
+//     Eight w-neighbours are then 128 contiguous bytes = one UMMA "core matrix" of the canonical no-swizzle K-major
+//     layout, the h rows are the 8-row groups (SBO = row pitch) and the hi / lo planes are the two K-chunks of a K = 16
+//     MMA (LBO = plane size).  A filter tap (kh, kw) is nothing but a different descriptor start address: no im2col;
+//   * per unit and tap two tcgen05.mma.kind::f16 (M = 128 cells, N = Cout, K = 16) are issued:
+//         [x_hi | x_lo] x [w_hi ; w_hi]   and   [x_hi | x_lo] x [w_lo ; 0]       (x_lo*w_lo ~ 2^-22 is dropped)
+//     with fp32 accumulation in TMEM; the weight slabs come pre-arranged from conv3d_tc_pack and are streamed with the
+//     unit through the same cp.async ring;
+//   * stride-(SD,2,2) convolutions keep four parity planes (even/odd h x even/odd w) so that every tap is again a dense
+//     plane access; transposed convolutions run in gather form over INPUT cells with four accumulators, one per output
+//     parity class (every (kh, kw) tap feeds exactly one class);
+//   * warps 0-3: producers, then the epilogue (one TMEM lane = one cell per thread: bias (folded BatchNorm), ReLU, skip
+//     add, fp16 hi|lo split or the fused 1x1x1 `prob` conv); warp 4: one thread issues the MMAs; mbarrier ring
+//     full[s] / empty[s]; tcgen05.commit releases a stage.
+#include "conv3d_tc.cuh"
+
+#include "linear_tc.cuh"
+#include "umma.cuh"
+
+namespace mvsf {
+
+using namespace umma;
+
+namespace c3 {
+constexpr int NPROD = 128, THREADS = 160, MAX_STAGES = 4;
+template <int MODE, int NT>
+struct Geo {
+  static constexpr int TW = 8 * NT, TH = 16;
+  static constexpr int PR = MODE == CONV_S1 ? TH + 2 : TH + 1;   // plane rows
+  static constexpr int PC = MODE == CONV_S1 ? TW + 2 : TW + 1;   // plane columns (voxel octets)
+  static constexpr int NSUB = MODE == CONV_S2 ? 4 : 1;           // parity sub-planes
+  static constexpr uint32_t SUB_BYTES = PR * PC * 16;
+  static constexpr uint32_t PLANE = NSUB * SUB_BYTES;            // hi plane set; the lo set follows
+  static constexpr uint32_t A_BYTES = 2 * PLANE;
+  static constexpr uint32_t PITCH = PC * 16;
+};
+__host__ __device__ inline int npad(int cout) { return cout < 16 ? 16 : cout; }
+__host__ __device__ inline uint32_t slab_bytes(int cout) { return (uint32_t)npad(cout) * 576u; }  // 9 taps x 2 MMAs x (2 x NPAD x 16 B)
+}  // namespace c3
+
+template <int MODE, int NT, int OUT>
+__global__ void __launch_bounds__(c3::THREADS)
+conv3d_tc_kernel(ConvTcArgs a, int NS, int OD, int OH, int OW) {
+  using G = c3::Geo<MODE, NT>;
+  constexpr int PR = G::PR, PC = G::PC, NSUB = G::NSUB;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int CIN = a.CIN, COUT = a.COUT, SD = a.SD, ID = a.ID, IH = a.IH, IW = a.IW;
+  const int NPAD = c3::npad(COUT);
+  const uint32_t b_bytes = c3::slab_bytes(COUT);
+  const uint32_t stage_bytes = G::A_BYTES + b_bytes;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + NS * stage_bytes;                 // full[4] | empty[4] | accf | tmem slot
+  const uint32_t bar_full = bars, bar_empty = bars + 32, bar_accf = bars + 64;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + NS * stage_bytes + 72);
+
+  const int od = blockIdx.z;
+  const int c0h = blockIdx.y * 16, c0w = blockIdx.x * G::TW;     // first cell of the tile (output cell; DECONV: input cell)
+
+  // depth taps of this slice: (kd, id) pairs
+  int kd0 = 0, kd1 = 0, kd2 = 0, id0 = 0, id1 = 0, id2 = 0, nd = 0;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd) {
+    int id;
+    bool ok = true;
+    if (MODE == CONV_S1) id = od + kd - 1;
+    else if (MODE == CONV_S2) id = od * SD + kd - 1;
+    else {
+      int num = od + 1 - kd;
+      if (SD == 1) id = num;
+      else { ok = (num & 1) == 0; id = num >> 1; }
+    }
+    ok = ok && id >= 0 && id < ID;
+    if (ok) {
+      if (nd == 0) { kd0 = kd; id0 = id; }
+      else if (nd == 1) { kd1 = kd; id1 = id; }
+      else { kd2 = kd; id2 = id; }
+      ++nd;
+    }
+  }
+  const int nocts = CIN >> 3;
+  const int U = nd * nocts;
+
+  uint32_t ncols = 32;
+  {
+    const uint32_t want = (uint32_t)(NT * NPAD * (MODE == DECONV_S2 ? 4 : 1));
+    while (ncols < want) ncols <<= 1;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < c3::MAX_STAGES; ++i) { mbar_init(bar_full + 8 * i, c3::NPROD); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_accf, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), ncols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid < c3::NPROD) {
+    // ------------------------------------------------------------------------------------------- producers
+    for (int u = 0; u < U; ++u) {
+      const int s = u % NS;
+      mbar_wait(bar_empty + 8 * s, (uint32_t)(((u / NS) & 1) ^ 1));
+      const int ds = u / nocts, o = u - ds * nocts;
+      const int kd = ds == 0 ? kd0 : (ds == 1 ? kd1 : kd2);
+      const int id = ds == 0 ? id0 : (ds == 1 ? id1 : id2);
+      const uint32_t st = sbase + s * stage_bytes;
+      constexpr int PER = NSUB * PR * PC;
+      for (int idx = tid; idx < 2 * PER; idx += c3::NPROD) {
+        const int hl = idx / PER, rem = idx - hl * PER;
+        const int sub = rem / (PR * PC), rc = rem - sub * (PR * PC);
+        const int r = rc / PC, c = rc - r * PC;
+        int ih, iw;
+        if (MODE == CONV_S1) { ih = c0h - 1 + r; iw = c0w - 1 + c; }
+        else if (MODE == CONV_S2) { ih = 2 * (c0h + r) - (sub >> 1); iw = 2 * (c0w + c) - (sub & 1); }
+        else { ih = c0h + r; iw = c0w + c; }
+        const bool ok = ih >= 0 && ih < IH && iw >= 0 && iw < IW;
+        const __half* src = (hl ? a.in_lo : a.in_hi) + (((size_t)id * IH + (ok ? ih : 0)) * IW + (ok ? iw : 0)) * CIN + o * 8;
+        cp_async16_zfill(st + (uint32_t)idx * 16u, src, ok);
+      }
+      const __half* wsrc = a.wtc + (size_t)(kd * nocts + o) * (b_bytes / 2);
+      for (int i = tid; i < (int)(b_bytes / 16); i += c3::NPROD) cp_async16_zfill(st + G::A_BYTES + i * 16, wsrc + i * 8, true);
+      cp_async_commit_group();
+      if (u > 0) {
+        cp_async_wait_group<1>();   // unit u-1 of this thread has landed
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * ((u - 1) % NS));
+      }
+    }
+    cp_async_wait_group<0>();
+    fence_proxy_async();
+    mbar_arrive(bar_full + 8 * ((U - 1) % NS));
+
+    // ------------------------------------------------------------------------------------------- epilogue
+    mbar_wait(bar_accf, 0u);
+    tc_fence_after_sync();
+    const int m = warp * 32 + lane;              // TMEM lane = GEMM row = cell (h = m / 8, w = m % 8) of an M-tile
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int ch = c0h + (m >> 3);
+    constexpr int NCLS = MODE == DECONV_S2 ? 4 : 1;
+#pragma unroll 1
+    for (int t = 0; t < NT; ++t) {
+      const int cw = c0w + t * 8 + (m & 7);
+#pragma unroll 1
+      for (int cls = 0; cls < NCLS; ++cls) {
+        int oh, ow;
+        bool valid;
+        if (MODE == DECONV_S2) { oh = 2 * ch + (cls >> 1); ow = 2 * cw + (cls & 1); valid = ch < IH && cw < IW; }
+        else { oh = ch; ow = cw; valid = ch < OH && cw < OW; }
+        const size_t vox = valid ? ((size_t)od * OH + oh) * OW + ow : 0;
+        const uint32_t tcol = trow + (uint32_t)((t * NCLS + cls) * NPAD);
+        float prob = 0.f;
+        for (int c16 = 0; c16 < NPAD / 16; ++c16) {
+          float v[16];
+          tmem_ld16(tcol + c16 * 16, v);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int c0 = c16 * 16 + g * 8;
+            if (c0 >= COUT) continue;
+            float x[8];
+            const float4 b0 = ldg4(a.bias + c0), b1 = ldg4(a.bias + c0 + 4);
+            x[0] = fmaxf(v[g * 8 + 0] + b0.x, 0.f); x[1] = fmaxf(v[g * 8 + 1] + b0.y, 0.f);
+            x[2] = fmaxf(v[g * 8 + 2] + b0.z, 0.f); x[3] = fmaxf(v[g * 8 + 3] + b0.w, 0.f);
+            x[4] = fmaxf(v[g * 8 + 4] + b1.x, 0.f); x[5] = fmaxf(v[g * 8 + 5] + b1.y, 0.f);
+            x[6] = fmaxf(v[g * 8 + 6] + b1.z, 0.f); x[7] = fmaxf(v[g * 8 + 7] + b1.w, 0.f);
+            if (!valid) continue;
+            if (OUT == OUT_SPLIT) {
+              if (a.skip_hi) {
+                const uint4 sh = *reinterpret_cast<const uint4*>(a.skip_hi + vox * COUT + c0);
+                const uint4 sl = *reinterpret_cast<const uint4*>(a.skip_lo + vox * COUT + c0);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&sh);
+                const __half2* l2 = reinterpret_cast<const __half2*>(&sl);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 fh = __half22float2(h2[e]), fl = __half22float2(l2[e]);
+                  x[2 * e] += fh.x + fl.x;
+                  x[2 * e + 1] += fh.y + fl.y;
+                }
+              }
+              split_store8(a.out_hi + vox * COUT + c0, a.out_lo + vox * COUT + c0, x);
+            } else {
+              const float4 s0 = ldg4(a.skip32 + vox * COUT + c0), s1 = ldg4(a.skip32 + vox * COUT + c0 + 4);
+              x[0] += s0.x; x[1] += s0.y; x[2] += s0.z; x[3] += s0.w;
+              x[4] += s1.x; x[5] += s1.y; x[6] += s1.z; x[7] += s1.w;
+              if (OUT == OUT_F32) {
+                float* op = a.out32 + vox * COUT + c0;
+                *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
+              } else {
+                if (c0 == 0) prob = __ldg(a.probw + COUT);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) prob = fmaf(x[e], __ldg(a.probw + c0 + e), prob);
+              }
+            }
+          }
+        }
+        if (OUT == OUT_PROB && valid) a.out32[vox] = prob;
+      }
+    }
+  } else if (tid == c3::NPROD) {
+    // ------------------------------------------------------------------------------------------- MMA issue
+    const uint32_t idesc = make_idesc_f16(128, NPAD);
+    const uint32_t btile = (uint32_t)(2 * NPAD * 16);
+    for (int u = 0; u < U; ++u) {
+      const int s = u % NS;
+      mbar_wait(bar_full + 8 * s, (uint32_t)((u / NS) & 1));
+      tc_fence_after_sync();
+      const uint32_t sA = sbase + s * stage_bytes, sB = sA + G::A_BYTES;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int tap = kh * 3 + kw;
+          int sub = 0, rs, cs, cls = 0;
+          bool first_of_acc;
+          if (MODE == CONV_S1) { rs = kh; cs = kw; first_of_acc = tap == 0; }
+          else if (MODE == CONV_S2) {
+            const int ph = kh == 1 ? 0 : 1, pw = kw == 1 ? 0 : 1;
+            sub = ph * 2 + pw; rs = kh == 2 ? 1 : 0; cs = kw == 2 ? 1 : 0; first_of_acc = tap == 0;
+          } else {
+            const int ph = kh == 1 ? 0 : 1, pw = kw == 1 ? 0 : 1;
+            cls = ph * 2 + pw; rs = kh == 0 ? 1 : 0; cs = kw == 0 ? 1 : 0;
+            first_of_acc = (kh == (ph ? 0 : 1)) && (kw == (pw ? 0 : 1));
+          }
+          const uint32_t aoff = (uint32_t)sub * G::SUB_BYTES + (uint32_t)(rs * PC + cs) * 16u;
+          const uint64_t b0 = make_desc(sB + (tap * 2 + 0) * btile, (uint32_t)NPAD * 16u, 128);
+          const uint64_t b1 = make_desc(sB + (tap * 2 + 1) * btile, (uint32_t)NPAD * 16u, 128);
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            const uint64_t ad = make_desc(sA + aoff + t * 128, G::PLANE, G::PITCH);
+            const uint32_t tacc = tmem_base + (uint32_t)((MODE == DECONV_S2 ? t * 4 + cls : t) * NPAD);
+            mma_f16_ss(tacc, ad, b0, idesc, (u == 0 && first_of_acc) ? 0u : 1u);
+            mma_f16_ss(tacc, ad, b1, idesc, 1u);
+          }
+        }
+      }
+      commit(bar_empty + 8 * s);
+    }
+    commit(bar_accf);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------------- host
+size_t conv3d_tc_packed_halves(int cin, int cout) { return (size_t)3 * (cin / 8) * (c3::slab_bytes(cout) / 2); }
+
+__global__ void conv3d_tc_pack_kernel(const float* __restrict__ w32, __half* __restrict__ out, int cin, int cout, int NPAD,
+                                      size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // i = ((((((kd * nocts + o) * 9 + tap) * 2 + mm) * 2 + kc) * NPAD + n) * 8 + e
+  int e = (int)(i & 7);
+  size_t q = i >> 3;
+  int n = (int)(q % NPAD); q /= NPAD;
+  int kc = (int)(q & 1); q >>= 1;
+  int mm = (int)(q & 1); q >>= 1;
+  int tap = (int)(q % 9); q /= 9;
+  const int nocts = cin / 8;
+  int o = (int)(q % nocts);
+  int kd = (int)(q / nocts);
+  float w = 0.f;
+  if (n < cout) w = w32[((size_t)(kd * 9 + tap) * cin + o * 8 + e) * cout + n];
+  const __half hi = __float2half_rn(w);
+  const __half lo = __float2half_rn(w - __half2float(hi));
+  __half v;
+  if (mm == 0) v = hi;
+  else v = kc == 0 ? lo : __float2half_rn(0.f);
+  out[i] = v;
+}
+
+int conv3d_tc_pack(const float* w32, __half* out, int cin, int cout, cudaStream_t s) {
+  MVSF_REQUIRE(w32 && out && cin % 8 == 0 && cout % 8 == 0, "conv3d_tc_pack: bad arguments");
+  const size_t total = conv3d_tc_packed_halves(cin, cout);
+  conv3d_tc_pack_kernel<<<cdiv((long long)total, 256), 256, 0, s>>>(w32, out, cin, cout, c3::npad(cout), total);
+  MVSF_LAUNCH_CHECK("conv3d_tc_pack");
+  return MVSF_OK;
+}
+
+__global__ void split_vec8_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, size_t n8) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = ldg4(x + i * 8), b = ldg4(x + i * 8 + 4);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  split_store8(hi + i * 8, lo + i * 8, v);
+}
+__global__ void merge_vec8_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ x, size_t n8) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 h = *reinterpret_cast<const uint4*>(hi + i * 8), l = *reinterpret_cast<const uint4*>(lo + i * 8);
+  const __half2* h2 = reinterpret_cast<const __half2*>(&h);
+  const __half2* l2 = reinterpret_cast<const __half2*>(&l);
+  float r[8];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 fh = __half22float2(h2[e]), fl = __half22float2(l2[e]);
+    r[2 * e] = fh.x + fl.x;
+    r[2 * e + 1] = fh.y + fl.y;
+  }
+  *reinterpret_cast<float4*>(x + i * 8) = make_float4(r[0], r[1], r[2], r[3]);
+  *reinterpret_cast<float4*>(x + i * 8 + 4) = make_float4(r[4], r[5], r[6], r[7]);
+}
+int launch_split_vec8(const float* x, __half* hi, __half* lo, size_t n, cudaStream_t s) {
+  MVSF_REQUIRE(x && hi && lo && n > 0 && n % 8 == 0, "split_vec8: bad arguments");
+  split_vec8_kernel<<<cdiv((long long)(n / 8), 256), 256, 0, s>>>(x, hi, lo, n / 8);
+  MVSF_LAUNCH_CHECK("split_vec8");
+  return MVSF_OK;
+}
+int launch_merge_vec8(const __half* hi, const __half* lo, float* x, size_t n, cudaStream_t s) {
+  MVSF_REQUIRE(x && hi && lo && n > 0 && n % 8 == 0, "merge_vec8: bad arguments");
+  merge_vec8_kernel<<<cdiv((long long)(n / 8), 256), 256, 0, s>>>(hi, lo, x, n / 8);
+  MVSF_LAUNCH_CHECK("merge_vec8");
+  return MVSF_OK;
+}
+
+template <int MODE, int NT, int OUT>
+static int launch_one(const ConvTcArgs& a, int NS, size_t smem, int OD, int OH, int OW, int cells_h, int cells_w,
+                      cudaStream_t s) {
+  auto kern = conv3d_tc_kernel<MODE, NT, OUT>;
+  static bool configured = false;
+  if (!configured) {
+    MVSF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  dim3 grid(cdiv(cells_w, 8 * NT), cdiv(cells_h, 16), OD);
+  MVSF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d_tc: volume too large");
+  kern<<<grid, c3::THREADS, smem, s>>>(a, NS, OD, OH, OW);
+  MVSF_LAUNCH_CHECK("conv3d_tc");
+  return MVSF_OK;
+}
+
+template <int MODE, int OUT>
+static int launch_mode(const ConvTcArgs& a, cudaStream_t s) {
+  int OD, OH, OW, cells_h, cells_w;
+  if (MODE == CONV_S1) { OD = a.ID; OH = a.IH; OW = a.IW; cells_h = OH; cells_w = OW; }
+  else if (MODE == CONV_S2) { OD = (a.ID - 1) / a.SD + 1; OH = (a.IH - 1) / 2 + 1; OW = (a.IW - 1) / 2 + 1; cells_h = OH; cells_w = OW; }
+  else { OD = a.ID * a.SD; OH = a.IH * 2; OW = a.IW * 2; cells_h = a.IH; cells_w = a.IW; }
+  const int NPAD = c3::npad(a.COUT);
+  const uint32_t b_bytes = c3::slab_bytes(a.COUT);
+  // tile width: the widest tile that still gives every SM two CTAs, fits TMEM twice (256 columns) and 2 stages in half an SM
+  int best_nt = 1;
+  const int nts[3] = {4, 2, 1};
+  for (int k = 0; k < 3; ++k) {
+    const int nt = nts[k];
+    const uint32_t a_bytes = nt == 4 ? c3::Geo<MODE, 4>::A_BYTES : (nt == 2 ? c3::Geo<MODE, 2>::A_BYTES : c3::Geo<MODE, 1>::A_BYTES);
+    const long long ctas = (long long)cdiv(cells_w, 8 * nt) * cdiv(cells_h, 16) * OD;
+    const int cols = nt * NPAD * (MODE == DECONV_S2 ? 4 : 1);
+    const bool fits = cols <= 256 && 2 * (size_t)(a_bytes + b_bytes) + 128 <= 113 * 1024;
+    if ((fits && ctas >= 2 * 148) || nt == 1) { best_nt = nt; break; }
+  }
+  const uint32_t a_bytes = best_nt == 4 ? c3::Geo<MODE, 4>::A_BYTES : (best_nt == 2 ? c3::Geo<MODE, 2>::A_BYTES : c3::Geo<MODE, 1>::A_BYTES);
+  const size_t stage = (size_t)a_bytes + b_bytes;
+  int NS = 3;
+  if (3 * stage + 128 > 113 * 1024) NS = 2;                       // keep two CTAs per SM when three stages do not fit
+  if (2 * stage + 128 > 113 * 1024) NS = (int)((226 * 1024 - 128) / stage);  // one CTA per SM
+  if (NS > c3::MAX_STAGES) NS = c3::MAX_STAGES;
+  MVSF_REQUIRE(NS >= 2, "conv3d_tc: stage of %zu bytes does not fit twice in shared memory", stage);
+  MVSF_REQUIRE(best_nt * NPAD * (MODE == DECONV_S2 ? 4 : 1) <= 512, "conv3d_tc: accumulators exceed TMEM");
+  const size_t smem = NS * stage + 128;
+  switch (best_nt) {
+    case 4: return launch_one<MODE, 4, OUT>(a, NS, smem, OD, OH, OW, cells_h, cells_w, s);
+    case 2: return launch_one<MODE, 2, OUT>(a, NS, smem, OD, OH, OW, cells_h, cells_w, s);
+    default: return launch_one<MODE, 1, OUT>(a, NS, smem, OD, OH, OW, cells_h, cells_w, s);
+  }
+}
+
+int launch_conv3d_tc(const ConvTcArgs& a, int mode, int out_mode, cudaStream_t s) {
+  MVSF_REQUIRE(a.in_hi && a.in_lo && a.wtc && a.bias, "conv3d_tc: null pointer");
+  MVSF_REQUIRE(a.CIN % 8 == 0 && a.CIN >= 8 && a.CIN <= 64 && a.COUT % 8 == 0 && a.COUT >= 8 && a.COUT <= 64 &&
+                   (a.COUT == 8 || a.COUT % 16 == 0), "conv3d_tc: channels must be 8, 16, 32, 48 or 64");
+  MVSF_REQUIRE(a.SD == 1 || a.SD == 2, "conv3d_tc: depth stride must be 1 or 2");
+  MVSF_REQUIRE(((uintptr_t)a.in_hi & 15) == 0 && ((uintptr_t)a.in_lo & 15) == 0 && ((uintptr_t)a.wtc & 15) == 0,
+               "conv3d_tc: operands must be 16-byte aligned");
+  if (out_mode == OUT_SPLIT) {
+    MVSF_REQUIRE(a.out_hi && a.out_lo, "conv3d_tc: split output missing");
+    if (mode == CONV_S1) return launch_mode<CONV_S1, OUT_SPLIT>(a, s);
+    if (mode == CONV_S2) return launch_mode<CONV_S2, OUT_SPLIT>(a, s);
+    if (mode == DECONV_S2) return launch_mode<DECONV_S2, OUT_SPLIT>(a, s);
+  } else if (mode == DECONV_S2 && (out_mode == OUT_F32 || out_mode == OUT_PROB)) {
+    MVSF_REQUIRE(a.out32 && a.skip32 && a.COUT == 8 && (out_mode == OUT_F32 || a.probw), "conv3d_tc: fp32 output needs out32, skip32, COUT == 8");
+    if (out_mode == OUT_F32) return launch_mode<DECONV_S2, OUT_F32>(a, s);
+    return launch_mode<DECONV_S2, OUT_PROB>(a, s);
+  }
+  return fail(MVSF_ERR_INVALID, "conv3d_tc: unsupported mode %d / output %d", mode, out_mode);
+}
+
+}  // namespace mvsf
+
+using namespace mvsf;
+
+/* Test entry: one 3x3x3 layer through the tensor-core path with fp32 in/out (split, pack and merge done here).
+ * in [ID][IH][IW][cin]; w32 = [27][cin][cout] then bias[cout]; skip (optional) and out [OD][OH][OW][cout]. */
+extern "C" int mvsf_conv3d_tc_layer(int mode, int sd, const float* in, const float* w32, const float* skip, float* out,
+                                    void* workspace, size_t workspace_bytes, int cin, int cout, int ID, int IH, int IW,
+                                    mvsf_stream_t stream) {
+  MVSF_REQUIRE(in && w32 && out && workspace && (mode >= 0 && mode <= 2) && (sd == 1 || sd == 2), "conv3d_tc_layer: bad arguments");
+  MVSF_REQUIRE(cin % 8 == 0 && cout % 8 == 0, "conv3d_tc_layer: channels must be multiples of 8");
+  int OD, OH, OW;
+  if (mode == CONV_S1) { OD = ID; OH = IH; OW = IW; }
+  else if (mode == CONV_S2) { OD = (ID - 1) / sd + 1; OH = (IH - 1) / 2 + 1; OW = (IW - 1) / 2 + 1; }
+  else { OD = ID * sd; OH = IH * 2; OW = IW * 2; }
+  const size_t nin = (size_t)ID * IH * IW * cin, nout = (size_t)OD * OH * OW * cout;
+  const size_t nw = align_up(conv3d_tc_packed_halves(cin, cout), 64);
+  const size_t need = (2 * nin + 4 * nout + nw) * sizeof(__half) + 256;
+  if (workspace_bytes < need) return fail(MVSF_ERR_WORKSPACE, "conv3d_tc_layer: workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t s = (cudaStream_t)stream;
+  __half* xin = reinterpret_cast<__half*>(workspace);
+  __half* xout = xin + 2 * nin;
+  __half* xskip = xout + 2 * nout;
+  __half* wtc = xskip + 2 * nout;
+  int rc;
+  if ((rc = launch_split_vec8(in, xin, xin + nin, nin, s))) return rc;
+  if (skip && (rc = launch_split_vec8(skip, xskip, xskip + nout, nout, s))) return rc;
+  if ((rc = conv3d_tc_pack(w32, wtc, cin, cout, s))) return rc;
+  ConvTcArgs a{};
+  a.in_hi = xin; a.in_lo = xin + nin; a.wtc = wtc; a.bias = w32 + (size_t)27 * cin * cout;
+  if (skip) { a.skip_hi = xskip; a.skip_lo = xskip + nout; }
+  a.out_hi = xout; a.out_lo = xout + nout;
+  a.CIN = cin; a.COUT = cout; a.SD = sd; a.ID = ID; a.IH = IH; a.IW = IW;
+  if ((rc = launch_conv3d_tc(a, mode, OUT_SPLIT, s))) return rc;
+  return launch_merge_vec8(xout, xout + nout, out, nout, s);
+}

@@ -71,6 +71,18 @@ def split_weights_f16(flat):
     return out
 
 
+def pack_unet_tc(flat):
+    """fp32 U-Net weight blob (packing.pack_costreg_unet) on the device -> fp16 hi/lo weight slabs of the tcgen05
+    implicit-GEMM convolutions (install time, once)."""
+    L = _lib.lib()
+    need = ctypes.c_size_t(0)
+    _lib.check(L.mvsf_costreg_unet_tc_bytes(ctypes.byref(need)), "costreg_unet_tc_bytes")
+    out = torch.empty(need.value // 2, device=flat.device, dtype=torch.float16)
+    _lib.check(L.mvsf_costreg_unet_pack_tc(_ptr(flat), _ptr(out), ctypes.c_size_t(need.value), _stream()),
+               "costreg_unet_pack_tc")
+    return out
+
+
 class _PackedMixin:
     """Packs the module's parameters for the CUDA library on first use / after load_state_dict."""
 
@@ -125,6 +137,7 @@ class StageNet(_PackedMixin, nn.Module):
             kind, flat = packing.pack_costreg_unet(sd, "cost_reg.")
             pk["kind"] = kind
             pk["reg"] = flat.to(device)
+            pk["reg_tc"] = pack_unet_tc(pk["reg"])
         self._packed = pk
         return pk
 
@@ -172,7 +185,8 @@ class StageNet(_PackedMixin, nn.Module):
             _lib.check(L.mvsf_costreg_unet_workspace_bytes(pk["kind"], G, D, H, W, ctypes.byref(need)),
                        "costreg_unet_workspace_bytes")
             ws = torch.empty(need.value // 4 + 4, **f32)
-            _lib.check(L.mvsf_costreg_unet_forward(pk["kind"], _ptr(volume), _ptr(pk["reg"]), _ptr(logits), _ptr(ws),
+            _lib.check(L.mvsf_costreg_unet_forward(pk["kind"], _ptr(volume), _ptr(pk["reg"]), _ptr(pk["reg_tc"]),
+                                                   _ptr(logits), _ptr(ws),
                                                    ctypes.c_size_t(ws.numel() * 4), G, D, H, W, st),
                        "costreg_unet_forward")
         prob = torch.empty((D, H, W), **f32)

@@ -222,6 +222,41 @@ def test_vis_cnn_tile_borders(dev, L):
 
 
 # ----------------------------------------------------------------------------------------------- regularisers
+@pytest.mark.parametrize("mode,sd,cin,cout,ID,IH,IW", [
+    (0, 1, 16, 16, 3, 16, 32), (0, 1, 32, 32, 2, 20, 44), (0, 1, 64, 64, 4, 9, 13), (0, 1, 16, 16, 5, 48, 160),
+    (1, 1, 8, 16, 3, 32, 64), (1, 2, 8, 16, 8, 24, 40), (1, 1, 16, 32, 2, 18, 26), (1, 2, 32, 64, 4, 16, 16),
+    (2, 1, 64, 32, 2, 9, 12), (2, 2, 32, 16, 3, 16, 24), (2, 1, 16, 8, 3, 20, 36), (2, 2, 16, 8, 2, 8, 8)])
+@pytest.mark.parametrize("skip", [False, True])
+def test_conv3d_tensor_core_layer(dev, L, mode, sd, cin, cout, ID, IH, IW, skip):
+    """One 3x3x3 layer of the tcgen05 implicit-GEMM path against torch's fp64 convolution (conv / strided conv /
+    transposed conv with output_padding = stride - 1, bias, ReLU, skip added after the ReLU)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(mode * 100 + cin + ID)
+    x = torch.randn(ID, IH, IW, cin, generator=g)
+    w = torch.randn(27, cin, cout, generator=g) / (27 * cin) ** 0.5 * 1.7
+    b = torch.randn(cout, generator=g) * 0.2
+    xin = x.permute(3, 0, 1, 2)[None].double()
+    if mode == 2:
+        wt = w.reshape(3, 3, 3, cin, cout).permute(3, 4, 0, 1, 2).double()
+        y = F.conv_transpose3d(xin, wt, stride=(sd, 2, 2), padding=1, output_padding=(sd - 1, 1, 1))
+    else:
+        wt = w.reshape(3, 3, 3, cin, cout).permute(4, 3, 0, 1, 2).double()
+        y = F.conv3d(xin, wt, stride=(1, 1, 1) if mode == 0 else (sd, 2, 2), padding=1)
+    y = torch.relu(y + b.double().view(1, -1, 1, 1, 1))[0].permute(1, 2, 3, 0).contiguous()
+    sk = torch.randn(y.shape, generator=g) if skip else None
+    if skip:
+        y = y + sk.double()
+    x_d, wb_d = x.contiguous().to(dev), torch.cat([w.reshape(-1), b]).to(dev)
+    sk_d = sk.contiguous().to(dev) if skip else None
+    out = torch.empty(y.shape, device=dev)
+    ws = torch.empty((2 * x.numel() + 4 * y.numel()) // 2 + 27 * cin * max(cout, 16) * 4 + 1024, device=dev)
+    ck(L.mvsf_conv3d_tc_layer(mode, sd, P(x_d), P(wb_d), P(sk_d) if skip else None, P(out), P(ws),
+                              ctypes.c_size_t(ws.numel() * 4), cin, cout, ID, IH, IW, S()), "conv3d_tc_layer")
+    e = float((out.cpu().double() - y).abs().max())
+    rec(f"conv3d_tc_mode{mode}_sd{sd}_{cin}to{cout}_{ID}x{IH}x{IW}_skip{int(skip)}", abs=e, scale=float(y.abs().max()))
+    assert e < 1e-5 * max(1.0, float(y.abs().max()))
+
+
 @pytest.mark.parametrize("stage,D,H,W", [(1, 16, 16, 24), (1, 8, 8, 40), (2, 8, 16, 24), (3, 4, 24, 40), (3, 3, 8, 8)])
 def test_costreg_unet(dev, L, stage, D, H, W):
     from mvsformerplusplus_b200 import packing
@@ -237,9 +272,11 @@ def test_costreg_unet(dev, L, stage, D, H, W):
     ws = torch.empty(need.value // 4 + 4, device=dev)
     logits = torch.empty(D, H, W, device=dev)
     v = vol[0].permute(1, 2, 3, 0).contiguous().to(dev)
+    from mvsformerplusplus_b200.hotpath import pack_unet_tc
     flat_d = flat.to(dev)
-    ck(L.mvsf_costreg_unet_forward(kind, P(v), P(flat_d), P(logits), P(ws), ctypes.c_size_t(ws.numel() * 4), 8, D, H, W, S()),
-       "costreg_unet_forward")
+    flat_tc = pack_unet_tc(flat_d)
+    ck(L.mvsf_costreg_unet_forward(kind, P(v), P(flat_d), P(flat_tc), P(logits), P(ws), ctypes.c_size_t(ws.numel() * 4),
+                                   8, D, H, W, S()), "costreg_unet_forward")
     e = max_abs(logits.cpu(), want)
     rec(f"costreg_unet_stage{stage}_{D}x{H}x{W}", abs=e, scale=float(want.abs().max()))
     assert e < 2e-4 * max(1.0, float(want.abs().max()))

@@ -39,8 +39,10 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
     assert rc == -1 and b"down_rate" in lib.mvsf_last_error()
     assert lib.mvsf_costreg_unet_workspace_bytes(0, 8, 12, 16, 16, ctypes.byref(need)) == -1  # CostRegNet needs D % 8 == 0
     assert lib.mvsf_costreg_unet_workspace_bytes(1, 8, 4, 1152, 1536, ctypes.byref(need)) == 0
-    # 2*(n1+n2+n3) floats, n1 = 4*576*768*16, n2 = 4*288*384*32, n3 = 4*144*192*64
-    assert need.value == 4 * 2 * (4 * 576 * 768 * 16 + 4 * 288 * 384 * 32 + 4 * 144 * 192 * 64)
+    # fp16 hi|lo buffers, 4 bytes per element: the split input (n0) + two buffers per level
+    n0, n1, n2, n3 = 4 * 1152 * 1536 * 8, 4 * 576 * 768 * 16, 4 * 288 * 384 * 32, 4 * 144 * 192 * 64
+    assert need.value == 4 * (n0 + 2 * (n1 + n2 + n3))
+    assert lib.mvsf_costreg_unet_tc_bytes(ctypes.byref(need)) == 0 and need.value % 16 == 0 and need.value > 0
     with pytest.raises(RuntimeError, match="status -1"):
         _lib.check(lib.mvsf_warp_corr_entropy(None, None, None, None, 5, 8, 8, 4, 16, 16, None), "warp_corr_entropy")
 
