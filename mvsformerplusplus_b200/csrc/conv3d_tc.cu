@@ -7,13 +7,17 @@
 //     Eight w-neighbours are then 128 contiguous bytes = one UMMA "core matrix" of the canonical no-swizzle K-major
 //     layout, the h rows are the 8-row groups (SBO = row pitch) and the hi / lo planes are the two K-chunks of a K = 16
 //     MMA (LBO = plane size).  A filter tap (kh, kw) is nothing but a different descriptor start address: no im2col;
-//   * per unit and tap two tcgen05.mma.kind::f16 (M = 128 cells, N = Cout, K = 16) are issued:
+//   * a unit carries KG channel octets.  KG = 1: per tap two tcgen05.mma.kind::f16 (M = 128 cells, N = Cout, K = 16)
 //         [x_hi | x_lo] x [w_hi ; w_hi]   and   [x_hi | x_lo] x [w_lo ; 0]       (x_lo*w_lo ~ 2^-22 is dropped)
-//     with fp32 accumulation in TMEM; the weight slabs come pre-arranged from conv3d_tc_pack and are streamed with the
-//     unit through the same cp.async ring;
+//     KG = 2 (16 channels per unit): K = 16 spans the two octets and three MMAs x_lo*w_hi, x_hi*w_lo, x_hi*w_hi are
+//     issued; fp32 accumulation in TMEM; the weight slabs come pre-arranged from conv3d_tc_pack and are streamed
+//     with the unit through the same cp.async ring.  The MMAs are bound by the shared-memory read of the A operand
+//     (4 KB per instruction at 128 B/clk), so fewer, wider instructions is what counts;
 //   * stride-(SD,2,2) convolutions keep four parity planes (even/odd h x even/odd w) so that every tap is again a dense
 //     plane access; transposed convolutions run in gather form over INPUT cells with four accumulators, one per output
-//     parity class (every (kh, kw) tap feeds exactly one class);
+//     parity class (every (kh, kw) tap feeds exactly one class).  Taps that read the same input shift (dih, diw) are
+//     fused along N: the class accumulators sit in TMEM in the order [0, 1, 3, 2] so that the 4 / 2 / 2 / 1 classes fed
+//     by the shifts (0,0) / (0,1) / (1,0) / (1,1) are contiguous column ranges - 4 wide MMAs instead of 9 narrow ones;
 //   * warps 0-3: producers, then the epilogue (one TMEM lane = one cell per thread: bias (folded BatchNorm), ReLU, skip
 //     add, fp16 hi|lo split or the fused 1x1x1 `prob` conv); warp 4: one thread issues the MMAs; mbarrier ring
 //     full[s] / empty[s]; tcgen05.commit releases a stage.
@@ -35,8 +39,8 @@ struct Geo {
   static constexpr int PC = MODE == CONV_S1 ? TW + 2 : TW + 1;   // plane columns (voxel octets)
   static constexpr int NSUB = MODE == CONV_S2 ? 4 : 1;           // parity sub-planes
   static constexpr uint32_t SUB_BYTES = PR * PC * 16;
-  static constexpr uint32_t PLANE = NSUB * SUB_BYTES;            // hi plane set; the lo set follows
-  static constexpr uint32_t A_BYTES = 2 * PLANE;
+  static constexpr uint32_t PLANE = NSUB * SUB_BYTES;            // one octet's plane set; order [hi|lo][octet of the unit]
+  static constexpr uint32_t A_BYTES = 2 * PLANE;                 // per octet of the unit (hi + lo)
   static constexpr uint32_t PITCH = PC * 16;
 };
 __host__ __device__ inline int npad(int cout) { return cout < 16 ? 16 : cout; }
@@ -53,7 +57,9 @@ conv3d_tc_kernel(ConvTcArgs a, int NS, int OD, int OH, int OW) {
   const int CIN = a.CIN, COUT = a.COUT, SD = a.SD, ID = a.ID, IH = a.IH, IW = a.IW;
   const int NPAD = c3::npad(COUT);
   const uint32_t b_bytes = c3::slab_bytes(COUT);
-  const uint32_t stage_bytes = G::A_BYTES + b_bytes;
+  const int KG = a.KG;                                            // channel octets per unit
+  const uint32_t a_bytes = (uint32_t)KG * G::A_BYTES;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + NS * stage_bytes;                 // full[4] | empty[4] | accf | tmem slot
   const uint32_t bar_full = bars, bar_empty = bars + 32, bar_accf = bars + 64;
@@ -83,8 +89,8 @@ conv3d_tc_kernel(ConvTcArgs a, int NS, int OD, int OH, int OW) {
       ++nd;
     }
   }
-  const int nocts = CIN >> 3;
-  const int U = nd * nocts;
+  const int ngroups = (CIN >> 3) / KG;
+  const int U = nd * ngroups;
 
   uint32_t ncols = 32;
   {
@@ -107,13 +113,14 @@ conv3d_tc_kernel(ConvTcArgs a, int NS, int OD, int OH, int OW) {
     for (int u = 0; u < U; ++u) {
       const int s = u % NS;
       mbar_wait(bar_empty + 8 * s, (uint32_t)(((u / NS) & 1) ^ 1));
-      const int ds = u / nocts, o = u - ds * nocts;
+      const int ds = u / ngroups, g = u - ds * ngroups;
       const int kd = ds == 0 ? kd0 : (ds == 1 ? kd1 : kd2);
       const int id = ds == 0 ? id0 : (ds == 1 ? id1 : id2);
       const uint32_t st = sbase + s * stage_bytes;
       constexpr int PER = NSUB * PR * PC;
-      for (int idx = tid; idx < 2 * PER; idx += c3::NPROD) {
-        const int hl = idx / PER, rem = idx - hl * PER;
+      for (int idx = tid; idx < 2 * KG * PER; idx += c3::NPROD) {
+        const int pl = idx / PER, rem = idx - pl * PER;          // plane set index = hl * KG + octet
+        const int hl = pl >= KG ? 1 : 0, o = g * KG + (pl - hl * KG);
         const int sub = rem / (PR * PC), rc = rem - sub * (PR * PC);
         const int r = rc / PC, c = rc - r * PC;
         int ih, iw;
@@ -124,8 +131,8 @@ conv3d_tc_kernel(ConvTcArgs a, int NS, int OD, int OH, int OW) {
         const __half* src = (hl ? a.in_lo : a.in_hi) + (((size_t)id * IH + (ok ? ih : 0)) * IW + (ok ? iw : 0)) * CIN + o * 8;
         cp_async16_zfill(st + (uint32_t)idx * 16u, src, ok);
       }
-      const __half* wsrc = a.wtc + (size_t)(kd * nocts + o) * (b_bytes / 2);
-      for (int i = tid; i < (int)(b_bytes / 16); i += c3::NPROD) cp_async16_zfill(st + G::A_BYTES + i * 16, wsrc + i * 8, true);
+      const __half* wsrc = a.wtc + (size_t)(kd * ngroups + g) * (b_bytes / 2);
+      for (int i = tid; i < (int)(b_bytes / 16); i += c3::NPROD) cp_async16_zfill(st + a_bytes + i * 16, wsrc + i * 8, true);
       cp_async_commit_group();
       if (u > 0) {
         cp_async_wait_group<1>();   // unit u-1 of this thread has landed
@@ -154,7 +161,7 @@ conv3d_tc_kernel(ConvTcArgs a, int NS, int OD, int OH, int OW) {
         if (MODE == DECONV_S2) { oh = 2 * ch + (cls >> 1); ow = 2 * cw + (cls & 1); valid = ch < IH && cw < IW; }
         else { oh = ch; ow = cw; valid = ch < OH && cw < OW; }
         const size_t vox = valid ? ((size_t)od * OH + oh) * OW + ow : 0;
-        const uint32_t tcol = trow + (uint32_t)((t * NCLS + cls) * NPAD);
+        const uint32_t tcol = trow + (uint32_t)((t * NCLS + (cls ^ (cls >> 1))) * NPAD);   // class order [0, 1, 3, 2]
         float prob = 0.f;
         for (int c16 = 0; c16 < NPAD / 16; ++c16) {
           float v[16];
@@ -205,38 +212,52 @@ conv3d_tc_kernel(ConvTcArgs a, int NS, int OD, int OH, int OW) {
     }
   } else if (tid == c3::NPROD) {
     // ------------------------------------------------------------------------------------------- MMA issue
-    const uint32_t idesc = make_idesc_f16(128, NPAD);
-    const uint32_t btile = (uint32_t)(2 * NPAD * 16);
+    constexpr int NCLS_ = MODE == DECONV_S2 ? 4 : 1;
+    const uint32_t blk = (uint32_t)NPAD * 32u;   // one weight block: NPAD rows x 2 k-chunks
     for (int u = 0; u < U; ++u) {
       const int s = u % NS;
       mbar_wait(bar_full + 8 * s, (uint32_t)((u / NS) & 1));
       tc_fence_after_sync();
-      const uint32_t sA = sbase + s * stage_bytes, sB = sA + G::A_BYTES;
+      const uint32_t sA = sbase + s * stage_bytes, sB = sA + a_bytes;
+      // one fused tap group: A start offset, first weight block, number of blocks (N = nb * NPAD), accumulator column
+      auto issue = [&](uint32_t aoff, int bstart, int nb, int dcol, bool overwrite) {
+        const uint32_t n = (uint32_t)(nb * NPAD);
+        const uint32_t idesc = make_idesc_f16(128, (int)n);
+        const uint32_t t0 = sB + (uint32_t)bstart * 2u * blk, t1 = t0 + (uint32_t)nb * blk;
+        const uint64_t b0 = make_desc(t0, n * 16u, 128), b1 = make_desc(t1, n * 16u, 128);
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int tap = kh * 3 + kw;
-          int sub = 0, rs, cs, cls = 0;
-          bool first_of_acc;
-          if (MODE == CONV_S1) { rs = kh; cs = kw; first_of_acc = tap == 0; }
-          else if (MODE == CONV_S2) {
-            const int ph = kh == 1 ? 0 : 1, pw = kw == 1 ? 0 : 1;
-            sub = ph * 2 + pw; rs = kh == 2 ? 1 : 0; cs = kw == 2 ? 1 : 0; first_of_acc = tap == 0;
+        for (int t = 0; t < NT; ++t) {
+          const uint32_t tacc = tmem_base + (uint32_t)(t * NCLS_ * NPAD + dcol);
+          if (KG == 1) {
+            const uint64_t ad = make_desc(sA + aoff + t * 128, G::PLANE, G::PITCH);       // K = [hi | lo] of one octet
+            mma_f16_ss(tacc, ad, b0, idesc, overwrite ? 0u : 1u);                        // x [w_hi ; w_hi]
+            mma_f16_ss(tacc, ad, b1, idesc, 1u);                                         // x [w_lo ; 0]
           } else {
-            const int ph = kh == 1 ? 0 : 1, pw = kw == 1 ? 0 : 1;
-            cls = ph * 2 + pw; rs = kh == 0 ? 1 : 0; cs = kw == 0 ? 1 : 0;
-            first_of_acc = (kh == (ph ? 0 : 1)) && (kw == (pw ? 0 : 1));
+            const uint64_t ah = make_desc(sA + aoff + t * 128, G::PLANE, G::PITCH);       // K = two octets, hi parts
+            const uint64_t al = make_desc(sA + 2 * G::PLANE + aoff + t * 128, G::PLANE, G::PITCH);
+            mma_f16_ss(tacc, al, b0, idesc, overwrite ? 0u : 1u);                        // x_lo * w_hi
+            mma_f16_ss(tacc, ah, b1, idesc, 1u);                                         // x_hi * w_lo
+            mma_f16_ss(tacc, ah, b0, idesc, 1u);                                         // x_hi * w_hi
           }
-          const uint32_t aoff = (uint32_t)sub * G::SUB_BYTES + (uint32_t)(rs * PC + cs) * 16u;
-          const uint64_t b0 = make_desc(sB + (tap * 2 + 0) * btile, (uint32_t)NPAD * 16u, 128);
-          const uint64_t b1 = make_desc(sB + (tap * 2 + 1) * btile, (uint32_t)NPAD * 16u, 128);
+        }
+      };
+      if (MODE == DECONV_S2) {
+        // input shift (dih, diw) -> fused classes; weight blocks in conv3d_tc_pack's order
+        issue(0u, 0, 4, 0, u == 0);                                   // (0,0): taps (1,1) (1,2) (2,2) (2,1) -> classes 0 1 3 2
+        issue(16u, 4, 2, NPAD, false);                                // (0,1): taps (1,0) (2,0)             -> classes 1 3
+        issue((uint32_t)PC * 16u, 6, 2, 2 * NPAD, false);             // (1,0): taps (0,2) (0,1)             -> classes 3 2
+        issue((uint32_t)(PC + 1) * 16u, 8, 1, 2 * NPAD, false);       // (1,1): tap  (0,0)                   -> class 3
+      } else {
 #pragma unroll
-          for (int t = 0; t < NT; ++t) {
-            const uint64_t ad = make_desc(sA + aoff + t * 128, G::PLANE, G::PITCH);
-            const uint32_t tacc = tmem_base + (uint32_t)((MODE == DECONV_S2 ? t * 4 + cls : t) * NPAD);
-            mma_f16_ss(tacc, ad, b0, idesc, (u == 0 && first_of_acc) ? 0u : 1u);
-            mma_f16_ss(tacc, ad, b1, idesc, 1u);
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            int sub = 0, rs = kh, cs = kw;
+            if (MODE == CONV_S2) {
+              sub = (kh == 1 ? 0 : 2) + (kw == 1 ? 0 : 1);
+              rs = kh == 2 ? 1 : 0; cs = kw == 2 ? 1 : 0;
+            }
+            issue((uint32_t)sub * G::SUB_BYTES + (uint32_t)(rs * PC + cs) * 16u, kh * 3 + kw, 1, 0, u == 0 && kh == 0 && kw == 0);
           }
         }
       }
@@ -250,36 +271,62 @@ conv3d_tc_kernel(ConvTcArgs a, int NS, int OD, int OH, int OW) {
 }
 
 // ------------------------------------------------------------------------------------------------------- host
-size_t conv3d_tc_packed_halves(int cin, int cout) { return (size_t)3 * (cin / 8) * (c3::slab_bytes(cout) / 2); }
+int conv3d_tc_kg(int mode, int cin) { return (mode != CONV_S2 && cin >= 16) ? 2 : 1; }
 
+size_t conv3d_tc_packed_halves(int mode, int cin, int cout) {
+  return (size_t)3 * (cin / 8 / conv3d_tc_kg(mode, cin)) * (c3::slab_bytes(cout) / 2);
+}
+
+// slab (kd, channel group g) = 9 weight blocks of [2 MMA variants][2 k-chunks][NPAD rows][8 halves]; blocks that are fused
+// into one MMA are interleaved as [variant][k-chunk][nb * NPAD rows][8] (conv: nb = 1; deconv: 4, 2, 2, 1)
 __global__ void conv3d_tc_pack_kernel(const float* __restrict__ w32, __half* __restrict__ out, int cin, int cout, int NPAD,
-                                      size_t total) {
+                                      int KG, int deconv, size_t total) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  // i = ((((((kd * nocts + o) * 9 + tap) * 2 + mm) * 2 + kc) * NPAD + n) * 8 + e
-  int e = (int)(i & 7);
-  size_t q = i >> 3;
-  int n = (int)(q % NPAD); q /= NPAD;
-  int kc = (int)(q & 1); q >>= 1;
-  int mm = (int)(q & 1); q >>= 1;
-  int tap = (int)(q % 9); q /= 9;
-  const int nocts = cin / 8;
-  int o = (int)(q % nocts);
-  int kd = (int)(q / nocts);
+  const int e = (int)(i & 7);
+  const size_t q = i >> 3;                           // 16-byte chunk
+  const int per_slab = NPAD * 36;
+  const int slab = (int)(q / per_slab), c = (int)(q % per_slab);
+  const int ngroups = cin / 8 / KG;
+  const int kd = slab / ngroups, g = slab % ngroups;
+  int mm, kc, n, kh, kw;
+  if (!deconv) {
+    n = c % NPAD;
+    int r = c / NPAD;
+    kc = r & 1; r >>= 1;
+    mm = r & 1; r >>= 1;
+    kh = r / 3; kw = r % 3;
+  } else {
+    const int bs[4] = {0, 4, 6, 8}, nbs[4] = {4, 2, 2, 1};
+    const int tkh[4][4] = {{1, 1, 2, 2}, {1, 2, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    const int tkw[4][4] = {{1, 2, 2, 1}, {0, 0, 0, 0}, {2, 1, 0, 0}, {0, 0, 0, 0}};
+    int t = 3;
+    for (int k = 0; k < 3; ++k)
+      if (c < bs[k + 1] * 4 * NPAD) { t = k; break; }
+    const int cc = c - bs[t] * 4 * NPAD, nb = nbs[t];
+    mm = cc / (2 * nb * NPAD);
+    kc = (cc / (nb * NPAD)) & 1;
+    const int nn = cc % (nb * NPAD);
+    const int b = nn / NPAD;
+    n = nn % NPAD;
+    kh = tkh[t][b]; kw = tkw[t][b];
+  }
+  const int ci = (KG == 1 ? g : g * 2 + kc) * 8 + e;
   float w = 0.f;
-  if (n < cout) w = w32[((size_t)(kd * 9 + tap) * cin + o * 8 + e) * cout + n];
+  if (n < cout) w = w32[((size_t)((kd * 3 + kh) * 3 + kw) * cin + ci) * cout + n];
   const __half hi = __float2half_rn(w);
   const __half lo = __float2half_rn(w - __half2float(hi));
   __half v;
-  if (mm == 0) v = hi;
-  else v = kc == 0 ? lo : __float2half_rn(0.f);
+  if (KG == 1) v = mm == 0 ? hi : (kc == 0 ? lo : __float2half_rn(0.f));
+  else v = mm == 0 ? hi : lo;
   out[i] = v;
 }
 
-int conv3d_tc_pack(const float* w32, __half* out, int cin, int cout, cudaStream_t s) {
+int conv3d_tc_pack(const float* w32, __half* out, int mode, int cin, int cout, cudaStream_t s) {
   MVSF_REQUIRE(w32 && out && cin % 8 == 0 && cout % 8 == 0, "conv3d_tc_pack: bad arguments");
-  const size_t total = conv3d_tc_packed_halves(cin, cout);
-  conv3d_tc_pack_kernel<<<cdiv((long long)total, 256), 256, 0, s>>>(w32, out, cin, cout, c3::npad(cout), total);
+  const size_t total = conv3d_tc_packed_halves(mode, cin, cout);
+  conv3d_tc_pack_kernel<<<cdiv((long long)total, 256), 256, 0, s>>>(w32, out, cin, cout, c3::npad(cout),
+                                                                     conv3d_tc_kg(mode, cin), mode == DECONV_S2 ? 1 : 0, total);
   MVSF_LAUNCH_CHECK("conv3d_tc_pack");
   return MVSF_OK;
 }
@@ -349,13 +396,13 @@ static int launch_mode(const ConvTcArgs& a, cudaStream_t s) {
   const int nts[3] = {4, 2, 1};
   for (int k = 0; k < 3; ++k) {
     const int nt = nts[k];
-    const uint32_t a_bytes = nt == 4 ? c3::Geo<MODE, 4>::A_BYTES : (nt == 2 ? c3::Geo<MODE, 2>::A_BYTES : c3::Geo<MODE, 1>::A_BYTES);
+    const uint32_t a_bytes = a.KG * (nt == 4 ? c3::Geo<MODE, 4>::A_BYTES : (nt == 2 ? c3::Geo<MODE, 2>::A_BYTES : c3::Geo<MODE, 1>::A_BYTES));
     const long long ctas = (long long)cdiv(cells_w, 8 * nt) * cdiv(cells_h, 16) * OD;
     const int cols = nt * NPAD * (MODE == DECONV_S2 ? 4 : 1);
     const bool fits = cols <= 256 && 2 * (size_t)(a_bytes + b_bytes) + 128 <= 113 * 1024;
     if ((fits && ctas >= 2 * 148) || nt == 1) { best_nt = nt; break; }
   }
-  const uint32_t a_bytes = best_nt == 4 ? c3::Geo<MODE, 4>::A_BYTES : (best_nt == 2 ? c3::Geo<MODE, 2>::A_BYTES : c3::Geo<MODE, 1>::A_BYTES);
+  const uint32_t a_bytes = a.KG * (best_nt == 4 ? c3::Geo<MODE, 4>::A_BYTES : (best_nt == 2 ? c3::Geo<MODE, 2>::A_BYTES : c3::Geo<MODE, 1>::A_BYTES));
   const size_t stage = (size_t)a_bytes + b_bytes;
   int NS = 3;
   if (3 * stage + 128 > 113 * 1024) NS = 2;                       // keep two CTAs per SM when three stages do not fit
@@ -376,6 +423,7 @@ int launch_conv3d_tc(const ConvTcArgs& a, int mode, int out_mode, cudaStream_t s
   MVSF_REQUIRE(a.CIN % 8 == 0 && a.CIN >= 8 && a.CIN <= 64 && a.COUT % 8 == 0 && a.COUT >= 8 && a.COUT <= 64 &&
                    (a.COUT == 8 || a.COUT % 16 == 0), "conv3d_tc: channels must be 8, 16, 32, 48 or 64");
   MVSF_REQUIRE(a.SD == 1 || a.SD == 2, "conv3d_tc: depth stride must be 1 or 2");
+  MVSF_REQUIRE(a.KG == conv3d_tc_kg(mode, a.CIN), "conv3d_tc: KG must be conv3d_tc_kg(mode, CIN) (it fixes the weight slab layout)");
   MVSF_REQUIRE(((uintptr_t)a.in_hi & 15) == 0 && ((uintptr_t)a.in_lo & 15) == 0 && ((uintptr_t)a.wtc & 15) == 0,
                "conv3d_tc: operands must be 16-byte aligned");
   if (out_mode == OUT_SPLIT) {
@@ -407,7 +455,7 @@ extern "C" int mvsf_conv3d_tc_layer(int mode, int sd, const float* in, const flo
   else if (mode == CONV_S2) { OD = (ID - 1) / sd + 1; OH = (IH - 1) / 2 + 1; OW = (IW - 1) / 2 + 1; }
   else { OD = ID * sd; OH = IH * 2; OW = IW * 2; }
   const size_t nin = (size_t)ID * IH * IW * cin, nout = (size_t)OD * OH * OW * cout;
-  const size_t nw = align_up(conv3d_tc_packed_halves(cin, cout), 64);
+  const size_t nw = align_up(conv3d_tc_packed_halves(mode, cin, cout), 64);
   const size_t need = (2 * nin + 4 * nout + nw) * sizeof(__half) + 256;
   if (workspace_bytes < need) return fail(MVSF_ERR_WORKSPACE, "conv3d_tc_layer: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t s = (cudaStream_t)stream;
@@ -418,12 +466,12 @@ extern "C" int mvsf_conv3d_tc_layer(int mode, int sd, const float* in, const flo
   int rc;
   if ((rc = launch_split_vec8(in, xin, xin + nin, nin, s))) return rc;
   if (skip && (rc = launch_split_vec8(skip, xskip, xskip + nout, nout, s))) return rc;
-  if ((rc = conv3d_tc_pack(w32, wtc, cin, cout, s))) return rc;
+  if ((rc = conv3d_tc_pack(w32, wtc, mode, cin, cout, s))) return rc;
   ConvTcArgs a{};
   a.in_hi = xin; a.in_lo = xin + nin; a.wtc = wtc; a.bias = w32 + (size_t)27 * cin * cout;
   if (skip) { a.skip_hi = xskip; a.skip_lo = xskip + nout; }
   a.out_hi = xout; a.out_lo = xout + nout;
-  a.CIN = cin; a.COUT = cout; a.SD = sd; a.ID = ID; a.IH = IH; a.IW = IW;
+  a.CIN = cin; a.COUT = cout; a.SD = sd; a.ID = ID; a.IH = IH; a.IW = IW; a.KG = conv3d_tc_kg(mode, cin);
   if ((rc = launch_conv3d_tc(a, mode, OUT_SPLIT, s))) return rc;
   return launch_merge_vec8(xout, xout + nout, out, nout, s);
 }

@@ -381,10 +381,11 @@ static int unet_forward(int kind, const float* vol, const float* wts, float* log
 
 // ------------------------------------------------------------------------------------ tensor-core path (conv3d_tc.cu)
 static const int kLayerCh[9][2] = {{8, 16}, {16, 16}, {16, 32}, {32, 32}, {32, 64}, {64, 64}, {64, 32}, {32, 16}, {16, 8}};
+static const int kLayerMode[9] = {CONV_S2, CONV_S1, CONV_S2, CONV_S1, CONV_S2, CONV_S1, DECONV_S2, DECONV_S2, DECONV_S2};
 
 static size_t tc_total_halves() {
   size_t n = 0;
-  for (int l = 0; l < 9; ++l) n += conv3d_tc_packed_halves(kLayerCh[l][0], kLayerCh[l][1]);
+  for (int l = 0; l < 9; ++l) n += conv3d_tc_packed_halves(kLayerMode[l], kLayerCh[l][0], kLayerCh[l][1]);
   return n;
 }
 
@@ -410,13 +411,13 @@ static int unet_forward_tc(int kind, const float* vol, const float* wts, const _
     for (int l = 0; l < 9; ++l) {
       w32[l] = p; w16[l] = q;
       p += layer_floats(kLayerCh[l][0], kLayerCh[l][1]);
-      q += conv3d_tc_packed_halves(kLayerCh[l][0], kLayerCh[l][1]);
+      q += conv3d_tc_packed_halves(kLayerMode[l], kLayerCh[l][0], kLayerCh[l][1]);
     }
   }
   const float* wp = w32[8] + layer_floats(16, 8);
   int rc;
   if ((rc = launch_split_vec8(vol, v0, v0 + n0, n0, s))) return rc;
-  auto conv = [&](int l, int mode, const __half* in, size_t nin, __half* out, size_t nout, const __half* skip, size_t nskip,
+  auto conv = [&](int l, const __half* in, size_t nin, __half* out, size_t nout, const __half* skip, size_t nskip,
                   int ID, int IH, int IW) {
     ConvTcArgs a{};
     a.in_hi = in; a.in_lo = in + nin;
@@ -424,23 +425,24 @@ static int unet_forward_tc(int kind, const float* vol, const float* wts, const _
     a.skip_hi = skip; a.skip_lo = skip ? skip + nskip : nullptr;
     a.out_hi = out; a.out_lo = out + nout;
     a.CIN = kLayerCh[l][0]; a.COUT = kLayerCh[l][1]; a.SD = SD; a.ID = ID; a.IH = IH; a.IW = IW;
-    return launch_conv3d_tc(a, mode, OUT_SPLIT, s);
+    a.KG = conv3d_tc_kg(kLayerMode[l], a.CIN);
+    return launch_conv3d_tc(a, kLayerMode[l], OUT_SPLIT, s);
   };
-  if ((rc = conv(0, CONV_S2, v0, n0, t1, n1, nullptr, 0, D, H, W))) return rc;
-  if ((rc = conv(1, CONV_S1, t1, n1, c2, n1, nullptr, 0, D1, H1, W1))) return rc;
-  if ((rc = conv(2, CONV_S2, c2, n1, t3, n2, nullptr, 0, D1, H1, W1))) return rc;
-  if ((rc = conv(3, CONV_S1, t3, n2, c4, n2, nullptr, 0, D2, H2, W2))) return rc;
-  if ((rc = conv(4, CONV_S2, c4, n2, t5, n3, nullptr, 0, D2, H2, W2))) return rc;
-  if ((rc = conv(5, CONV_S1, t5, n3, c6, n3, nullptr, 0, D3, H3, W3))) return rc;
+  if ((rc = conv(0, v0, n0, t1, n1, nullptr, 0, D, H, W))) return rc;
+  if ((rc = conv(1, t1, n1, c2, n1, nullptr, 0, D1, H1, W1))) return rc;
+  if ((rc = conv(2, c2, n1, t3, n2, nullptr, 0, D1, H1, W1))) return rc;
+  if ((rc = conv(3, t3, n2, c4, n2, nullptr, 0, D2, H2, W2))) return rc;
+  if ((rc = conv(4, c4, n2, t5, n3, nullptr, 0, D2, H2, W2))) return rc;
+  if ((rc = conv(5, t5, n3, c6, n3, nullptr, 0, D3, H3, W3))) return rc;
   // x = conv4 + conv7(x) -> t3 ; x = conv2 + conv9(x) -> t1 ; x = conv0 + conv11(x)
-  if ((rc = conv(6, DECONV_S2, c6, n3, t3, n2, c4, n2, D3, H3, W3))) return rc;
-  if ((rc = conv(7, DECONV_S2, t3, n2, t1, n1, c2, n1, D2, H2, W2))) return rc;
+  if ((rc = conv(6, c6, n3, t3, n2, c4, n2, D3, H3, W3))) return rc;
+  if ((rc = conv(7, t3, n2, t1, n1, c2, n1, D2, H2, W2))) return rc;
   {
     ConvTcArgs a{};
     a.in_hi = t1; a.in_lo = t1 + n1;
     a.wtc = w16[8]; a.bias = w32[8] + (size_t)27 * 16 * 8;
     a.skip32 = vol;
-    a.CIN = 16; a.COUT = 8; a.SD = SD; a.ID = D1; a.IH = H1; a.IW = W1;
+    a.CIN = 16; a.COUT = 8; a.SD = SD; a.ID = D1; a.IH = H1; a.IW = W1; a.KG = conv3d_tc_kg(DECONV_S2, 16);
     if (kind == 1) {
       a.out32 = logits; a.probw = wp;
       if ((rc = launch_conv3d_tc(a, DECONV_S2, OUT_PROB, s))) return rc;
@@ -487,10 +489,10 @@ int mvsf_costreg_unet_pack_tc(const float* wts, void* wts_tc, size_t wts_tc_byte
   const float* p = wts;
   __half* q = reinterpret_cast<__half*>(wts_tc);
   for (int l = 0; l < 9; ++l) {
-    int rc = conv3d_tc_pack(p, q, kLayerCh[l][0], kLayerCh[l][1], (cudaStream_t)stream);
+    int rc = conv3d_tc_pack(p, q, kLayerMode[l], kLayerCh[l][0], kLayerCh[l][1], (cudaStream_t)stream);
     if (rc) return rc;
     p += layer_floats(kLayerCh[l][0], kLayerCh[l][1]);
-    q += conv3d_tc_packed_halves(kLayerCh[l][0], kLayerCh[l][1]);
+    q += conv3d_tc_packed_halves(kLayerMode[l], kLayerCh[l][0], kLayerCh[l][1]);
   }
   return MVSF_OK;
 }

@@ -1,0 +1,63 @@
+"""Host-side staging for the hot path: pinned host batches are uploaded on a copy stream into one of two resident
+device slots while the previous batch is still being computed, so the PCIe transfer of the FPN pyramids (531 MB per
+DTU reference view) overlaps the kernels instead of preceding them.
+
+The reference's test loop uploads synchronously (`sample_cuda = tocuda(sample)` then `model.forward(...)`,
+test.py / base trainer); this is the drop-in equivalent for a caller that already holds the feature pyramids on the
+host.  Only streams, events and `Tensor.copy_` are used here - no computation."""
+import torch
+
+
+class PrefetchingRunner:
+    def __init__(self, net, device, slots=2):
+        self.net = net
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = [dict(bufs=None, ready=torch.cuda.Event(), free=torch.cuda.Event(), tag=None) for _ in range(slots)]
+        self._next = 0
+
+    # a batch is (features: dict[str, Tensor], proj_matrices: dict[str, Tensor], depth_values: Tensor), pinned host tensors
+    @staticmethod
+    def _flat(batch):
+        f, p, d = batch
+        return [f[k] for k in sorted(f)] + [p[k] for k in sorted(p)] + [d]
+
+    @staticmethod
+    def _unflat(batch, flat):
+        f, p, _ = batch
+        kf, kp = sorted(f), sorted(p)
+        return ({k: flat[i] for i, k in enumerate(kf)}, {k: flat[len(kf) + i] for i, k in enumerate(kp)}, flat[-1])
+
+    def _upload(self, slot, batch):
+        host = self._flat(batch)
+        if slot["bufs"] is None or any(b.shape != h.shape or b.stride() != h.stride() for b, h in zip(slot["bufs"], host)):
+            slot["bufs"] = [torch.empty_strided(h.shape, h.stride(), dtype=h.dtype, device=self.device) for h in host]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot["free"])     # the kernels that read this slot have finished
+            for b, h in zip(slot["bufs"], host):
+                b.copy_(h, non_blocking=True)
+            slot["ready"].record(self.copy_stream)
+        slot["tag"] = id(batch)
+
+    def bytes_per_batch(self, batch):
+        return sum(t.numel() * t.element_size() for t in self._flat(batch))
+
+    @torch.no_grad()
+    def run(self, batch, next_batch=None, tmp=(5.0, 5.0, 5.0, 1.0)):
+        """Runs the hot path on `batch` (uploaded now unless a previous call prefetched it) and starts the upload of
+        `next_batch` so that it overlaps this call's kernels.  Returns the reference's output dict (device tensors)."""
+        cur = next((s for s in self.slots if s["tag"] == id(batch)), None)
+        if cur is None:
+            cur = self.slots[self._next]
+            self._next = (self._next + 1) % len(self.slots)
+            self._upload(cur, batch)
+        compute = torch.cuda.current_stream(self.device)
+        compute.wait_event(cur["ready"])
+        if next_batch is not None and not any(s["tag"] == id(next_batch) for s in self.slots if s is not cur):
+            nxt = next(s for s in self.slots if s is not cur)
+            self._upload(nxt, next_batch)
+        f, p, d = self._unflat(batch, cur["bufs"])
+        out = self.net.forward_features(f, p, d, tmp)
+        cur["free"].record(compute)
+        cur["tag"] = None                                  # consumed: the same host batch is uploaded again next time
+        return out
