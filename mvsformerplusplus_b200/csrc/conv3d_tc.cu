@@ -1,27 +1,31 @@
 // 3x3x3 convolutions of the U-Net cost regularisers (models/module.py:367-408 CostRegNet, :453-504 CostRegNet3D) as
 // implicit GEMMs on the 5th-generation tensor cores, fp32-class accuracy.
 //
-//   * activations live in HBM as two fp16 tensors (hi, lo; x ~= hi + lo carries 22 mantissa bits), NDHWC.  A CTA owns a
-//     tile of 16 (h) x 8*NT (w) cells of one depth slice.  Per (input depth slice, channel octet) "unit" the producers
-//     cp.async the halo of the tile into shared memory as PLANES of voxel octets: plane[row][col] = 8 channels = 16 bytes.
-//     Eight w-neighbours are then 128 contiguous bytes = one UMMA "core matrix" of the canonical no-swizzle K-major
-//     layout, the h rows are the 8-row groups (SBO = row pitch) and the hi / lo planes are the two K-chunks of a K = 16
-//     MMA (LBO = plane size).  A filter tap (kh, kw) is nothing but a different descriptor start address: no im2col;
-//   * a unit carries KG channel octets.  KG = 1: per tap two tcgen05.mma.kind::f16 (M = 128 cells, N = Cout, K = 16)
+//   * activations live in HBM as two fp16 tensors (hi, lo; x ~= hi + lo carries 22 mantissa bits), NDHWC.  A tile is
+//     16 (h) x 8*NT (w) cells of one depth slice.  Per (input depth slice, group of KG channel octets) "unit" ONE thread
+//     issues TMA box loads (cp.async.bulk.tensor.5d over (c, w, h, d, hi|lo); the conv padding is TMA's out-of-bounds
+//     zero fill) that land the halo of the tile in shared memory as PLANES of voxel octets: plane[row][col] = 8 channels
+//     = 16 bytes.  Eight w-neighbours are then 128 contiguous bytes = one UMMA "core matrix" of the canonical no-swizzle
+//     K-major layout, the h rows are the 8-row groups (SBO = row pitch) and hi / lo planes (or the two octets) are the
+//     two K-chunks of a K = 16 MMA (LBO = plane distance).  A filter tap (kh, kw) is nothing but a different descriptor
+//     start address: no im2col, no per-element address arithmetic anywhere;
+//   * KG = 1: per tap two tcgen05.mma.kind::f16 (M = 128 cells, N = Cout, K = 16)
 //         [x_hi | x_lo] x [w_hi ; w_hi]   and   [x_hi | x_lo] x [w_lo ; 0]       (x_lo*w_lo ~ 2^-22 is dropped)
 //     KG = 2 (16 channels per unit): K = 16 spans the two octets and three MMAs x_lo*w_hi, x_hi*w_lo, x_hi*w_hi are
-//     issued; fp32 accumulation in TMEM; the weight slabs come pre-arranged from conv3d_tc_pack and are streamed
-//     with the unit through the same cp.async ring.  The MMAs are bound by the shared-memory read of the A operand
-//     (4 KB per instruction at 128 B/clk), so fewer, wider instructions is what counts;
-//   * stride-(SD,2,2) convolutions keep four parity planes (even/odd h x even/odd w) so that every tap is again a dense
-//     plane access; transposed convolutions run in gather form over INPUT cells with four accumulators, one per output
-//     parity class (every (kh, kw) tap feeds exactly one class).  Taps that read the same input shift (dih, diw) are
-//     fused along N: the class accumulators sit in TMEM in the order [0, 1, 3, 2] so that the 4 / 2 / 2 / 1 classes fed
-//     by the shifts (0,0) / (0,1) / (1,0) / (1,1) are contiguous column ranges - 4 wide MMAs instead of 9 narrow ones;
-//   * warps 0-3: producers, then the epilogue (one TMEM lane = one cell per thread: bias (folded BatchNorm), ReLU, skip
-//     add, fp16 hi|lo split or the fused 1x1x1 `prob` conv); warp 4: one thread issues the MMAs; mbarrier ring
-//     full[s] / empty[s]; tcgen05.commit releases a stage.
+//     issued; fp32 accumulation in TMEM; the weight slabs come pre-arranged from conv3d_tc_pack and travel with the
+//     unit (one cp.async.bulk) through the same mbarrier ring (expect_tx / complete_tx);
+//   * stride-(SD,2,2) convolutions keep four parity planes (even/odd h x even/odd w, one strided tensor map each) so
+//     that every tap is again a dense plane access; transposed convolutions run in gather form over INPUT cells with
+//     four accumulators, one per output parity class (every (kh, kw) tap feeds exactly one class).  Taps that read the
+//     same input shift (dih, diw) are fused along N: the class accumulators sit in TMEM in the order [0, 1, 3, 2] so
+//     that the 4 / 2 / 2 / 1 classes fed by the shifts (0,0) / (0,1) / (1,0) / (1,1) are contiguous column ranges;
+//   * persistent, warp-specialised CTAs (one per SM, tiles strided by gridDim.x): warp 0 = TMA producer, warp 1 = MMA
+//     issuer, warps 2-9 = two epilogue warpgroups (one TMEM lane = one cell per thread: bias (folded BatchNorm), ReLU,
+//     skip add, fp16 hi|lo split or the fused 1x1x1 `prob` conv).  Rings: full[s]/empty[s] for the operand stages,
+//     accf[b]/acce[b] for the two TMEM accumulator buffers, so loads, MMAs and the epilogue of consecutive tiles overlap.
 #include "conv3d_tc.cuh"
+
+#include <cuda.h>
 
 #include "linear_tc.cuh"
 #include "umma.cuh"
@@ -31,45 +35,44 @@ namespace mvsf {
 using namespace umma;
 
 namespace c3 {
-constexpr int NPROD = 128, THREADS = 160, MAX_STAGES = 4;
+constexpr int NEPI = 256, THREADS = 64 + NEPI, MAX_STAGES = 8;   // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 template <int MODE, int NT>
 struct Geo {
   static constexpr int TW = 8 * NT, TH = 16;
   static constexpr int PR = MODE == CONV_S1 ? TH + 2 : TH + 1;   // plane rows
   static constexpr int PC = MODE == CONV_S1 ? TW + 2 : TW + 1;   // plane columns (voxel octets)
   static constexpr int NSUB = MODE == CONV_S2 ? 4 : 1;           // parity sub-planes
-  static constexpr uint32_t SUB_BYTES = PR * PC * 16;
-  static constexpr uint32_t PLANE = NSUB * SUB_BYTES;            // one octet's plane set; order [hi|lo][octet of the unit]
-  static constexpr uint32_t A_BYTES = 2 * PLANE;                 // per octet of the unit (hi + lo)
+  static constexpr uint32_t SUB_BYTES = PR * PC * 16;            // one plane; a TMA box = hi plane + lo plane
+  static constexpr uint32_t PAIR = (2 * SUB_BYTES + 127) / 128 * 128;
+  static constexpr uint32_t OCT_BYTES = NSUB * PAIR;             // everything of one channel octet
   static constexpr uint32_t PITCH = PC * 16;
 };
 __host__ __device__ inline int npad(int cout) { return cout < 16 ? 16 : cout; }
-__host__ __device__ inline uint32_t slab_bytes(int cout) { return (uint32_t)npad(cout) * 576u; }  // 9 taps x 2 MMAs x (2 x NPAD x 16 B)
+__host__ __device__ inline uint32_t slab_bytes(int cout) { return (uint32_t)npad(cout) * 576u; }  // 9 blocks x 2 variants x (2 x NPAD x 16 B)
+
+struct alignas(64) Maps { CUtensorMap m[4]; };   // CONV_S2: one map per (h, w) parity; otherwise m[0]
+
+__device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA tile load of a 5-D box (c, w, h, d, hi/lo); out-of-range coordinates (the conv padding) are filled with zeros
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 }  // namespace c3
 
-template <int MODE, int NT, int OUT>
-__global__ void __launch_bounds__(c3::THREADS)
-conv3d_tc_kernel(ConvTcArgs a, int NS, int OD, int OH, int OW) {
-  using G = c3::Geo<MODE, NT>;
-  constexpr int PR = G::PR, PC = G::PC, NSUB = G::NSUB;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int CIN = a.CIN, COUT = a.COUT, SD = a.SD, ID = a.ID, IH = a.IH, IW = a.IW;
-  const int NPAD = c3::npad(COUT);
-  const uint32_t b_bytes = c3::slab_bytes(COUT);
-  const int KG = a.KG;                                            // channel octets per unit
-  const uint32_t a_bytes = (uint32_t)KG * G::A_BYTES;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bars = sbase + NS * stage_bytes;                 // full[4] | empty[4] | accf | tmem slot
-  const uint32_t bar_full = bars, bar_empty = bars + 32, bar_accf = bars + 64;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + NS * stage_bytes + 72);
-
-  const int od = blockIdx.z;
-  const int c0h = blockIdx.y * 16, c0w = blockIdx.x * G::TW;     // first cell of the tile (output cell; DECONV: input cell)
-
-  // depth taps of this slice: (kd, id) pairs
-  int kd0 = 0, kd1 = 0, kd2 = 0, id0 = 0, id1 = 0, id2 = 0, nd = 0;
+// depth taps (kd, id) of output slice od
+struct DepthTaps { int n, kd[3], id[3]; };
+template <int MODE>
+__device__ __forceinline__ DepthTaps depth_taps(int od, int SD, int ID) {
+  DepthTaps t;
+  t.n = 0;
 #pragma unroll
   for (int kd = 0; kd < 3; ++kd) {
     int id;
@@ -77,197 +80,239 @@ conv3d_tc_kernel(ConvTcArgs a, int NS, int OD, int OH, int OW) {
     if (MODE == CONV_S1) id = od + kd - 1;
     else if (MODE == CONV_S2) id = od * SD + kd - 1;
     else {
-      int num = od + 1 - kd;
+      const int num = od + 1 - kd;
       if (SD == 1) id = num;
       else { ok = (num & 1) == 0; id = num >> 1; }
     }
-    ok = ok && id >= 0 && id < ID;
-    if (ok) {
-      if (nd == 0) { kd0 = kd; id0 = id; }
-      else if (nd == 1) { kd1 = kd; id1 = id; }
-      else { kd2 = kd; id2 = id; }
-      ++nd;
+    if (ok && id >= 0 && id < ID) { t.kd[t.n] = kd; t.id[t.n] = id; ++t.n; }
+  }
+  return t;
+}
+
+template <int MODE, int OUT>
+__device__ __forceinline__ void conv_epilogue_item(const ConvTcArgs& a, uint32_t tcol, int NPAD, bool valid, size_t vox) {
+  const int COUT = a.COUT;
+  float prob = 0.f;
+  for (int c16 = 0; c16 < NPAD / 16; ++c16) {
+    float v[16];
+    tmem_ld16(tcol + c16 * 16, v);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int c0 = c16 * 16 + g * 8;
+      if (c0 >= COUT) continue;
+      float x[8];
+      const float4 b0 = ldg4(a.bias + c0), b1 = ldg4(a.bias + c0 + 4);
+      x[0] = fmaxf(v[g * 8 + 0] + b0.x, 0.f); x[1] = fmaxf(v[g * 8 + 1] + b0.y, 0.f);
+      x[2] = fmaxf(v[g * 8 + 2] + b0.z, 0.f); x[3] = fmaxf(v[g * 8 + 3] + b0.w, 0.f);
+      x[4] = fmaxf(v[g * 8 + 4] + b1.x, 0.f); x[5] = fmaxf(v[g * 8 + 5] + b1.y, 0.f);
+      x[6] = fmaxf(v[g * 8 + 6] + b1.z, 0.f); x[7] = fmaxf(v[g * 8 + 7] + b1.w, 0.f);
+      if (!valid) continue;
+      if (OUT == OUT_SPLIT) {
+        if (a.skip_hi) {
+          const uint4 sh = *reinterpret_cast<const uint4*>(a.skip_hi + vox * COUT + c0);
+          const uint4 sl = *reinterpret_cast<const uint4*>(a.skip_lo + vox * COUT + c0);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&sh);
+          const __half2* l2 = reinterpret_cast<const __half2*>(&sl);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fh = __half22float2(h2[e]), fl = __half22float2(l2[e]);
+            x[2 * e] += fh.x + fl.x;
+            x[2 * e + 1] += fh.y + fl.y;
+          }
+        }
+        split_store8(a.out_hi + vox * COUT + c0, a.out_lo + vox * COUT + c0, x);
+      } else {
+        const float4 s0 = ldg4(a.skip32 + vox * COUT + c0), s1 = ldg4(a.skip32 + vox * COUT + c0 + 4);
+        x[0] += s0.x; x[1] += s0.y; x[2] += s0.z; x[3] += s0.w;
+        x[4] += s1.x; x[5] += s1.y; x[6] += s1.z; x[7] += s1.w;
+        if (OUT == OUT_F32) {
+          float* op = a.out32 + vox * COUT + c0;
+          *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+          *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
+        } else {
+          if (c0 == 0) prob = __ldg(a.probw + COUT);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) prob = fmaf(x[e], __ldg(a.probw + c0 + e), prob);
+        }
+      }
     }
   }
+  if (OUT == OUT_PROB && valid) a.out32[vox] = prob;
+}
+
+// Persistent kernel: CTA i works on tiles i, i + gridDim.x, ...; tile = (output depth slice, 16 x 8*NT cells).
+template <int MODE, int NT, int OUT>
+__global__ void __launch_bounds__(c3::THREADS, 1)
+conv3d_tc_kernel(const __grid_constant__ c3::Maps maps, ConvTcArgs a, int NS, int OD, int OH, int OW, int tiles_w,
+                 int tiles_h, int ntiles) {
+  using G = c3::Geo<MODE, NT>;
+  constexpr int PC = G::PC, NSUB = G::NSUB;
+  constexpr int NCLS = MODE == DECONV_S2 ? 4 : 1;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int CIN = a.CIN, COUT = a.COUT, SD = a.SD, ID = a.ID, IH = a.IH, IW = a.IW;
+  const int NPAD = c3::npad(COUT);
+  const int KG = a.KG;                                            // channel octets per unit
+  const uint32_t b_bytes = c3::slab_bytes(COUT);
+  const uint32_t a_bytes = (uint32_t)KG * G::OCT_BYTES;
+  const uint32_t stage_bytes = (a_bytes + b_bytes + 127u) / 128u * 128u;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + NS * stage_bytes;                 // full[8] | empty[8] | accf[2] | acce[2] | tmem slot
+  const uint32_t bar_full = bars, bar_empty = bars + 64, bar_accf = bars + 128, bar_acce = bars + 144;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + NS * stage_bytes + 160);
   const int ngroups = (CIN >> 3) / KG;
-  const int U = nd * ngroups;
+  const uint32_t acc_cols = (uint32_t)(NT * NCLS * NPAD);         // one accumulator buffer
 
   uint32_t ncols = 32;
-  {
-    const uint32_t want = (uint32_t)(NT * NPAD * (MODE == DECONV_S2 ? 4 : 1));
-    while (ncols < want) ncols <<= 1;
-  }
+  while (ncols < 2 * acc_cols) ncols <<= 1;
   if (tid == 0) {
-    for (int i = 0; i < c3::MAX_STAGES; ++i) { mbar_init(bar_full + 8 * i, c3::NPROD); mbar_init(bar_empty + 8 * i, 1); }
-    mbar_init(bar_accf, 1);
+    for (int i = 0; i < c3::MAX_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_accf, 1); mbar_init(bar_accf + 8, 1);
+    mbar_init(bar_acce, c3::NEPI); mbar_init(bar_acce + 8, c3::NEPI);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), ncols);
+  if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), ncols);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (tid < c3::NPROD) {
-    // ------------------------------------------------------------------------------------------- producers
-    for (int u = 0; u < U; ++u) {
-      const int s = u % NS;
-      mbar_wait(bar_empty + 8 * s, (uint32_t)(((u / NS) & 1) ^ 1));
-      const int ds = u / ngroups, g = u - ds * ngroups;
-      const int kd = ds == 0 ? kd0 : (ds == 1 ? kd1 : kd2);
-      const int id = ds == 0 ? id0 : (ds == 1 ? id1 : id2);
-      const uint32_t st = sbase + s * stage_bytes;
-      constexpr int PER = NSUB * PR * PC;
-      for (int idx = tid; idx < 2 * KG * PER; idx += c3::NPROD) {
-        const int pl = idx / PER, rem = idx - pl * PER;          // plane set index = hl * KG + octet
-        const int hl = pl >= KG ? 1 : 0, o = g * KG + (pl - hl * KG);
-        const int sub = rem / (PR * PC), rc = rem - sub * (PR * PC);
-        const int r = rc / PC, c = rc - r * PC;
-        int ih, iw;
-        if (MODE == CONV_S1) { ih = c0h - 1 + r; iw = c0w - 1 + c; }
-        else if (MODE == CONV_S2) { ih = 2 * (c0h + r) - (sub >> 1); iw = 2 * (c0w + c) - (sub & 1); }
-        else { ih = c0h + r; iw = c0w + c; }
-        const bool ok = ih >= 0 && ih < IH && iw >= 0 && iw < IW;
-        const __half* src = (hl ? a.in_lo : a.in_hi) + (((size_t)id * IH + (ok ? ih : 0)) * IW + (ok ? iw : 0)) * CIN + o * 8;
-        cp_async16_zfill(st + (uint32_t)idx * 16u, src, ok);
-      }
-      const __half* wsrc = a.wtc + (size_t)(kd * ngroups + g) * (b_bytes / 2);
-      for (int i = tid; i < (int)(b_bytes / 16); i += c3::NPROD) cp_async16_zfill(st + a_bytes + i * 16, wsrc + i * 8, true);
-      cp_async_commit_group();
-      if (u > 0) {
-        cp_async_wait_group<1>();   // unit u-1 of this thread has landed
-        fence_proxy_async();
-        mbar_arrive(bar_full + 8 * ((u - 1) % NS));
+  if (warp == 0) {
+    // --------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, od = tile / (tiles_w * tiles_h);
+        const int c0h = th * 16, c0w = tw * G::TW;
+        const DepthTaps dt = depth_taps<MODE>(od, SD, ID);
+        for (int ds = 0; ds < dt.n; ++ds) {
+          for (int grp = 0; grp < ngroups; ++grp, ++g) {
+            const int s = g % NS;
+            mbar_wait(bar_empty + 8 * s, (uint32_t)(((g / NS) & 1) ^ 1));
+            const uint32_t st = sbase + s * stage_bytes, full = bar_full + 8 * s;
+            c3::expect_tx(full, (uint32_t)(KG * NSUB) * 2u * G::SUB_BYTES + b_bytes);
+            for (int og = 0; og < KG; ++og) {
+              const int c = (grp * KG + og) * 8;
+#pragma unroll
+              for (int sub = 0; sub < NSUB; ++sub) {
+                int w0, h0;
+                if (MODE == CONV_S1) { w0 = c0w - 1; h0 = c0h - 1; }
+                else if (MODE == CONV_S2) { w0 = c0w - (sub & 1); h0 = c0h - (sub >> 1); }   // odd plane: index j <-> 2j + 1
+                else { w0 = c0w; h0 = c0h; }
+                c3::tma_load_5d(st + (uint32_t)(og * NSUB + sub) * G::PAIR, &maps.m[sub], c, w0, h0, dt.id[ds], 0, full);
+              }
+            }
+            c3::bulk_load(st + a_bytes, a.wtc + (size_t)(dt.kd[ds] * ngroups + grp) * (b_bytes / 2), b_bytes, full);
+          }
+        }
       }
     }
-    cp_async_wait_group<0>();
-    fence_proxy_async();
-    mbar_arrive(bar_full + 8 * ((U - 1) % NS));
-
-    // ------------------------------------------------------------------------------------------- epilogue
-    mbar_wait(bar_accf, 0u);
-    tc_fence_after_sync();
-    const int m = warp * 32 + lane;              // TMEM lane = GEMM row = cell (h = m / 8, w = m % 8) of an M-tile
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int ch = c0h + (m >> 3);
-    constexpr int NCLS = MODE == DECONV_S2 ? 4 : 1;
+  } else if (warp == 1) {
+    // --------------------------------------------------------------------------------------- MMA issue
+    if (lane == 0) {
+      const uint32_t blk = (uint32_t)NPAD * 32u;   // one weight block: NPAD rows x 2 k-chunks
+      uint32_t g = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int od = tile / (tiles_w * tiles_h);
+        const DepthTaps dt = depth_taps<MODE>(od, SD, ID);
+        const int U = dt.n * ngroups;
+        const int buf = it & 1;
+        mbar_wait(bar_acce + 8 * buf, (uint32_t)(((it >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator buffer
+        tc_fence_after_sync();
+        const uint32_t tacc0 = tmem_base + (uint32_t)buf * acc_cols;
+        for (int u = 0; u < U; ++u, ++g) {
+          const int s = g % NS;
+          mbar_wait(bar_full + 8 * s, (uint32_t)((g / NS) & 1));
+          tc_fence_after_sync();
+          const uint32_t sA = sbase + s * stage_bytes, sB = sA + a_bytes;
+          // one fused tap group: A start offset, first weight block, number of blocks (N = nb * NPAD), accumulator column
+          auto issue = [&](uint32_t aoff, int bstart, int nb, int dcol, bool overwrite) {
+            const uint32_t n = (uint32_t)(nb * NPAD);
+            const uint32_t idesc = make_idesc_f16(128, (int)n);
+            const uint32_t t0 = sB + (uint32_t)bstart * 2u * blk, t1 = t0 + (uint32_t)nb * blk;
+            const uint64_t b0 = make_desc(t0, n * 16u, 128), b1 = make_desc(t1, n * 16u, 128);
+            // consecutive MMAs go to different accumulators (M-tiles): back-to-back MMAs on one accumulator serialise
+            if (KG == 1) {
+#pragma unroll
+              for (int t = 0; t < NT; ++t)                                                       // K = [hi | lo] of one octet
+                mma_f16_ss(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::SUB_BYTES, G::PITCH), b0,
+                           idesc, overwrite ? 0u : 1u);                                        // x [w_hi ; w_hi]
+#pragma unroll
+              for (int t = 0; t < NT; ++t)
+                mma_f16_ss(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::SUB_BYTES, G::PITCH), b1,
+                           idesc, 1u);                                                         // x [w_lo ; 0]
+            } else {
+#pragma unroll
+              for (int t = 0; t < NT; ++t)                                                       // K = two octets; lo planes
+                mma_f16_ss(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol),
+                           make_desc(sA + G::SUB_BYTES + aoff + t * 128, G::OCT_BYTES, G::PITCH), b0, idesc, overwrite ? 0u : 1u);  // x_lo * w_hi
+#pragma unroll
+              for (int t = 0; t < NT; ++t)
+                mma_f16_ss(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::OCT_BYTES, G::PITCH), b1,
+                           idesc, 1u);                                                         // x_hi * w_lo
+#pragma unroll
+              for (int t = 0; t < NT; ++t)
+                mma_f16_ss(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::OCT_BYTES, G::PITCH), b0,
+                           idesc, 1u);                                                         // x_hi * w_hi
+            }
+          };
+          if (MODE == DECONV_S2) {
+            // input shift (dih, diw) -> fused classes; weight blocks in conv3d_tc_pack's order
+            issue(0u, 0, 4, 0, u == 0);                                   // (0,0): taps (1,1) (1,2) (2,2) (2,1) -> classes 0 1 3 2
+            issue(16u, 4, 2, NPAD, false);                                // (0,1): taps (1,0) (2,0)             -> classes 1 3
+            issue((uint32_t)PC * 16u, 6, 2, 2 * NPAD, false);             // (1,0): taps (0,2) (0,1)             -> classes 3 2
+            issue((uint32_t)(PC + 1) * 16u, 8, 1, 2 * NPAD, false);       // (1,1): tap  (0,0)                   -> class 3
+          } else {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                int sub = 0, rs = kh, cs = kw;
+                if (MODE == CONV_S2) {
+                  sub = (kh == 1 ? 0 : 2) + (kw == 1 ? 0 : 1);
+                  rs = kh == 2 ? 1 : 0; cs = kw == 2 ? 1 : 0;
+                }
+                issue((uint32_t)sub * G::PAIR + (uint32_t)(rs * PC + cs) * 16u, kh * 3 + kw, 1, 0, u == 0 && kh == 0 && kw == 0);
+              }
+            }
+          }
+          commit(bar_empty + 8 * s);
+        }
+        commit(bar_accf + 8 * buf);
+      }
+    }
+  } else {
+    // --------------------------------------------------------------------------------------- epilogue (2 warpgroups)
+    const int wg = (warp - 2) >> 2, quarter = warp & 3;   // a warp may only touch TMEM lanes 32 * (warp % 4) ...
+    const int m = quarter * 32 + lane;                    // TMEM lane = GEMM row = cell (h = m / 8, w = m % 8) of an M-tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, od = tile / (tiles_w * tiles_h);
+      const int buf = it & 1;
+      mbar_wait(bar_accf + 8 * buf, (uint32_t)((it >> 1) & 1));
+      tc_fence_after_sync();
+      const uint32_t trow = tmem_base + (uint32_t)buf * acc_cols + ((uint32_t)(quarter * 32) << 16);
+      const int ch = th * 16 + (m >> 3);
 #pragma unroll 1
-    for (int t = 0; t < NT; ++t) {
-      const int cw = c0w + t * 8 + (m & 7);
-#pragma unroll 1
-      for (int cls = 0; cls < NCLS; ++cls) {
+      for (int item = wg; item < NT * NCLS; item += 2) {
+        const int t = item / NCLS, cls = item % NCLS;
+        const int cw = tw * G::TW + t * 8 + (m & 7);
         int oh, ow;
         bool valid;
         if (MODE == DECONV_S2) { oh = 2 * ch + (cls >> 1); ow = 2 * cw + (cls & 1); valid = ch < IH && cw < IW; }
         else { oh = ch; ow = cw; valid = ch < OH && cw < OW; }
         const size_t vox = valid ? ((size_t)od * OH + oh) * OW + ow : 0;
         const uint32_t tcol = trow + (uint32_t)((t * NCLS + (cls ^ (cls >> 1))) * NPAD);   // class order [0, 1, 3, 2]
-        float prob = 0.f;
-        for (int c16 = 0; c16 < NPAD / 16; ++c16) {
-          float v[16];
-          tmem_ld16(tcol + c16 * 16, v);
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int c0 = c16 * 16 + g * 8;
-            if (c0 >= COUT) continue;
-            float x[8];
-            const float4 b0 = ldg4(a.bias + c0), b1 = ldg4(a.bias + c0 + 4);
-            x[0] = fmaxf(v[g * 8 + 0] + b0.x, 0.f); x[1] = fmaxf(v[g * 8 + 1] + b0.y, 0.f);
-            x[2] = fmaxf(v[g * 8 + 2] + b0.z, 0.f); x[3] = fmaxf(v[g * 8 + 3] + b0.w, 0.f);
-            x[4] = fmaxf(v[g * 8 + 4] + b1.x, 0.f); x[5] = fmaxf(v[g * 8 + 5] + b1.y, 0.f);
-            x[6] = fmaxf(v[g * 8 + 6] + b1.z, 0.f); x[7] = fmaxf(v[g * 8 + 7] + b1.w, 0.f);
-            if (!valid) continue;
-            if (OUT == OUT_SPLIT) {
-              if (a.skip_hi) {
-                const uint4 sh = *reinterpret_cast<const uint4*>(a.skip_hi + vox * COUT + c0);
-                const uint4 sl = *reinterpret_cast<const uint4*>(a.skip_lo + vox * COUT + c0);
-                const __half2* h2 = reinterpret_cast<const __half2*>(&sh);
-                const __half2* l2 = reinterpret_cast<const __half2*>(&sl);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 fh = __half22float2(h2[e]), fl = __half22float2(l2[e]);
-                  x[2 * e] += fh.x + fl.x;
-                  x[2 * e + 1] += fh.y + fl.y;
-                }
-              }
-              split_store8(a.out_hi + vox * COUT + c0, a.out_lo + vox * COUT + c0, x);
-            } else {
-              const float4 s0 = ldg4(a.skip32 + vox * COUT + c0), s1 = ldg4(a.skip32 + vox * COUT + c0 + 4);
-              x[0] += s0.x; x[1] += s0.y; x[2] += s0.z; x[3] += s0.w;
-              x[4] += s1.x; x[5] += s1.y; x[6] += s1.z; x[7] += s1.w;
-              if (OUT == OUT_F32) {
-                float* op = a.out32 + vox * COUT + c0;
-                *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
-              } else {
-                if (c0 == 0) prob = __ldg(a.probw + COUT);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) prob = fmaf(x[e], __ldg(a.probw + c0 + e), prob);
-              }
-            }
-          }
-        }
-        if (OUT == OUT_PROB && valid) a.out32[vox] = prob;
+        conv_epilogue_item<MODE, OUT>(a, tcol, NPAD, valid, vox);
       }
+      tc_fence_before_sync();
+      mbar_arrive(bar_acce + 8 * buf);
     }
-  } else if (tid == c3::NPROD) {
-    // ------------------------------------------------------------------------------------------- MMA issue
-    constexpr int NCLS_ = MODE == DECONV_S2 ? 4 : 1;
-    const uint32_t blk = (uint32_t)NPAD * 32u;   // one weight block: NPAD rows x 2 k-chunks
-    for (int u = 0; u < U; ++u) {
-      const int s = u % NS;
-      mbar_wait(bar_full + 8 * s, (uint32_t)((u / NS) & 1));
-      tc_fence_after_sync();
-      const uint32_t sA = sbase + s * stage_bytes, sB = sA + a_bytes;
-      // one fused tap group: A start offset, first weight block, number of blocks (N = nb * NPAD), accumulator column
-      auto issue = [&](uint32_t aoff, int bstart, int nb, int dcol, bool overwrite) {
-        const uint32_t n = (uint32_t)(nb * NPAD);
-        const uint32_t idesc = make_idesc_f16(128, (int)n);
-        const uint32_t t0 = sB + (uint32_t)bstart * 2u * blk, t1 = t0 + (uint32_t)nb * blk;
-        const uint64_t b0 = make_desc(t0, n * 16u, 128), b1 = make_desc(t1, n * 16u, 128);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const uint32_t tacc = tmem_base + (uint32_t)(t * NCLS_ * NPAD + dcol);
-          if (KG == 1) {
-            const uint64_t ad = make_desc(sA + aoff + t * 128, G::PLANE, G::PITCH);       // K = [hi | lo] of one octet
-            mma_f16_ss(tacc, ad, b0, idesc, overwrite ? 0u : 1u);                        // x [w_hi ; w_hi]
-            mma_f16_ss(tacc, ad, b1, idesc, 1u);                                         // x [w_lo ; 0]
-          } else {
-            const uint64_t ah = make_desc(sA + aoff + t * 128, G::PLANE, G::PITCH);       // K = two octets, hi parts
-            const uint64_t al = make_desc(sA + 2 * G::PLANE + aoff + t * 128, G::PLANE, G::PITCH);
-            mma_f16_ss(tacc, al, b0, idesc, overwrite ? 0u : 1u);                        // x_lo * w_hi
-            mma_f16_ss(tacc, ah, b1, idesc, 1u);                                         // x_hi * w_lo
-            mma_f16_ss(tacc, ah, b0, idesc, 1u);                                         // x_hi * w_hi
-          }
-        }
-      };
-      if (MODE == DECONV_S2) {
-        // input shift (dih, diw) -> fused classes; weight blocks in conv3d_tc_pack's order
-        issue(0u, 0, 4, 0, u == 0);                                   // (0,0): taps (1,1) (1,2) (2,2) (2,1) -> classes 0 1 3 2
-        issue(16u, 4, 2, NPAD, false);                                // (0,1): taps (1,0) (2,0)             -> classes 1 3
-        issue((uint32_t)PC * 16u, 6, 2, 2 * NPAD, false);             // (1,0): taps (0,2) (0,1)             -> classes 3 2
-        issue((uint32_t)(PC + 1) * 16u, 8, 1, 2 * NPAD, false);       // (1,1): tap  (0,0)                   -> class 3
-      } else {
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            int sub = 0, rs = kh, cs = kw;
-            if (MODE == CONV_S2) {
-              sub = (kh == 1 ? 0 : 2) + (kw == 1 ? 0 : 1);
-              rs = kh == 2 ? 1 : 0; cs = kw == 2 ? 1 : 0;
-            }
-            issue((uint32_t)sub * G::SUB_BYTES + (uint32_t)(rs * PC + cs) * 16u, kh * 3 + kw, 1, 0, u == 0 && kh == 0 && kw == 0);
-          }
-        }
-      }
-      commit(bar_empty + 8 * s);
-    }
-    commit(bar_accf);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+  if (warp == 2) tmem_dealloc(tmem_base, ncols);
 }
 
 // ------------------------------------------------------------------------------------------------------- host
@@ -367,18 +412,62 @@ int launch_merge_vec8(const __half* hi, const __half* lo, float* x, size_t n, cu
   return MVSF_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 5-D map (c, w, h, d, hi|lo) over the fp16 activation pair; sh/sw = 2 and (ph, pw) select one parity plane of (h, w)
+static int make_map(CUtensorMap* m, const __half* hi, const __half* lo, int C, int D, int H, int W, int sh, int sw, int ph,
+                    int pw, int box_w, int box_h) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  MVSF_REQUIRE(enc, "conv3d_tc: cuTensorMapEncodeTiled is not available from this driver");
+  const long long lo_off = (lo - hi) * (long long)sizeof(__half);
+  MVSF_REQUIRE(lo_off > 0 && lo_off % 16 == 0, "conv3d_tc: the lo tensor must follow the hi tensor at a 16-byte multiple");
+  const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)((W - pw + sw - 1) / sw), (cuuint64_t)((H - ph + sh - 1) / sh), (cuuint64_t)D, 2};
+  const cuuint64_t strides[4] = {(cuuint64_t)sw * C * 2, (cuuint64_t)sh * W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)lo_off};
+  const cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 2};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  void* base = const_cast<__half*>(hi + ((size_t)ph * W + pw) * C);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MVSF_ERR_CUDA, "conv3d_tc: cuTensorMapEncodeTiled failed (%d) for C=%d D=%d H=%d W=%d", (int)r, C, D, H, W);
+  return MVSF_OK;
+}
+
 template <int MODE, int NT, int OUT>
 static int launch_one(const ConvTcArgs& a, int NS, size_t smem, int OD, int OH, int OW, int cells_h, int cells_w,
-                      cudaStream_t s) {
+                      int num_sms, cudaStream_t s) {
+  using G = c3::Geo<MODE, NT>;
   auto kern = conv3d_tc_kernel<MODE, NT, OUT>;
   static bool configured = false;
   if (!configured) {
     MVSF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  dim3 grid(cdiv(cells_w, 8 * NT), cdiv(cells_h, 16), OD);
-  MVSF_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv3d_tc: volume too large");
-  kern<<<grid, c3::THREADS, smem, s>>>(a, NS, OD, OH, OW);
+  c3::Maps maps;
+  int rc;
+  if (MODE == CONV_S2) {
+    for (int sub = 0; sub < 4; ++sub)
+      if ((rc = make_map(&maps.m[sub], a.in_hi, a.in_lo, a.CIN, a.ID, a.IH, a.IW, 2, 2, sub >> 1, sub & 1, G::PC, G::PR))) return rc;
+  } else {
+    if ((rc = make_map(&maps.m[0], a.in_hi, a.in_lo, a.CIN, a.ID, a.IH, a.IW, 1, 1, 0, 0, G::PC, G::PR))) return rc;
+    maps.m[1] = maps.m[2] = maps.m[3] = maps.m[0];
+  }
+  const int tiles_w = cdiv(cells_w, 8 * NT), tiles_h = cdiv(cells_h, 16);
+  const long long ntiles = (long long)tiles_w * tiles_h * OD;
+  MVSF_REQUIRE(ntiles < (1ll << 30), "conv3d_tc: volume too large");
+  const int grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+  kern<<<grid, c3::THREADS, smem, s>>>(maps, a, NS, OD, OH, OW, tiles_w, tiles_h, (int)ntiles);
   MVSF_LAUNCH_CHECK("conv3d_tc");
   return MVSF_OK;
 }
@@ -389,32 +478,40 @@ static int launch_mode(const ConvTcArgs& a, cudaStream_t s) {
   if (MODE == CONV_S1) { OD = a.ID; OH = a.IH; OW = a.IW; cells_h = OH; cells_w = OW; }
   else if (MODE == CONV_S2) { OD = (a.ID - 1) / a.SD + 1; OH = (a.IH - 1) / 2 + 1; OW = (a.IW - 1) / 2 + 1; cells_h = OH; cells_w = OW; }
   else { OD = a.ID * a.SD; OH = a.IH * 2; OW = a.IW * 2; cells_h = a.IH; cells_w = a.IW; }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    MVSF_CUDA_OK(cudaGetDevice(&dev));
+    MVSF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   const int NPAD = c3::npad(a.COUT);
   const uint32_t b_bytes = c3::slab_bytes(a.COUT);
-  // tile width: the widest tile that still gives every SM two CTAs, fits TMEM twice (256 columns) and 2 stages in half an SM
-  int best_nt = 1;
+  const int ncls = MODE == DECONV_S2 ? 4 : 1;
+  // tile width: the widest tile (least halo) whose two accumulator buffers fit TMEM and that keeps the persistent CTAs busy
+  int best_nt = 0;
+  double best_eff = -1.0;
   const int nts[3] = {4, 2, 1};
+  size_t stage_of[5] = {0, 0, 0, 0, 0};
   for (int k = 0; k < 3; ++k) {
     const int nt = nts[k];
-    const uint32_t a_bytes = a.KG * (nt == 4 ? c3::Geo<MODE, 4>::A_BYTES : (nt == 2 ? c3::Geo<MODE, 2>::A_BYTES : c3::Geo<MODE, 1>::A_BYTES));
-    const long long ctas = (long long)cdiv(cells_w, 8 * nt) * cdiv(cells_h, 16) * OD;
-    const int cols = nt * NPAD * (MODE == DECONV_S2 ? 4 : 1);
-    const bool fits = cols <= 256 && 2 * (size_t)(a_bytes + b_bytes) + 128 <= 113 * 1024;
-    if ((fits && ctas >= 2 * 148) || nt == 1) { best_nt = nt; break; }
+    const uint32_t oct = nt == 4 ? c3::Geo<MODE, 4>::OCT_BYTES : (nt == 2 ? c3::Geo<MODE, 2>::OCT_BYTES : c3::Geo<MODE, 1>::OCT_BYTES);
+    const size_t stage = align_up((size_t)a.KG * oct + b_bytes, 128);
+    stage_of[nt] = stage;
+    if (2 * nt * ncls * NPAD > 512 || 2 * stage + 256 > 227 * 1024) continue;
+    const long long ntiles = (long long)cdiv(cells_w, 8 * nt) * cdiv(cells_h, 16) * OD;
+    const double eff = (double)ntiles / (double)(cdiv(ntiles, num_sms) * (long long)num_sms);
+    if (eff >= 0.85) { best_nt = nt; break; }
+    if (eff > best_eff) { best_eff = eff; best_nt = nt; }
   }
-  const uint32_t a_bytes = a.KG * (best_nt == 4 ? c3::Geo<MODE, 4>::A_BYTES : (best_nt == 2 ? c3::Geo<MODE, 2>::A_BYTES : c3::Geo<MODE, 1>::A_BYTES));
-  const size_t stage = (size_t)a_bytes + b_bytes;
-  int NS = 3;
-  if (3 * stage + 128 > 113 * 1024) NS = 2;                       // keep two CTAs per SM when three stages do not fit
-  if (2 * stage + 128 > 113 * 1024) NS = (int)((226 * 1024 - 128) / stage);  // one CTA per SM
+  MVSF_REQUIRE(best_nt > 0, "conv3d_tc: no tile shape fits (COUT %d)", a.COUT);
+  const size_t stage = stage_of[best_nt];
+  int NS = (int)((227 * 1024 - 256) / stage);
   if (NS > c3::MAX_STAGES) NS = c3::MAX_STAGES;
-  MVSF_REQUIRE(NS >= 2, "conv3d_tc: stage of %zu bytes does not fit twice in shared memory", stage);
-  MVSF_REQUIRE(best_nt * NPAD * (MODE == DECONV_S2 ? 4 : 1) <= 512, "conv3d_tc: accumulators exceed TMEM");
-  const size_t smem = NS * stage + 128;
+  const size_t smem = NS * stage + 256;
   switch (best_nt) {
-    case 4: return launch_one<MODE, 4, OUT>(a, NS, smem, OD, OH, OW, cells_h, cells_w, s);
-    case 2: return launch_one<MODE, 2, OUT>(a, NS, smem, OD, OH, OW, cells_h, cells_w, s);
-    default: return launch_one<MODE, 1, OUT>(a, NS, smem, OD, OH, OW, cells_h, cells_w, s);
+    case 4: return launch_one<MODE, 4, OUT>(a, NS, smem, OD, OH, OW, cells_h, cells_w, num_sms, s);
+    case 2: return launch_one<MODE, 2, OUT>(a, NS, smem, OD, OH, OW, cells_h, cells_w, num_sms, s);
+    default: return launch_one<MODE, 1, OUT>(a, NS, smem, OD, OH, OW, cells_h, cells_w, num_sms, s);
   }
 }
 
