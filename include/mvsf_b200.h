@@ -87,7 +87,7 @@ int mvsf_warp_corr_aggregate(const float* feat, const float* homs, const float* 
 int mvsf_costreg_unet_workspace_bytes(int kind, int C, int D, int H, int W, size_t* bytes);
 /* install time: wts -> wts_tc, the fp16 hi/lo weight slabs of the tcgen05 implicit-GEMM convolutions (csrc/conv3d_tc.cu) */
 int mvsf_costreg_unet_tc_bytes(size_t* bytes);
-int mvsf_costreg_unet_pack_tc(const float* wts, void* wts_tc, size_t wts_tc_bytes, mvsf_stream_t stream);
+int mvsf_costreg_unet_pack_tc(int kind, const float* wts, void* wts_tc, size_t wts_tc_bytes, mvsf_stream_t stream);
 int mvsf_costreg_unet_forward(int kind, const float* volume, const float* wts, const void* wts_tc, float* logits,
                               void* workspace, size_t workspace_bytes, int C, int D, int H, int W, mvsf_stream_t stream);
 

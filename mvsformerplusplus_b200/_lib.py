@@ -23,7 +23,7 @@ SIGNATURES = {
     "mvsf_warp_corr_aggregate": ([P, P, P, P, P, I, I, I, I, I, I, P], I),
     "mvsf_costreg_unet_workspace_bytes": ([I, I, I, I, I, ctypes.POINTER(Z)], I),
     "mvsf_costreg_unet_tc_bytes": ([ctypes.POINTER(Z)], I),
-    "mvsf_costreg_unet_pack_tc": ([P, P, Z, P], I),
+    "mvsf_costreg_unet_pack_tc": ([I, P, P, Z, P], I),
     "mvsf_costreg_unet_forward": ([I, P, P, P, P, P, Z, I, I, I, I, P], I),
     "mvsf_conv3d_tc_layer": ([I, I, P, P, P, P, P, Z, I, I, I, I, I, P], I),
     "mvsf_costreg_tr_workspace_bytes": ([I, I, I, I, ctypes.POINTER(Z)], I),

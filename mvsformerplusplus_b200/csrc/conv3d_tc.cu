@@ -315,27 +315,224 @@ conv3d_tc_kernel(const __grid_constant__ c3::Maps maps, ConvTcArgs a, int NS, in
   if (warp == 2) tmem_dealloc(tmem_base, ncols);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Depth-streaming variant for layers whose DEPTH stride is 1 (every 3x3x3 conv of CostRegNet3D, the stride-1 convs of
+// CostRegNet).  The MMAs above are bound by the shared-memory read of the A operand (4 KB per instruction whatever N is),
+// so instead of visiting an input slice three times - once per output slice it feeds - a work item is a COLUMN: a tile
+// x a run of output depth slices [d0, d1).  Input slice `id` is loaded ONCE and one MMA per tap multiplies it with
+// [W(kd=2) ; W(kd=1) ; W(kd=0)] (N = 3 * Cout), feeding the accumulators of the output slices id-1, id, id+1 at once.
+// The accumulators live in a ring of 4 TMEM slots per M-tile (slot = od % 4, consecutive slots are contiguous columns,
+// a window that wraps is issued as two MMAs); slice id-1 is complete once the MMAs of input slice id have retired and is
+// drained by the epilogue warps while the next input slice is multiplied.  3x fewer A-operand reads and TMA bytes.
+template <int MODE, int NT>
+__global__ void __launch_bounds__(c3::THREADS, 1)
+conv3d_col_kernel(const __grid_constant__ c3::Maps maps, ConvTcArgs a, int NS, int wres, int OH, int OW, int tiles_w,
+                  int tiles_h, int DC, int nitems) {
+  using G = c3::Geo<MODE, NT>;
+  constexpr int PC = G::PC, NSUB = G::NSUB;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int CIN = a.CIN, COUT = a.COUT, D = a.ID;
+  const int NPAD = c3::npad(COUT);
+  const int KG = a.KG;
+  const int ngroups = (CIN >> 3) / KG;
+  const uint32_t slab = (uint32_t)NPAD * 1728u;                   // 9 taps x 2 variants x (2 k-chunks x 3*NPAD rows x 16 B)
+  const uint32_t a_bytes = (uint32_t)KG * G::OCT_BYTES;
+  const uint32_t stage_bytes = (a_bytes + (wres ? 0u : slab) + 127u) / 128u * 128u;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t wbase = sbase;                                   // resident weight slabs (wres)
+  const uint32_t ring = sbase + (wres ? ((uint32_t)ngroups * slab + 127u) / 128u * 128u : 0u);
+  const uint32_t bars = ring + NS * stage_bytes;                  // full[8] | empty[8] | accf[4] | acce[4] | wbar | tmem slot
+  const uint32_t bar_full = bars, bar_empty = bars + 64, bar_accf = bars + 128, bar_acce = bars + 160, bar_w = bars + 192;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bars - sbase) + 200);
+
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)(4 * NT * NPAD)) ncols <<= 1;
+  if (tid == 0) {
+    for (int i = 0; i < c3::MAX_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, c3::NEPI); }
+    mbar_init(bar_w, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), ncols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_hw = tiles_w * tiles_h;
+
+  if (warp == 0) {
+    // --------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      if (wres) {
+        c3::expect_tx(bar_w, (uint32_t)ngroups * slab);
+        for (int grp = 0; grp < ngroups; ++grp) c3::bulk_load(wbase + grp * slab, a.wtc + (size_t)grp * (slab / 2), slab, bar_w);
+      }
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tw = item % tiles_w, th = (item / tiles_w) % tiles_h, ck = item / tiles_hw;
+        const int c0h = th * 16, c0w = tw * G::TW;
+        const int d0 = ck * DC, d1 = min(D, d0 + DC);
+        const int first_id = max(d0 - 1, 0), last_id = min(d1, D - 1);
+        for (int id = first_id; id <= last_id; ++id) {
+          for (int grp = 0; grp < ngroups; ++grp, ++g) {
+            const int s = g % NS;
+            mbar_wait(bar_empty + 8 * s, (uint32_t)(((g / NS) & 1) ^ 1));
+            const uint32_t st = ring + s * stage_bytes, full = bar_full + 8 * s;
+            c3::expect_tx(full, (uint32_t)(KG * NSUB) * 2u * G::SUB_BYTES + (wres ? 0u : slab));
+            for (int og = 0; og < KG; ++og) {
+              const int c = (grp * KG + og) * 8;
+#pragma unroll
+              for (int sub = 0; sub < NSUB; ++sub) {
+                int w0, h0;
+                if (MODE == CONV_S1) { w0 = c0w - 1; h0 = c0h - 1; }
+                else { w0 = c0w - (sub & 1); h0 = c0h - (sub >> 1); }
+                c3::tma_load_5d(st + (uint32_t)(og * NSUB + sub) * G::PAIR, &maps.m[sub], c, w0, h0, id, 0, full);
+              }
+            }
+            if (!wres) c3::bulk_load(st + a_bytes, a.wtc + (size_t)grp * (slab / 2), slab, full);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------------------------------------- MMA issue
+    if (lane == 0) {
+      if (wres) mbar_wait(bar_w, 0u);
+      const uint32_t btile = (uint32_t)NPAD * 96u;    // one (tap, variant) weight tile: 2 k-chunks x 3*NPAD rows x 16 B
+      const uint32_t blbo = (uint32_t)NPAD * 48u;     // k-chunk stride inside a weight tile
+      uint32_t g = 0, pm = 0;                         // pm bit s: parity of the number of completed uses of slot s
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int ck = item / tiles_hw;
+        const int d0 = ck * DC, d1 = min(D, d0 + DC);
+        const int first_id = max(d0 - 1, 0), last_id = min(d1, D - 1);
+        for (int id = first_id; id <= last_id; ++id) {
+          const int oa = max(id - 1, d0), ob = min(id + 1, d1 - 1);       // output slices fed by this input slice
+          const int fa = id == first_id ? oa : id + 1;                    // [fa, ob]: slices that receive their FIRST contribution
+          for (int od = fa; od <= ob; ++od) mbar_wait(bar_acce + 8 * (od & 3), ((pm >> (od & 3)) & 1u) ^ 1u);  // slot drained
+          tc_fence_after_sync();
+          for (int grp = 0; grp < ngroups; ++grp, ++g) {
+            const int s = g % NS;
+            mbar_wait(bar_full + 8 * s, (uint32_t)((g / NS) & 1));
+            tc_fence_after_sync();
+            const uint32_t sA = ring + s * stage_bytes;
+            const uint32_t sB = wres ? wbase + grp * slab : sA + a_bytes;
+            // MMAs of one (tap, variant) over the output slices [x, y]; a window that wraps around the 4-slot ring is split
+            auto mma_range = [&](int x, int y, bool overwrite, uint32_t astart, uint32_t albo, uint32_t tile) {
+              while (x <= y) {
+                const int sx = x & 3;
+                const int len = min(y - x + 1, 4 - sx);
+                const uint32_t n = (uint32_t)(len * NPAD);
+                const uint32_t idesc = make_idesc_f16(128, (int)n);
+                const uint64_t bd = make_desc(tile + (uint32_t)((x - id + 1) * NPAD) * 16u, blbo, 128);
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+                  mma_f16_ss(tmem_base + (uint32_t)((t * 4 + sx) * NPAD), make_desc(astart + t * 128, albo, G::PITCH), bd, idesc,
+                             overwrite ? 0u : 1u);
+                x += len;
+              }
+            };
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                int sub = 0, rs = kh, cs = kw;
+                if (MODE == CONV_S2) {
+                  sub = (kh == 1 ? 0 : 2) + (kw == 1 ? 0 : 1);
+                  rs = kh == 2 ? 1 : 0; cs = kw == 2 ? 1 : 0;
+                }
+                const uint32_t aoff = sA + (uint32_t)sub * G::PAIR + (uint32_t)(rs * PC + cs) * 16u;
+                const uint32_t t0 = sB + (uint32_t)(kh * 3 + kw) * 2u * btile, t1 = t0 + btile;   // w_hi tile, w_lo tile
+                const bool first = grp == 0 && kh == 0 && kw == 0;
+                // variant list: (A start, A k-chunk stride, weight tile)
+                const uint32_t va[3] = {KG == 1 ? aoff : aoff + G::SUB_BYTES, KG == 1 ? aoff : aoff, aoff};
+                const uint32_t vl = KG == 1 ? G::SUB_BYTES : G::OCT_BYTES;
+                const uint32_t vt[3] = {t0, t1, t0};
+                const int nv = KG == 1 ? 2 : 3;     // KG 1: x [w_hi;w_hi], x [w_lo;0]   KG 2: x_lo*w_hi, x_hi*w_lo, x_hi*w_hi
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                  if (v >= nv) break;
+                  if (first && v == 0) {
+                    if (fa > oa) mma_range(oa, fa - 1, false, va[v], vl, vt[v]);
+                    if (fa <= ob) mma_range(fa, ob, true, va[v], vl, vt[v]);
+                  } else {
+                    mma_range(oa, ob, false, va[v], vl, vt[v]);
+                  }
+                }
+              }
+            }
+            commit(bar_empty + 8 * s);
+          }
+          if (id - 1 >= d0) { commit(bar_accf + 8 * ((id - 1) & 3)); pm ^= 1u << ((id - 1) & 3); }
+          if (id == last_id && id <= d1 - 1) { commit(bar_accf + 8 * (id & 3)); pm ^= 1u << (id & 3); }
+        }
+      }
+    }
+  } else {
+    // --------------------------------------------------------------------------------------- epilogue (2 warpgroups)
+    const int wg = (warp - 2) >> 2, quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    uint32_t pm = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int tw = item % tiles_w, th = (item / tiles_w) % tiles_h, ck = item / tiles_hw;
+      const int d0 = ck * DC, d1 = min(D, d0 + DC);
+      const int ch = th * 16 + (m >> 3);
+      for (int od = d0; od < d1; ++od) {
+        const int slot = od & 3;
+        mbar_wait(bar_accf + 8 * slot, (pm >> slot) & 1u);
+        pm ^= 1u << slot;
+        tc_fence_after_sync();
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int t = wg; t < NT; t += 2) {
+          const int cw = tw * G::TW + t * 8 + (m & 7);
+          const bool valid = ch < OH && cw < OW;
+          const size_t vox = valid ? ((size_t)od * OH + ch) * OW + cw : 0;
+          conv_epilogue_item<MODE, OUT_SPLIT>(a, trow + (uint32_t)((t * 4 + slot) * NPAD), NPAD, valid, vox);
+        }
+        tc_fence_before_sync();
+        mbar_arrive(bar_acce + 8 * slot);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, ncols);
+}
+
 // ------------------------------------------------------------------------------------------------------- host
 int conv3d_tc_kg(int mode, int cin) { return (mode != CONV_S2 && cin >= 16) ? 2 : 1; }
+// depth-streaming kernel: convolutions with depth stride 1 whose 3*Cout-wide weight tiles still fit shared memory
+int conv3d_tc_col(int mode, int sd, int cout) { return (mode == CONV_S1 || (mode == CONV_S2 && sd == 1)) && c3::npad(cout) <= 32; }
 
-size_t conv3d_tc_packed_halves(int mode, int cin, int cout) {
+size_t conv3d_tc_packed_halves(int mode, int cin, int cout) {   // the same for both layouts
   return (size_t)3 * (cin / 8 / conv3d_tc_kg(mode, cin)) * (c3::slab_bytes(cout) / 2);
 }
 
 // slab (kd, channel group g) = 9 weight blocks of [2 MMA variants][2 k-chunks][NPAD rows][8 halves]; blocks that are fused
 // into one MMA are interleaved as [variant][k-chunk][nb * NPAD rows][8] (conv: nb = 1; deconv: 4, 2, 2, 1)
+// col layout (depth-streaming kernel): slab (channel group g) = [9 taps][2 variants][2 k-chunks][kd = 2, 1, 0][NPAD rows][8]
 __global__ void conv3d_tc_pack_kernel(const float* __restrict__ w32, __half* __restrict__ out, int cin, int cout, int NPAD,
-                                      int KG, int deconv, size_t total) {
+                                      int KG, int deconv, int col, size_t total) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int e = (int)(i & 7);
   const size_t q = i >> 3;                           // 16-byte chunk
-  const int per_slab = NPAD * 36;
+  const int per_slab = col ? NPAD * 108 : NPAD * 36;
   const int slab = (int)(q / per_slab), c = (int)(q % per_slab);
   const int ngroups = cin / 8 / KG;
-  const int kd = slab / ngroups, g = slab % ngroups;
+  int kd = slab / ngroups, g = slab % ngroups;
   int mm, kc, n, kh, kw;
-  if (!deconv) {
+  if (col) {
+    g = slab;
+    n = c % NPAD;
+    int r = c / NPAD;
+    kd = 2 - r % 3; r /= 3;
+    kc = r & 1; r >>= 1;
+    mm = r & 1; r >>= 1;
+    kh = r / 3; kw = r % 3;
+  } else if (!deconv) {
     n = c % NPAD;
     int r = c / NPAD;
     kc = r & 1; r >>= 1;
@@ -367,11 +564,12 @@ __global__ void conv3d_tc_pack_kernel(const float* __restrict__ w32, __half* __r
   out[i] = v;
 }
 
-int conv3d_tc_pack(const float* w32, __half* out, int mode, int cin, int cout, cudaStream_t s) {
+int conv3d_tc_pack(const float* w32, __half* out, int mode, int sd, int cin, int cout, cudaStream_t s) {
   MVSF_REQUIRE(w32 && out && cin % 8 == 0 && cout % 8 == 0, "conv3d_tc_pack: bad arguments");
   const size_t total = conv3d_tc_packed_halves(mode, cin, cout);
   conv3d_tc_pack_kernel<<<cdiv((long long)total, 256), 256, 0, s>>>(w32, out, cin, cout, c3::npad(cout),
-                                                                     conv3d_tc_kg(mode, cin), mode == DECONV_S2 ? 1 : 0, total);
+                                                                     conv3d_tc_kg(mode, cin), mode == DECONV_S2 ? 1 : 0,
+                                                                     conv3d_tc_col(mode, sd, cout), total);
   MVSF_LAUNCH_CHECK("conv3d_tc_pack");
   return MVSF_OK;
 }
@@ -515,6 +713,82 @@ static int launch_mode(const ConvTcArgs& a, cudaStream_t s) {
   }
 }
 
+
+template <int MODE, int NT>
+static int launch_col_one(const ConvTcArgs& a, int NS, int wres, size_t smem, int OH, int OW, int DC, int num_sms, cudaStream_t s) {
+  using G = c3::Geo<MODE, NT>;
+  auto kern = conv3d_col_kernel<MODE, NT>;
+  static bool configured = false;
+  if (!configured) {
+    MVSF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  c3::Maps maps;
+  int rc;
+  if (MODE == CONV_S2) {
+    for (int sub = 0; sub < 4; ++sub)
+      if ((rc = make_map(&maps.m[sub], a.in_hi, a.in_lo, a.CIN, a.ID, a.IH, a.IW, 2, 2, sub >> 1, sub & 1, G::PC, G::PR))) return rc;
+  } else {
+    if ((rc = make_map(&maps.m[0], a.in_hi, a.in_lo, a.CIN, a.ID, a.IH, a.IW, 1, 1, 0, 0, G::PC, G::PR))) return rc;
+    maps.m[1] = maps.m[2] = maps.m[3] = maps.m[0];
+  }
+  const int tiles_w = cdiv(OW, 8 * NT), tiles_h = cdiv(OH, 16);
+  const long long nitems = (long long)tiles_w * tiles_h * cdiv(a.ID, DC);
+  MVSF_REQUIRE(nitems < (1ll << 30), "conv3d_tc: volume too large");
+  const int grid = (int)(nitems < num_sms ? nitems : num_sms);
+  kern<<<grid, c3::THREADS, smem, s>>>(maps, a, NS, wres, OH, OW, tiles_w, tiles_h, DC, (int)nitems);
+  MVSF_LAUNCH_CHECK("conv3d_col");
+  return MVSF_OK;
+}
+
+template <int MODE>
+static int launch_col(const ConvTcArgs& a, cudaStream_t s) {
+  const int D = a.ID;
+  const int OH = MODE == CONV_S1 ? a.IH : (a.IH - 1) / 2 + 1, OW = MODE == CONV_S1 ? a.IW : (a.IW - 1) / 2 + 1;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    MVSF_CUDA_OK(cudaGetDevice(&dev));
+    MVSF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int NPAD = c3::npad(a.COUT);
+  const int ngroups = a.CIN / 8 / a.KG;
+  const size_t slab = (size_t)NPAD * 1728;
+  const size_t wres_bytes = align_up(ngroups * slab, 128);
+  const int wres = wres_bytes <= 112 * 1024 ? 1 : 0;            // all weight slabs stay resident in shared memory
+  // (tile width, depth run) with the least redundant halo traffic per useful output at full occupancy of the persistent CTAs
+  int best_nt = 0, best_dc = 0, best_ns = 0;
+  size_t best_smem = 0;
+  double best_cost = 1e30;
+  const int nts[3] = {4, 2, 1};
+  for (int k = 0; k < 3; ++k) {
+    const int nt = nts[k];
+    if (4 * nt * NPAD > 512) continue;
+    const uint32_t oct = nt == 4 ? c3::Geo<MODE, 4>::OCT_BYTES : (nt == 2 ? c3::Geo<MODE, 2>::OCT_BYTES : c3::Geo<MODE, 1>::OCT_BYTES);
+    const size_t stage = align_up((size_t)a.KG * oct + (wres ? 0 : slab), 128);
+    const size_t fixed = (wres ? wres_bytes : 0) + 256;
+    int ns = (int)((227 * 1024 - fixed) / stage);
+    if (ns > c3::MAX_STAGES) ns = c3::MAX_STAGES;
+    if (ns < 2) continue;
+    for (int div = 1; div <= 8; div *= 2) {
+      const int dc = cdiv(D, div);
+      if (div > 1 && dc == cdiv(D, div / 2)) continue;
+      const long long items = (long long)cdiv(OW, 8 * nt) * cdiv(OH, 16) * cdiv(D, dc);
+      const double eff = (double)items / (double)(cdiv(items, num_sms) * (long long)num_sms);
+      const double halo_w = MODE == CONV_S1 ? (8.0 * nt + 2) / (8.0 * nt) : (16.0 * nt + 1) / (16.0 * nt);
+      const double halo_d = dc >= D ? 1.0 : (dc + 2.0) / dc;
+      const double cost = halo_w * halo_d / eff;
+      if (cost < best_cost) { best_cost = cost; best_nt = nt; best_dc = dc; best_ns = ns; best_smem = fixed + ns * stage; }
+    }
+  }
+  MVSF_REQUIRE(best_nt > 0, "conv3d_col: no tile shape fits (CIN %d COUT %d)", a.CIN, a.COUT);
+  switch (best_nt) {
+    case 4: return launch_col_one<MODE, 4>(a, best_ns, wres, best_smem, OH, OW, best_dc, num_sms, s);
+    case 2: return launch_col_one<MODE, 2>(a, best_ns, wres, best_smem, OH, OW, best_dc, num_sms, s);
+    default: return launch_col_one<MODE, 1>(a, best_ns, wres, best_smem, OH, OW, best_dc, num_sms, s);
+  }
+}
+
 int launch_conv3d_tc(const ConvTcArgs& a, int mode, int out_mode, cudaStream_t s) {
   MVSF_REQUIRE(a.in_hi && a.in_lo && a.wtc && a.bias, "conv3d_tc: null pointer");
   MVSF_REQUIRE(a.CIN % 8 == 0 && a.CIN >= 8 && a.CIN <= 64 && a.COUT % 8 == 0 && a.COUT >= 8 && a.COUT <= 64 &&
@@ -523,8 +797,10 @@ int launch_conv3d_tc(const ConvTcArgs& a, int mode, int out_mode, cudaStream_t s
   MVSF_REQUIRE(a.KG == conv3d_tc_kg(mode, a.CIN), "conv3d_tc: KG must be conv3d_tc_kg(mode, CIN) (it fixes the weight slab layout)");
   MVSF_REQUIRE(((uintptr_t)a.in_hi & 15) == 0 && ((uintptr_t)a.in_lo & 15) == 0 && ((uintptr_t)a.wtc & 15) == 0,
                "conv3d_tc: operands must be 16-byte aligned");
+  MVSF_REQUIRE(a.col == conv3d_tc_col(mode, a.SD, a.COUT), "conv3d_tc: col must be conv3d_tc_col(mode, SD, COUT) (weight slab layout)");
   if (out_mode == OUT_SPLIT) {
     MVSF_REQUIRE(a.out_hi && a.out_lo, "conv3d_tc: split output missing");
+    if (a.col) return mode == CONV_S1 ? launch_col<CONV_S1>(a, s) : launch_col<CONV_S2>(a, s);
     if (mode == CONV_S1) return launch_mode<CONV_S1, OUT_SPLIT>(a, s);
     if (mode == CONV_S2) return launch_mode<CONV_S2, OUT_SPLIT>(a, s);
     if (mode == DECONV_S2) return launch_mode<DECONV_S2, OUT_SPLIT>(a, s);
@@ -563,12 +839,13 @@ extern "C" int mvsf_conv3d_tc_layer(int mode, int sd, const float* in, const flo
   int rc;
   if ((rc = launch_split_vec8(in, xin, xin + nin, nin, s))) return rc;
   if (skip && (rc = launch_split_vec8(skip, xskip, xskip + nout, nout, s))) return rc;
-  if ((rc = conv3d_tc_pack(w32, wtc, mode, cin, cout, s))) return rc;
+  if ((rc = conv3d_tc_pack(w32, wtc, mode, sd, cin, cout, s))) return rc;
   ConvTcArgs a{};
   a.in_hi = xin; a.in_lo = xin + nin; a.wtc = wtc; a.bias = w32 + (size_t)27 * cin * cout;
   if (skip) { a.skip_hi = xskip; a.skip_lo = xskip + nout; }
   a.out_hi = xout; a.out_lo = xout + nout;
   a.CIN = cin; a.COUT = cout; a.SD = sd; a.ID = ID; a.IH = IH; a.IW = IW; a.KG = conv3d_tc_kg(mode, cin);
+  a.col = conv3d_tc_col(mode, sd, cout);
   if ((rc = launch_conv3d_tc(a, mode, OUT_SPLIT, s))) return rc;
   return launch_merge_vec8(xout, xout + nout, out, nout, s);
 }

@@ -426,6 +426,7 @@ static int unet_forward_tc(int kind, const float* vol, const float* wts, const _
     a.out_hi = out; a.out_lo = out + nout;
     a.CIN = kLayerCh[l][0]; a.COUT = kLayerCh[l][1]; a.SD = SD; a.ID = ID; a.IH = IH; a.IW = IW;
     a.KG = conv3d_tc_kg(kLayerMode[l], a.CIN);
+    a.col = conv3d_tc_col(kLayerMode[l], SD, a.COUT);
     return launch_conv3d_tc(a, kLayerMode[l], OUT_SPLIT, s);
   };
   if ((rc = conv(0, v0, n0, t1, n1, nullptr, 0, D, H, W))) return rc;
@@ -482,14 +483,14 @@ int mvsf_costreg_unet_tc_bytes(size_t* bytes) {
   return MVSF_OK;
 }
 
-int mvsf_costreg_unet_pack_tc(const float* wts, void* wts_tc, size_t wts_tc_bytes, mvsf_stream_t stream) {
-  MVSF_REQUIRE(wts && wts_tc && ((uintptr_t)wts_tc & 15) == 0, "costreg_unet_pack_tc: null or unaligned pointer");
+int mvsf_costreg_unet_pack_tc(int kind, const float* wts, void* wts_tc, size_t wts_tc_bytes, mvsf_stream_t stream) {
+  MVSF_REQUIRE(wts && wts_tc && ((uintptr_t)wts_tc & 15) == 0 && (kind == 0 || kind == 1), "costreg_unet_pack_tc: null or unaligned pointer, or bad kind");
   if (wts_tc_bytes < tc_total_halves() * sizeof(__half))
     return fail(MVSF_ERR_WORKSPACE, "costreg_unet_pack_tc: buffer %zu < %zu bytes", wts_tc_bytes, tc_total_halves() * sizeof(__half));
   const float* p = wts;
   __half* q = reinterpret_cast<__half*>(wts_tc);
   for (int l = 0; l < 9; ++l) {
-    int rc = conv3d_tc_pack(p, q, kLayerMode[l], kLayerCh[l][0], kLayerCh[l][1], (cudaStream_t)stream);
+    int rc = conv3d_tc_pack(p, q, kLayerMode[l], kind == 0 ? 2 : 1, kLayerCh[l][0], kLayerCh[l][1], (cudaStream_t)stream);
     if (rc) return rc;
     p += layer_floats(kLayerCh[l][0], kLayerCh[l][1]);
     q += conv3d_tc_packed_halves(kLayerMode[l], kLayerCh[l][0], kLayerCh[l][1]);

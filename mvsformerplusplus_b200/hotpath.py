@@ -71,14 +71,14 @@ def split_weights_f16(flat):
     return out
 
 
-def pack_unet_tc(flat):
+def pack_unet_tc(kind, flat):
     """fp32 U-Net weight blob (packing.pack_costreg_unet) on the device -> fp16 hi/lo weight slabs of the tcgen05
     implicit-GEMM convolutions (install time, once)."""
     L = _lib.lib()
     need = ctypes.c_size_t(0)
     _lib.check(L.mvsf_costreg_unet_tc_bytes(ctypes.byref(need)), "costreg_unet_tc_bytes")
     out = torch.empty(need.value // 2, device=flat.device, dtype=torch.float16)
-    _lib.check(L.mvsf_costreg_unet_pack_tc(_ptr(flat), _ptr(out), ctypes.c_size_t(need.value), _stream()),
+    _lib.check(L.mvsf_costreg_unet_pack_tc(kind, _ptr(flat), _ptr(out), ctypes.c_size_t(need.value), _stream()),
                "costreg_unet_pack_tc")
     return out
 
@@ -137,7 +137,7 @@ class StageNet(_PackedMixin, nn.Module):
             kind, flat = packing.pack_costreg_unet(sd, "cost_reg.")
             pk["kind"] = kind
             pk["reg"] = flat.to(device)
-            pk["reg_tc"] = pack_unet_tc(pk["reg"])
+            pk["reg_tc"] = pack_unet_tc(kind, pk["reg"])
         self._packed = pk
         return pk
 

@@ -224,6 +224,7 @@ def test_vis_cnn_tile_borders(dev, L):
 # ----------------------------------------------------------------------------------------------- regularisers
 @pytest.mark.parametrize("mode,sd,cin,cout,ID,IH,IW", [
     (0, 1, 16, 16, 3, 16, 32), (0, 1, 32, 32, 2, 20, 44), (0, 1, 64, 64, 4, 9, 13), (0, 1, 16, 16, 5, 48, 160),
+    (0, 1, 16, 16, 9, 64, 1200), (0, 2, 32, 32, 11, 40, 72), (1, 1, 8, 16, 6, 96, 1300), (0, 1, 16, 16, 1, 16, 16),
     (1, 1, 8, 16, 3, 32, 64), (1, 2, 8, 16, 8, 24, 40), (1, 1, 16, 32, 2, 18, 26), (1, 2, 32, 64, 4, 16, 16),
     (2, 1, 64, 32, 2, 9, 12), (2, 2, 32, 16, 3, 16, 24), (2, 1, 16, 8, 3, 20, 36), (2, 2, 16, 8, 2, 8, 8)])
 @pytest.mark.parametrize("skip", [False, True])
@@ -274,7 +275,7 @@ def test_costreg_unet(dev, L, stage, D, H, W):
     v = vol[0].permute(1, 2, 3, 0).contiguous().to(dev)
     from mvsformerplusplus_b200.hotpath import pack_unet_tc
     flat_d = flat.to(dev)
-    flat_tc = pack_unet_tc(flat_d)
+    flat_tc = pack_unet_tc(kind, flat_d)
     ck(L.mvsf_costreg_unet_forward(kind, P(v), P(flat_d), P(flat_tc), P(logits), P(ws), ctypes.c_size_t(ws.numel() * 4),
                                    8, D, H, W, S()), "costreg_unet_forward")
     e = max_abs(logits.cpu(), want)
