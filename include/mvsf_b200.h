@@ -40,6 +40,10 @@ const char* mvsf_last_error(void);
 int mvsf_abi_version(void);
 /* number of kernel launches issued by this library on the calling thread since the last reset (bench.py's gpu_launches) */
 long long mvsf_launch_count(int reset);
+/* opt-in device timers around single kernels launched from inside a multi-kernel entry point ("attention_tc"):
+ * CUDA events on the launching stream; read = device ms + launches since the last read (synchronises, resets). */
+int mvsf_ktimer_enable(int on);
+int mvsf_ktimer_read(const char* name, double* ms, long long* launches);
 
 /* ---- layout helpers at the boundary (reference tensors are NCHW: DINOv2_mvsformer_model.py:95-98) */
 int mvsf_nchw_to_nhwc(const float* src, float* dst, int N, int C, int HW, mvsf_stream_t stream);

@@ -11,6 +11,8 @@ P, I, F, Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 SIGNATURES = {
     "mvsf_abi_version": ([], I),
     "mvsf_launch_count": ([I], ctypes.c_longlong),
+    "mvsf_ktimer_enable": ([I], I),
+    "mvsf_ktimer_read": ([ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)], I),
     "mvsf_nchw_to_nhwc": ([P, P, I, I, I, P], I),
     "mvsf_nhwc_to_nchw": ([P, P, I, I, I, P], I),
     "mvsf_compose_geometry": ([P, I, P, P, P], I),
@@ -78,7 +80,8 @@ class profile_calls:
         L = lib()
         self._orig = {}
         for name in SIGNATURES:
-            if name.endswith("_workspace_bytes") or name in ("mvsf_abi_version", "mvsf_launch_count"):
+            if name.endswith("_workspace_bytes") or name in ("mvsf_abi_version", "mvsf_launch_count", "mvsf_ktimer_enable",
+                                                             "mvsf_ktimer_read"):
                 continue
             fn = getattr(L, name)
             self._orig[name] = fn
@@ -108,3 +111,14 @@ class profile_calls:
             d["ms"] += s.elapsed_time(e)
             d["calls"] += 1
         return out
+
+
+def ktimer_enable(on):
+    check(lib().mvsf_ktimer_enable(1 if on else 0), "ktimer_enable")
+
+
+def ktimer_read(name):
+    """(device ms, launches) recorded around the named kernel since the last read."""
+    ms, n = ctypes.c_double(0.0), ctypes.c_longlong(0)
+    check(lib().mvsf_ktimer_read(name.encode(), ctypes.byref(ms), ctypes.byref(n)), "ktimer_read")
+    return ms.value, n.value

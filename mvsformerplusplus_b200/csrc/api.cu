@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <string>
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace mvsf {
@@ -16,6 +20,26 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 void count_launch(int n) { g_launches += n; }
+
+// Opt-in per-kernel device timers (CUDA events on the launching stream around selected launches): bench.py needs the
+// duration of single kernels that are launched from inside a multi-kernel entry point.
+struct KTimer { std::string name; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; };
+static bool g_ktimer_on = false;
+static std::vector<KTimer> g_ktimers;
+bool ktimer_enabled() { return g_ktimer_on; }
+cudaEvent_t ktimer_begin(const char* name, cudaStream_t s) {
+  KTimer* t = nullptr;
+  for (auto& k : g_ktimers)
+    if (k.name == name) t = &k;
+  if (!t) { g_ktimers.push_back(KTimer{name, {}}); t = &g_ktimers.back(); }
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  t->ev.push_back({a, b});
+  cudaEventRecord(a, s);
+  return b;
+}
+void ktimer_end(cudaEvent_t e, cudaStream_t s) { cudaEventRecord(e, s); }
 
 // [N][C][HW] -> [N][HW][C] through a 32x32 shared-memory tile (coalesced on both sides)
 __global__ void transpose_chw_hwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
@@ -60,6 +84,31 @@ long long mvsf_launch_count(int reset) {
   long long v = mvsf::g_launches;
   if (reset) mvsf::g_launches = 0;
   return v;
+}
+
+int mvsf_ktimer_enable(int on) {
+  mvsf::g_ktimer_on = on != 0;
+  return MVSF_OK;
+}
+/* device milliseconds and launches recorded under `name` since the last read (synchronises the device, then resets) */
+int mvsf_ktimer_read(const char* name, double* ms, long long* launches) {
+  MVSF_REQUIRE(name && ms && launches, "ktimer_read: null pointer");
+  *ms = 0.0;
+  *launches = 0;
+  for (auto& k : mvsf::g_ktimers) {
+    if (k.name != name) continue;
+    for (auto& pr : k.ev) {
+      float t = 0.f;
+      MVSF_CUDA_OK(cudaEventSynchronize(pr.second));
+      MVSF_CUDA_OK(cudaEventElapsedTime(&t, pr.first, pr.second));
+      *ms += t;
+      *launches += 1;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    k.ev.clear();
+  }
+  return MVSF_OK;
 }
 
 int mvsf_nchw_to_nhwc(const float* src, float* dst, int N, int C, int HW, mvsf_stream_t stream) {

@@ -145,6 +145,13 @@ __device__ __forceinline__ float ex2f(float x) {
 //                              tiles on one accumulator biases the result, see profiles/)
 // Two CTAs per SM (<= 113 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's MMAs.
 // ------------------------------------------------------------------------------------------------------------------
+// Debug build (-DMVSF_FA_TRACE, tools/fa_trace.py): clock64 stamps of thread 0's phases for 64 key tiles of one CTA.
+#ifdef MVSF_FA_TRACE
+__device__ long long g_fa_trace[64 * 8];
+#define FA_TRACE(slot) do { if (blockIdx.x == 100 && blockIdx.y == 1 && tid == 0 && j >= 100 && j < 164) g_fa_trace[(j - 100) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define FA_TRACE(slot) do {} while (0)
+#endif
 namespace fa5 {
 using namespace umma;
 constexpr int BM = 128, BN = 128, THREADS = 256;
@@ -251,8 +258,10 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
 
   for (int j = 0; j < ntiles; ++j) {
     // ---- 1. this thread's 64 columns of S(j) -> registers (single wait), partial row maximum -> exchange buffer
+    FA_TRACE(0);
     mbar_wait(bar_s, (uint32_t)(j & 1));
     tc_fence_after_sync();
+    FA_TRACE(1);
     uint32_t sr[2][32];
     tmem_ld32_nowait(tS + trow + half * 64, sr[0]);
     tmem_ld32_nowait(tS + trow + half * 64 + 32, sr[1]);
@@ -276,12 +285,15 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
     cp_async_wait_group<1>();   // K(j+1) and V(j) have landed
     fence_proxy_async();
     tc_fence_before_sync();
+    FA_TRACE(2);
     __syncthreads();
+    FA_TRACE(3);
     if (tid == 0 && j + 1 < ntiles) { tc_fence_after_sync(); issue_s(tS, j + 1); }
     // ---- 3. row maximum, fold O_tile(j-1)
     const float mx = fmaxf(m, fmaxf(pmax, xchg[(half ^ 1) * 128 + row]));
     const float corr = ex2f(m - mx);
     m = mx;
+    FA_TRACE(4);
     if (j > 0) {
       mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
       tc_fence_after_sync();
@@ -291,6 +303,7 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
       for (int d = 0; d < 8; ++d) o[d] = fmaf(o[d], corr_prev, half ? ot[8 + d] : ot[d]);
     }
     corr_prev = corr;
+    FA_TRACE(5);
     float tsum = 0.f;
     load_v(j + 1);   // its stage held V(j-1), released by the P*V product we just waited for
     // ---- 4. P = exp2(S - m), hi/lo split -> shared memory (A operand of P*V); chunk = 8 keys
@@ -317,7 +330,9 @@ attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, _
     // ---- 5. O_tile(j) = P(j) V(j)
     fence_proxy_async();
     tc_fence_before_sync();
+    FA_TRACE(6);
     __syncthreads();
+    FA_TRACE(7);
     if (tid == 0) {
       tc_fence_after_sync();
       const uint32_t sV = sb + OFF_V + (j & 1) * 2 * V_TILE;
@@ -409,7 +424,9 @@ static int run_attention(const float* qkv, float* o, __half* o2, __half* split, 
     MVSF_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa5::SMEM));
     configured = true;
   }
+  cudaEvent_t kt = ktimer_enabled() ? ktimer_begin("attention_tc", s) : nullptr;
   attention_tc_kernel<<<dim3(cdiv(N, fa5::BM), 4), fa5::THREADS, fa5::SMEM, s>>>(split, o, o2, N, Np);
+  if (kt) ktimer_end(kt, s);
   MVSF_LAUNCH_CHECK("attention_tc");
   return MVSF_OK;
 }
@@ -417,6 +434,14 @@ static int run_attention(const float* qkv, float* o, __half* o2, __half* split, 
 }  // namespace mvsf
 
 using namespace mvsf;
+
+#ifdef MVSF_FA_TRACE
+extern "C" int mvsf_debug_fa_trace(long long* out) {
+  MVSF_CUDA_OK(cudaDeviceSynchronize());
+  MVSF_CUDA_OK(cudaMemcpyFromSymbol(out, mvsf::g_fa_trace, sizeof(long long) * 64 * 8));
+  return MVSF_OK;
+}
+#endif
 
 extern "C" {
 
