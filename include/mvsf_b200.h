@@ -94,6 +94,13 @@ int mvsf_costreg_unet_tc_bytes(size_t* bytes);
 int mvsf_costreg_unet_pack_tc(int kind, const float* wts, void* wts_tc, size_t wts_tc_bytes, mvsf_stream_t stream);
 int mvsf_costreg_unet_forward(int kind, const float* volume, const float* wts, const void* wts_tc, float* logits,
                               void* workspace, size_t workspace_bytes, int C, int D, int H, int W, mvsf_stream_t stream);
+/* test seam: ONE 3x3x3 layer of the U-Nets on the tcgen05 implicit-GEMM path, fp32 in / out (module.py:367-504:
+ * Conv3d / strided Conv3d / ConvTranspose3d(output_padding = stride - 1) + folded BN + ReLU, optional skip added after the
+ * ReLU).  mode 0: stride 1, 1: stride (sd,2,2), 2: transposed (sd,2,2).  in [ID][IH][IW][cin]; w32 = [27][cin][cout] then
+ * bias[cout]; skip (or NULL) and out [OD][OH][OW][cout]; workspace >= 4*(nin + 2*nout) + 216*cin*max(cout,16) + 512 bytes. */
+int mvsf_conv3d_tc_layer(int mode, int sd, const float* in, const float* w32, const float* skip, float* out,
+                         void* workspace, size_t workspace_bytes, int cin, int cout, int ID, int IH, int IW,
+                         mvsf_stream_t stream);
 
 /* ---- R1: models/module.py:602-646 PureTransformerCostReg (+ position_encoding.py:164-189 PositionEncoding3D).
  * volume [D][H][W][C] is modified in place by the PE add; pos [3][D][H][W] or NULL.
