@@ -498,3 +498,29 @@ def test_attention_tensor_core_vs_fp64(dev, L, N):
     e_tc, sc = max_abs(o0, want), float(want.abs().max())
     rec(f"attention_N{N}", tc_vs_f64=e_tc, scale=sc)
     assert e_tc < 2.5e-5 * sc  # r1: 1.1e-6 (N=200) .. 4.9e-5 (N=27648, scale 4.3); an fp32 one-thread-per-query kernel measured 4.3e-4
+
+
+def test_prefetching_runner_matches_direct_call(dev):
+    """streaming.PrefetchingRunner (copy stream + two device slots) returns what a direct forward_features on
+    device-resident inputs returns, for alternating batches, with and without prefetch."""
+    import bench
+    from mvsformerplusplus_b200.streaming import PrefetchingRunner
+    net, _ = bench.make_net()
+    net = net.to(dev)
+    wl = bench.WORKLOADS["small"]
+    batches = []
+    for seed in (11, 12, 13):
+        f, p, d = bench.make_inputs(wl, seed)
+        batches.append(({k: v.pin_memory() for k, v in f.items()}, {k: v.pin_memory() for k, v in p.items()}, d.pin_memory()))
+    want = []
+    for f, p, d in batches:
+        out = net.forward_features({k: v.to(dev) for k, v in f.items()}, {k: v.to(dev) for k, v in p.items()}, d.to(dev), bench.TMP)
+        want.append((out["refined_depth"].clone(), out["photometric_confidence"].clone()))
+    runner = PrefetchingRunner(net, dev)
+    order = [0, 1, 2, 0, 2, 1, 1]
+    for i, b in enumerate(order):
+        nxt = batches[order[i + 1]] if i + 1 < len(order) and i % 3 != 2 else None   # every third call: no prefetch
+        out = runner.run(batches[b], next_batch=nxt, tmp=bench.TMP)
+        torch.cuda.synchronize()
+        assert torch.equal(out["refined_depth"], want[b][0]), f"call {i} (batch {b})"
+        assert torch.equal(out["photometric_confidence"], want[b][1])
