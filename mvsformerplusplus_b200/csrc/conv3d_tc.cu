@@ -209,7 +209,7 @@ conv3d_tc_kernel(const __grid_constant__ c3::Maps maps, ConvTcArgs a, int NS, in
     }
   } else if (warp == 1) {
     // --------------------------------------------------------------------------------------- MMA issue
-    if (lane == 0) {
+    {   // converged warp, one elected lane per tcgen05 instruction (see conv3d_col_kernel)
       const uint32_t blk = (uint32_t)NPAD * 32u;   // one weight block: NPAD rows x 2 k-chunks
       uint32_t g = 0;
       int it = 0;
@@ -236,24 +236,24 @@ conv3d_tc_kernel(const __grid_constant__ c3::Maps maps, ConvTcArgs a, int NS, in
             if (KG == 1) {
 #pragma unroll
               for (int t = 0; t < NT; ++t)                                                       // K = [hi | lo] of one octet
-                mma_f16_ss(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::SUB_BYTES, G::PITCH), b0,
+                mma_f16_ss_elect(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::SUB_BYTES, G::PITCH), b0,
                            idesc, overwrite ? 0u : 1u);                                        // x [w_hi ; w_hi]
 #pragma unroll
               for (int t = 0; t < NT; ++t)
-                mma_f16_ss(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::SUB_BYTES, G::PITCH), b1,
+                mma_f16_ss_elect(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::SUB_BYTES, G::PITCH), b1,
                            idesc, 1u);                                                         // x [w_lo ; 0]
             } else {
 #pragma unroll
               for (int t = 0; t < NT; ++t)                                                       // K = two octets; lo planes
-                mma_f16_ss(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol),
+                mma_f16_ss_elect(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol),
                            make_desc(sA + G::SUB_BYTES + aoff + t * 128, G::OCT_BYTES, G::PITCH), b0, idesc, overwrite ? 0u : 1u);  // x_lo * w_hi
 #pragma unroll
               for (int t = 0; t < NT; ++t)
-                mma_f16_ss(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::OCT_BYTES, G::PITCH), b1,
+                mma_f16_ss_elect(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::OCT_BYTES, G::PITCH), b1,
                            idesc, 1u);                                                         // x_hi * w_lo
 #pragma unroll
               for (int t = 0; t < NT; ++t)
-                mma_f16_ss(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::OCT_BYTES, G::PITCH), b0,
+                mma_f16_ss_elect(tacc0 + (uint32_t)(t * NCLS * NPAD + dcol), make_desc(sA + aoff + t * 128, G::OCT_BYTES, G::PITCH), b0,
                            idesc, 1u);                                                         // x_hi * w_hi
             }
           };
@@ -277,9 +277,9 @@ conv3d_tc_kernel(const __grid_constant__ c3::Maps maps, ConvTcArgs a, int NS, in
               }
             }
           }
-          commit(bar_empty + 8 * s);
+          commit_elect(bar_empty + 8 * s);
         }
-        commit(bar_accf + 8 * buf);
+        commit_elect(bar_accf + 8 * buf);
       }
     }
   } else {
@@ -398,7 +398,10 @@ conv3d_col_kernel(const __grid_constant__ c3::Maps maps, ConvTcArgs a, int NS, i
     }
   } else if (warp == 1) {
     // --------------------------------------------------------------------------------------- MMA issue
-    if (lane == 0) {
+    // The whole warp runs this code converged (every value is warp-uniform and lives in uniform registers); one elected
+    // lane issues each tcgen05 instruction.  An `if (lane == 0)` version costs ~20 instructions per MMA (per-instruction
+    // divergence handling + register -> uniform register moves) and the issuing thread is the bottleneck of the kernel.
+    {
       if (wres) mbar_wait(bar_w, 0u);
       const uint32_t btile = (uint32_t)NPAD * 96u;    // one (tap, variant) weight tile: 2 k-chunks x 3*NPAD rows x 16 B
       const uint32_t blbo = (uint32_t)NPAD * 48u;     // k-chunk stride inside a weight tile
@@ -428,8 +431,8 @@ conv3d_col_kernel(const __grid_constant__ c3::Maps maps, ConvTcArgs a, int NS, i
                 const uint64_t bd = make_desc(tile + (uint32_t)((x - id + 1) * NPAD) * 16u, blbo, 128);
 #pragma unroll
                 for (int t = 0; t < NT; ++t)
-                  mma_f16_ss(tmem_base + (uint32_t)((t * 4 + sx) * NPAD), make_desc(astart + t * 128, albo, G::PITCH), bd, idesc,
-                             overwrite ? 0u : 1u);
+                  mma_f16_ss_elect(tmem_base + (uint32_t)((t * 4 + sx) * NPAD), make_desc(astart + t * 128, albo, G::PITCH), bd, idesc,
+                                   overwrite ? 0u : 1u);
                 x += len;
               }
             };
@@ -462,10 +465,10 @@ conv3d_col_kernel(const __grid_constant__ c3::Maps maps, ConvTcArgs a, int NS, i
                 }
               }
             }
-            commit(bar_empty + 8 * s);
+            commit_elect(bar_empty + 8 * s);
           }
-          if (id - 1 >= d0) { commit(bar_accf + 8 * ((id - 1) & 3)); pm ^= 1u << ((id - 1) & 3); }
-          if (id == last_id && id <= d1 - 1) { commit(bar_accf + 8 * (id & 3)); pm ^= 1u << (id & 3); }
+          if (id - 1 >= d0) { commit_elect(bar_accf + 8 * ((id - 1) & 3)); pm ^= 1u << ((id - 1) & 3); }
+          if (id == last_id && id <= d1 - 1) { commit_elect(bar_accf + 8 * (id & 3)); pm ^= 1u << (id & 3); }
         }
       }
     }
