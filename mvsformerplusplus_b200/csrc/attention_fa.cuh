@@ -1,0 +1,323 @@
+// Softmax attention of the stage-1 transformer regulariser (models/module.py:507-600 -> attention.py:141-170), second
+// generation: no CTA-wide barrier in the main loop.  Included by costreg_tr.cu (uses its split_f16 / ex2f helpers).
+//
+// One CTA works on TWO 128-query tiles of one head.
+//   warp 0        bulk-copy producer: K / V^T tiles (pre-tiled by qkv_tile_kernel into the canonical UMMA layouts, 4 KB
+//                 each) through two mbarrier rings; both query tiles share them
+//   warp 1        MMA issuer for both tiles, fully converged, one elected lane per tcgen05 instruction, every shared-memory
+//                 descriptor reduced to "precomputed low word + constant": the issuing warp is the critical resource
+//                 (a tcgen05.mma costs ~50 clk even stand-alone, profiles/r1_ncu_and_microbench_tcgen05.md)
+//   warps 2-5 / 6-9   softmax warpgroup 0 / 1: thread = query row = TMEM lane, 128 key columns in registers, no
+//                 cross-thread traffic; warpgroup 1 starts one phase late so that the two alternate between softmax and
+//                 waiting for their MMAs (ping-pong)
+// S_w(t) = Q_w K(t)^T is issued as soon as warpgroup w has pulled S_w(t-1) out of TMEM, O_w(t) = P_w(t) V(t) as soon as
+// P_w(t) is complete.  P_hi is written back to TENSOR MEMORY (tcgen05.st) and consumed as the A operand of two of the
+// three P*V products; only P_lo travels through shared memory.  The three products accumulate in three separate TMEM
+// accumulators that the softmax thread adds (round to nearest) while folding the tile into its running output.
+#pragma once
+
+namespace fa6 {
+using namespace umma;
+constexpr int NSOFT = 256, THREADS = 64 + NSOFT, NKV = 3;   // 320 threads -> 204 registers: the 128 scores of a row stay in registers
+constexpr uint32_t TILE = 4096;                 // one canonical 128 x 16 (Q, K) or 16 x 128 (V^T) fp16 tile
+constexpr uint32_t LBO_QK = 2048, LBO_V = 256;  // k-chunk strides inside those tiles
+constexpr uint32_t LBO_P = 2048, P_TILE = 16 * LBO_P;
+// Q (2 tiles x hi,lo) | K ring (hi,lo) | V ring (hi,lo) | P_lo (2 warpgroups) | barriers
+constexpr uint32_t OFF_Q = 0, OFF_K = 4 * TILE, OFF_V = OFF_K + NKV * 2 * TILE, OFF_P = OFF_V + NKV * 2 * TILE,
+                   OFF_BAR = OFF_P + 2 * P_TILE;
+constexpr uint32_t SMEM = OFF_BAR + 256;
+// TMEM columns: S_w at 128 w; O_w (3 accumulators x 16) at 256 + 64 w; P_hi_w (64) at 384 + 64 w
+__device__ __forceinline__ uint32_t col_s(int w) { return 128u * w; }
+__device__ __forceinline__ uint32_t col_o(int w) { return 256u + 64u * w; }
+__device__ __forceinline__ uint32_t col_p(int w) { return 384u + 64u * w; }
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// shared-memory descriptor = {low word: start address and k-chunk stride, high word: 8-row-group stride 128 B + version}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3fffu) | ((lbo >> 4) << 16); }
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(e));
+  return e;
+}
+// `el` != 0 on exactly one lane of the converged warp
+__device__ __forceinline__ void mma_ss(uint32_t el, uint32_t d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 q, %0, 0;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%2, %4};\n\tmov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %5, p;\n\t}"
+      ::"r"(el), "r"(d), "r"(alo), "r"(blo), "r"(DESC_HI), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t el, uint32_t d, uint32_t ta, uint32_t blo, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 q, %0, 0;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], db, %5, p;\n\t}"
+      ::"r"(el), "r"(d), "r"(ta), "r"(blo), "r"(DESC_HI), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void commit_e(uint32_t el, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}" ::"r"(el), "r"(bar) : "memory");
+}
+}  // namespace fa6
+
+// tiled layout: 6 planes [Qh, Ql, Kh, Kl, Vh, Vl] of 4 heads x ntiles x 2048 halves.  Q/K tile = [2 k-chunks][128 rows][8];
+// V^T tile = [16 k-chunks of 8 keys][16 dims][8 keys].  Rows / keys >= N are zero.
+__global__ void qkv_tile_kernel(const float* __restrict__ qkv, __half* __restrict__ tiled, int N, int ntiles, float qscale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (token, which, head, octet of 8 dims)
+  const int total = ntiles * 128 * 3 * 4 * 2;
+  if (i >= total) return;
+  const int oct = i & 1, h = (i >> 1) & 3, which = (i >> 3) % 3, tok = i / 24;
+  const size_t plane = (size_t)4 * ntiles * 2048;
+  const int tile = tok >> 7, r = tok & 127;
+  float v[8];
+  if (tok < N) {
+    const float4 a = ldg4(qkv + (size_t)tok * 192 + which * 64 + h * 16 + oct * 8);
+    const float4 b = ldg4(qkv + (size_t)tok * 192 + which * 64 + h * 16 + oct * 8 + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    if (which == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= qscale;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  }
+  __half* ph = tiled + (size_t)(which * 2) * plane + ((size_t)h * ntiles + tile) * 2048;
+  __half* pl = ph + plane;
+  if (which < 2) {
+    split_store8(ph + oct * 1024 + r * 8, pl + oct * 1024 + r * 8, v);
+  } else {
+    const int kc = r >> 3, e = r & 7;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      __half hi, lo;
+      split_f16(v[d], hi, lo);
+      ph[kc * 128 + (oct * 8 + d) * 8 + e] = hi;
+      pl[kc * 128 + (oct * 8 + d) * 8 + e] = lo;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(fa6::THREADS, 1)
+attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, __half* __restrict__ out2, int N, int ntiles) {
+  using namespace fa6;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.y;
+  const int qt0 = blockIdx.x * 2;                               // first of this CTA's two query tiles
+  const size_t plane = (size_t)4 * ntiles * 2048;
+  const __half* base = tiled + (size_t)h * ntiles * 2048;       // + plane index * plane + tile * 2048
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bars = sb + OFF_BAR;
+  const uint32_t bar_q = bars, bar_kf = bars + 8, bar_ke = bar_kf + 8 * NKV, bar_vf = bar_ke + 8 * NKV, bar_ve = bar_vf + 8 * NKV,
+                 bar_sf = bar_ve + 8 * NKV, bar_sfree = bar_sf + 16, bar_pf = bar_sfree + 16, bar_of = bar_pf + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 200);
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < NKV; ++i) { mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, 1); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(bar_sf + 8 * w, 1); mbar_init(bar_sfree + 8 * w, 128); mbar_init(bar_pf + 8 * w, 128); mbar_init(bar_of + 8 * w, 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ producer
+    if (lane == 0) {
+      expect_tx(bar_q, 4 * TILE);
+      for (int w = 0; w < 2; ++w) {
+        const int qt = min(qt0 + w, ntiles - 1);   // an odd tile count repeats the last tile (its results are not stored)
+        bulk_load(sb + OFF_Q + (2 * w) * TILE, base + 0 * plane + (size_t)qt * 2048, TILE, bar_q);
+        bulk_load(sb + OFF_Q + (2 * w + 1) * TILE, base + 1 * plane + (size_t)qt * 2048, TILE, bar_q);
+      }
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t % NKV;
+        const uint32_t par = (uint32_t)(((t / NKV) & 1) ^ 1);
+        mbar_wait(bar_ke + 8 * s, par);
+        expect_tx(bar_kf + 8 * s, 2 * TILE);
+        bulk_load(sb + OFF_K + (2 * s) * TILE, base + 2 * plane + (size_t)t * 2048, TILE, bar_kf + 8 * s);
+        bulk_load(sb + OFF_K + (2 * s + 1) * TILE, base + 3 * plane + (size_t)t * 2048, TILE, bar_kf + 8 * s);
+        mbar_wait(bar_ve + 8 * s, par);
+        expect_tx(bar_vf + 8 * s, 2 * TILE);
+        bulk_load(sb + OFF_V + (2 * s) * TILE, base + 4 * plane + (size_t)t * 2048, TILE, bar_vf + 8 * s);
+        bulk_load(sb + OFF_V + (2 * s + 1) * TILE, base + 5 * plane + (size_t)t * 2048, TILE, bar_vf + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer (converged warp)
+    const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 16);
+    const uint32_t el = elect_one();
+    // low descriptor words of everything that does not move
+    const uint32_t q_hi[2] = {desc_lo(sb + OFF_Q, LBO_QK), desc_lo(sb + OFF_Q + 2 * TILE, LBO_QK)};
+    const uint32_t q_lo[2] = {desc_lo(sb + OFF_Q + TILE, LBO_QK), desc_lo(sb + OFF_Q + 3 * TILE, LBO_QK)};
+    const uint32_t p_lo[2] = {desc_lo(sb + OFF_P, LBO_P), desc_lo(sb + OFF_P + P_TILE, LBO_P)};
+    const uint32_t k0 = desc_lo(sb + OFF_K, LBO_QK), v0 = desc_lo(sb + OFF_V, LBO_V);
+    // one lane polls, the warp reconverges: 32 polling lanes would steal issue slots and shared-memory bandwidth
+    auto wait1 = [&](uint32_t bar, uint32_t parity) {
+      if (lane == 0) mbar_wait(bar, parity);
+      __syncwarp();
+    };
+    auto issue_s = [&](int w, int t) {           // S_w(t) = Q_w K(t)^T  (K(t) has landed)
+      tc_fence_after_sync();
+      const uint32_t kh = k0 + (uint32_t)(t % NKV) * (2 * TILE >> 4), kl = kh + (TILE >> 4);
+      const uint32_t tS = tmem_base + col_s(w);
+      mma_ss(el, tS, q_lo[w], kh, idesc_s, 0u);
+      mma_ss(el, tS, q_hi[w], kl, idesc_s, 1u);
+      mma_ss(el, tS, q_hi[w], kh, idesc_s, 1u);
+      commit_e(el, bar_sf + 8 * w);
+    };
+    auto issue_pv = [&](int w, int u) {          // O_w(u) = P_w(u) V(u)  (V(u) has landed, P_w(u) is complete)
+      tc_fence_after_sync();
+      const uint32_t vh = v0 + (uint32_t)(u % NKV) * (2 * TILE >> 4), vl = vh + (TILE >> 4);
+      const uint32_t tO = tmem_base + col_o(w), tP = tmem_base + col_p(w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t acc = i > 0 ? 1u : 0u;
+        mma_ss(el, tO, p_lo[w] + i * (2 * LBO_P >> 4), vh + i * (2 * LBO_V >> 4), idesc_o, acc);      // P_lo (smem) x V_hi
+        mma_ts(el, tO + 16, tP + i * 8, vl + i * (2 * LBO_V >> 4), idesc_o, acc);                    // P_hi (TMEM) x V_lo
+        mma_ts(el, tO + 32, tP + i * 8, vh + i * (2 * LBO_V >> 4), idesc_o, acc);                    // P_hi x V_hi
+      }
+      commit_e(el, bar_of + 8 * w);
+    };
+    // Static schedule = the order in which the events arrive when the two warpgroups alternate (warpgroup 1 starts one
+    // softmax phase after warpgroup 0): sfree0(t), pfull0(t), sfree1(t), pfull1(t), sfree0(t+1), ...
+    wait1(bar_q, 0u);
+    wait1(bar_kf, 0u);
+    issue_s(0, 0);
+    for (int t = 0; t < ntiles; ++t) {
+      const int tn = t + 1;
+      if (tn < ntiles) {
+        wait1(bar_sfree, (uint32_t)(t & 1));                                      // S_0(t) is in registers
+        wait1(bar_kf + 8 * (tn % NKV), (uint32_t)((tn / NKV) & 1));
+        issue_s(0, tn);
+      }
+      wait1(bar_pf, (uint32_t)(t & 1));                                           // P_0(t) complete, O_0(t-1) folded
+      wait1(bar_vf + 8 * (t % NKV), (uint32_t)((t / NKV) & 1));
+      issue_pv(0, t);
+      if (t == 0) { issue_s(1, 0); commit_e(el, bar_ke); }                        // warpgroup 1 starts here
+      if (tn < ntiles) {
+        wait1(bar_sfree + 8, (uint32_t)(t & 1));
+        issue_s(1, tn);
+        commit_e(el, bar_ke + 8 * (tn % NKV));                                    // K(t+1): both products issued
+      }
+      wait1(bar_pf + 8, (uint32_t)(t & 1));
+      issue_pv(1, t);
+      commit_e(el, bar_ve + 8 * (t % NKV));                                       // V(t): both products issued
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ softmax warpgroups
+    const int w = (warp - 2) >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = ((uint32_t)(quarter * 32)) << 16;
+    const uint32_t tS = tmem_base + col_s(w) + lane_off, tO = tmem_base + col_o(w) + lane_off, tP = tmem_base + col_p(w) + lane_off;
+    const uint32_t prow = sb + OFF_P + w * P_TILE + (row >> 3) * 128 + (row & 7) * 16;   // this row inside every P_lo k-chunk
+    float o[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = 0.f;
+    float m = -1e30f, l = 0.f, corr_prev = 1.0f;
+    auto fold = [&](int t) {   // o = o * corr_prev + (three partial products of tile t)
+      mbar_wait(bar_of + 8 * w, (uint32_t)(t & 1));
+      tc_fence_after_sync();
+      float a0[16], a1[16], a2[16];
+      tmem_ld16(tO, a0);
+      tmem_ld16(tO + 16, a1);
+      tmem_ld16(tO + 32, a2);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], corr_prev, (a0[d] + a1[d]) + a2[d]);
+    };
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(bar_sf + 8 * w, (uint32_t)(j & 1));
+      tc_fence_after_sync();
+      uint32_t sr[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32_nowait(tS + c * 32, sr[c]);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(bar_sfree + 8 * w);          // S_w may be overwritten by the next tile's product
+      if (j * 128 + 128 > N) {                 // last, partial tile only: keys >= N never win the max and get P = 0
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (j * 128 + c * 32 + e >= N) sr[c][e] = 0xf149f2caU;  // -1e30f
+      }
+      float mx = m;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sr[c][e]));
+      const float corr = ex2f(m - mx);
+      m = mx;
+      if (j > 0) fold(j - 1);                  // also guarantees that P_w(j-1) has been consumed
+      corr_prev = corr;
+      float tsum = 0.f;
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {      // 32 keys: one tcgen05.st of 16 packed columns, four P_lo chunks of 8 keys
+        uint32_t pw[16];
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint32_t pl[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float p0 = ex2f(__uint_as_float(sr[c16][c8 * 8 + 2 * e]) - m);
+            const float p1 = ex2f(__uint_as_float(sr[c16][c8 * 8 + 2 * e + 1]) - m);
+            tsum += p0 + p1;
+            const __half2 hh = __floats2half2_rn(p0, p1);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+            pw[c8 * 4 + e] = *reinterpret_cast<const uint32_t*>(&hh);
+            pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          const uint32_t dst = prow + (c16 * 4 + c8) * LBO_P;
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+        }
+        tmem_st16(tP + c16 * 16, pw);
+      }
+      l = fmaf(l, corr, tsum);
+      tmem_st_wait();
+      fence_proxy_async();
+      tc_fence_before_sync();
+      mbar_arrive(bar_pf + 8 * w);
+    }
+    fold(ntiles - 1);
+    const int qt = qt0 + w;
+    const int r = qt * 128 + row;
+    if (qt < ntiles && r < N) {
+      const float inv = __fdiv_rn(1.0f, l);
+      float res[16];
+#pragma unroll
+      for (int d = 0; d < 16; ++d) res[d] = o[d] * inv;
+      const int col = h * 16;
+      if (out) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<float4*>(out + (size_t)r * 64 + col + q4 * 4) = make_float4(res[q4 * 4], res[q4 * 4 + 1], res[q4 * 4 + 2], res[q4 * 4 + 3]);
+      }
+      if (out2) {
+        float r0[8], r1[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { r0[d] = res[d]; r1[d] = res[8 + d]; }
+        split_store8(out2 + (size_t)r * 128 + col, out2 + (size_t)r * 128 + 64 + col, r0);
+        split_store8(out2 + (size_t)r * 128 + col + 8, out2 + (size_t)r * 128 + 64 + col + 8, r1);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}

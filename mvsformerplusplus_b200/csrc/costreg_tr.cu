@@ -11,6 +11,8 @@
 #include <float.h>
 
 #include "linear.cuh"
+#include <stdlib.h>
+
 #include "linear_tc.cuh"
 #include "umma.cuh"
 
@@ -134,8 +136,10 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+#include "attention_fa.cuh"   // second-generation attention kernel (inside namespace mvsf)
+
 // ------------------------------------------------------------------------------------------------------------------
-// tcgen05 softmax attention (product path).  CTA = 128 queries x one head, 128 threads, thread t owns query row t
+// tcgen05 softmax attention, first generation (kept for reference measurements: MVSF_ATTENTION_V3=1).  CTA = 128 queries x one head, 128 threads, thread t owns query row t
 // (TMEM lane t), so row max / row sum need no cross-thread traffic.  Per 128-key tile:
 //   S[128x128] = Q K^T      : 3 split-fp16 tcgen05.mma (lo*hi, hi*lo, hi*hi), K = 16, fp32 accumulators in TMEM
 //   softmax                  : tcgen05.ld the row, online max, P = exp2(S - m), split P into fp16 hi/lo, store both in the
@@ -416,16 +420,32 @@ __global__ void unpatch_ln_prob_kernel(const float* __restrict__ u, const float*
 
 
 static int run_attention(const float* qkv, float* o, __half* o2, __half* split, int N, float scale_log2e, cudaStream_t s) {
-  const int Np = (N + 7) & ~7;
-  qkv_split_kernel<<<cdiv((long long)Np * 48, 256), 256, 0, s>>>(qkv, split, N, Np, scale_log2e);
-  MVSF_LAUNCH_CHECK("qkv_split");
-  static bool configured = false;
-  if (!configured) {
-    MVSF_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa5::SMEM));
-    configured = true;
+  static int use_v3 = -1;
+  if (use_v3 < 0) { const char* e = getenv("MVSF_ATTENTION_V3"); use_v3 = (e && e[0] == '1') ? 1 : 0; }
+  cudaEvent_t kt = nullptr;
+  if (use_v3) {
+    const int Np = (N + 7) & ~7;
+    qkv_split_kernel<<<cdiv((long long)Np * 48, 256), 256, 0, s>>>(qkv, split, N, Np, scale_log2e);
+    MVSF_LAUNCH_CHECK("qkv_split");
+    static bool configured = false;
+    if (!configured) {
+      MVSF_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa5::SMEM));
+      configured = true;
+    }
+    kt = ktimer_enabled() ? ktimer_begin("attention_tc", s) : nullptr;
+    attention_tc_kernel<<<dim3(cdiv(N, fa5::BM), 4), fa5::THREADS, fa5::SMEM, s>>>(split, o, o2, N, Np);
+  } else {
+    const int ntiles = cdiv(N, 128);
+    qkv_tile_kernel<<<cdiv((long long)ntiles * 128 * 24, 256), 256, 0, s>>>(qkv, split, N, ntiles, scale_log2e);
+    MVSF_LAUNCH_CHECK("qkv_tile");
+    static bool configured = false;
+    if (!configured) {
+      MVSF_CUDA_OK(cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa6::SMEM));
+      configured = true;
+    }
+    kt = ktimer_enabled() ? ktimer_begin("attention_tc", s) : nullptr;
+    attention_fa_kernel<<<dim3(cdiv(ntiles, 2), 4), fa6::THREADS, fa6::SMEM, s>>>(split, o, o2, N, ntiles);
   }
-  cudaEvent_t kt = ktimer_enabled() ? ktimer_begin("attention_tc", s) : nullptr;
-  attention_tc_kernel<<<dim3(cdiv(N, fa5::BM), 4), fa5::THREADS, fa5::SMEM, s>>>(split, o, o2, N, Np);
   if (kt) ktimer_end(kt, s);
   MVSF_LAUNCH_CHECK("attention_tc");
   return MVSF_OK;
@@ -452,7 +472,7 @@ int mvsf_costreg_tr_workspace_bytes(int C, int D, int H, int W, size_t* bytes) {
   size_t N = (size_t)(D / 2) * (H / 4) * (W / 4);
   // per token (in floats): big 256 (patches2 / ffn hidden split / un-patchify out), x 64, y 64, x2 64, y2 64, o2 64,
   // qkv 192, attention operand split 192
-  *bytes = (N * (256 + 64 + 64 + 64 + 64 + 64 + 192) + (N + 8) * 192) * sizeof(float);
+  *bytes = (N * (256 + 64 + 64 + 64 + 64 + 64 + 192) + (N + 128) * 192) * sizeof(float);
   return MVSF_OK;
 }
 
@@ -534,7 +554,7 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, c
 int mvsf_attention_forward(const float* qkv, float* out, void* workspace, size_t workspace_bytes, int N,
                            float softmax_scale, mvsf_stream_t stream) {
   MVSF_REQUIRE(qkv && out && workspace && N > 0, "attention_forward: bad arguments");
-  if (workspace_bytes < (size_t)(N + 8) * 768) return fail(MVSF_ERR_WORKSPACE, "attention_forward: workspace %zu < %zu bytes", workspace_bytes, (size_t)(N + 8) * 768);
+  if (workspace_bytes < (size_t)(N + 128) * 768) return fail(MVSF_ERR_WORKSPACE, "attention_forward: workspace %zu < %zu bytes", workspace_bytes, (size_t)(N + 128) * 768);
   return run_attention(qkv, out, nullptr, reinterpret_cast<__half*>(workspace), N, softmax_scale * 1.4426950408889634f, (cudaStream_t)stream);
 }
 }
