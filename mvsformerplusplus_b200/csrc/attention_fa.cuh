@@ -37,23 +37,9 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 __device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// shared-memory descriptor = {low word: start address and k-chunk stride, high word: 8-row-group stride 128 B + version}
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3fffu) | ((lbo >> 4) << 16); }
-constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t e;
-  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(e));
-  return e;
-}
-// `el` != 0 on exactly one lane of the converged warp
+constexpr uint32_t DESC_HI = desc_hi(128);
 __device__ __forceinline__ void mma_ss(uint32_t el, uint32_t d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 q, %0, 0;\n\tsetp.ne.b32 p, %6, 0;\n\t"
-      "mov.b64 da, {%2, %4};\n\tmov.b64 db, {%3, %4};\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %5, p;\n\t}"
-      ::"r"(el), "r"(d), "r"(alo), "r"(blo), "r"(DESC_HI), "r"(idesc), "r"(acc)
-      : "memory");
+  mma_f16_ss_lh(el, d, alo, DESC_HI, blo, DESC_HI, idesc, acc);
 }
 __device__ __forceinline__ void mma_ts(uint32_t el, uint32_t d, uint32_t ta, uint32_t blo, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -64,11 +50,7 @@ __device__ __forceinline__ void mma_ts(uint32_t el, uint32_t d, uint32_t ta, uin
       ::"r"(el), "r"(d), "r"(ta), "r"(blo), "r"(DESC_HI), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void commit_e(uint32_t el, uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}" ::"r"(el), "r"(bar) : "memory");
-}
+__device__ __forceinline__ void commit_e(uint32_t el, uint32_t bar) { commit_el(el, bar); }
 }  // namespace fa6
 
 // tiled layout: 6 planes [Qh, Ql, Kh, Kl, Vh, Vl] of 4 heads x ntiles x 2048 halves.  Q/K tile = [2 k-chunks][128 rows][8];
@@ -168,10 +150,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
     const uint32_t p_lo[2] = {desc_lo(sb + OFF_P, LBO_P), desc_lo(sb + OFF_P + P_TILE, LBO_P)};
     const uint32_t k0 = desc_lo(sb + OFF_K, LBO_QK), v0 = desc_lo(sb + OFF_V, LBO_V);
     // one lane polls, the warp reconverges: 32 polling lanes would steal issue slots and shared-memory bandwidth
-    auto wait1 = [&](uint32_t bar, uint32_t parity) {
-      if (lane == 0) mbar_wait(bar, parity);
-      __syncwarp();
-    };
+    auto wait1 = [&](uint32_t bar, uint32_t parity) { mbar_wait_warp(bar, parity); };
     auto issue_s = [&](int w, int t) {           // S_w(t) = Q_w K(t)^T  (K(t) has landed)
       tc_fence_after_sync();
       const uint32_t kh = k0 + (uint32_t)(t % NKV) * (2 * TILE >> 4), kl = kh + (TILE >> 4);

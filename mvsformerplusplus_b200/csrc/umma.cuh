@@ -88,6 +88,37 @@ __device__ __forceinline__ void commit_elect(uint32_t bar) {
       "elect.sync _|q, 0xffffffff;\n\t"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
 }
+// Lean issue path for a dedicated, converged MMA warp: the issuing warp is the critical resource of the small-N kernels
+// (a tcgen05.mma costs ~50 clk stand-alone, more when its ~20 set-up instructions compete for issue slots).  Descriptors
+// are handled as {low word = start address | k-chunk stride, high word = 8-row-group stride | version}: moving a
+// descriptor is one 32-bit add on the low word.  `el` (from elect_one()) is non-zero on exactly one lane.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3fffu) | ((lbo_bytes >> 4) << 16); }
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14); }
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t e;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(e));
+  return e;
+}
+__device__ __forceinline__ void mma_f16_ss_lh(uint32_t el, uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 q, %0, 0;\n\tsetp.ne.b32 p, %7, 0;\n\t"
+      "mov.b64 da, {%2, %3};\n\tmov.b64 db, {%4, %5};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %6, p;\n\t}"
+      ::"r"(el), "r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit_el(uint32_t el, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}" ::"r"(el), "r"(bar) : "memory");
+}
+// one lane polls, the warp reconverges (32 polling lanes steal issue slots and shared-memory bandwidth)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 // A operand from tensor memory (128 lanes = rows, K = 16 fp16 packed two per 32-bit column: 8 columns), B from shared memory
 __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
