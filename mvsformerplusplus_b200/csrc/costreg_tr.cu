@@ -11,8 +11,6 @@
 #include <float.h>
 
 #include "linear.cuh"
-#include <stdlib.h>
-
 #include "linear_tc.cuh"
 #include "umma.cuh"
 
@@ -96,40 +94,6 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
 }
-// split layout: 6 planes of 4*16*Np halves (Np = N rounded up to 8): 0 Qh, 1 Ql, 2 Kh, 3 Kl as [4 heads][Np][16];
-// 4 Vh, 5 Vl TRANSPOSED per head as [4 heads][16 dims][Np] (keys contiguous: K-major B operand of the tcgen05 P*V
-// product).  Pad keys [N, Np) of V are zero.
-__global__ void qkv_split_kernel(const float* __restrict__ qkv, __half* __restrict__ split, int N, int Np, float qscale) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (token, which(q/k/v), head, quad of 4 dims)
-  int total = Np * 3 * 4 * 4;
-  if (i >= total) return;
-  int quad = i & 3, h = (i >> 2) & 3, which = (i >> 4) % 3, tok = i / 48;
-  const size_t plane = (size_t)4 * 16 * Np;
-  if (tok >= N) {
-    if (which == 2) {
-      __half* th = split + (size_t)4 * plane + ((size_t)h * 16 + quad * 4) * Np + tok;
-      __half* tl = split + (size_t)5 * plane + ((size_t)h * 16 + quad * 4) * Np + tok;
-      for (int e = 0; e < 4; ++e) { th[(size_t)e * Np] = __float2half_rn(0.f); tl[(size_t)e * Np] = __float2half_rn(0.f); }
-    }
-    return;
-  }
-  float4 v = ldg4(qkv + (size_t)tok * 192 + which * 64 + h * 16 + quad * 4);
-  if (which == 0) { v.x *= qscale; v.y *= qscale; v.z *= qscale; v.w *= qscale; }
-  __half hi[4], lo[4];
-  split_f16(v.x, hi[0], lo[0]); split_f16(v.y, hi[1], lo[1]); split_f16(v.z, hi[2], lo[2]); split_f16(v.w, hi[3], lo[3]);
-  if (which == 2) {
-    __half* th = split + (size_t)4 * plane + ((size_t)h * 16 + quad * 4) * Np + tok;
-    __half* tl = split + (size_t)5 * plane + ((size_t)h * 16 + quad * 4) * Np + tok;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { th[(size_t)e * Np] = hi[e]; tl[(size_t)e * Np] = lo[e]; }
-    return;
-  }
-  size_t off = ((size_t)h * Np + tok) * 16 + quad * 4;
-  __half2* ph = reinterpret_cast<__half2*>(split + (size_t)(which * 2) * plane + off);
-  __half2* pl = reinterpret_cast<__half2*>(split + (size_t)(which * 2 + 1) * plane + off);
-  ph[0] = __halves2half2(hi[0], hi[1]); ph[1] = __halves2half2(hi[2], hi[3]);
-  pl[0] = __halves2half2(lo[0], lo[1]); pl[1] = __halves2half2(lo[2], lo[3]);
-}
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -137,253 +101,6 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 
 #include "attention_fa.cuh"   // second-generation attention kernel (inside namespace mvsf)
-
-// ------------------------------------------------------------------------------------------------------------------
-// tcgen05 softmax attention, first generation (kept for reference measurements: MVSF_ATTENTION_V3=1).  CTA = 128 queries x one head, 128 threads, thread t owns query row t
-// (TMEM lane t), so row max / row sum need no cross-thread traffic.  Per 128-key tile:
-//   S[128x128] = Q K^T      : 3 split-fp16 tcgen05.mma (lo*hi, hi*lo, hi*hi), K = 16, fp32 accumulators in TMEM
-//   softmax                  : tcgen05.ld the row, online max, P = exp2(S - m), split P into fp16 hi/lo, store both in the
-//                              canonical K-major A-operand layout in shared memory
-//   Otile[128x16] = P V      : 8 k-steps x 3 split products = 24 tcgen05.mma (N = 16), V^T tiles are K-major B operands
-//   O = O * corr + Otile     : round-to-nearest FMA in registers (tensor-core accumulation truncates; chaining all
-//                              tiles on one accumulator biases the result, see profiles/)
-// Two CTAs per SM (<= 113 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's MMAs.
-// ------------------------------------------------------------------------------------------------------------------
-// Debug build (-DMVSF_FA_TRACE, tools/fa_trace.py): clock64 stamps of thread 0's phases for 64 key tiles of one CTA.
-#ifdef MVSF_FA_TRACE
-__device__ long long g_fa_trace[64 * 8];
-#define FA_TRACE(slot) do { if (blockIdx.x == 100 && blockIdx.y == 1 && tid == 0 && j >= 100 && j < 164) g_fa_trace[(j - 100) * 8 + (slot)] = clock64(); } while (0)
-#else
-#define FA_TRACE(slot) do {} while (0)
-#endif
-namespace fa5 {
-using namespace umma;
-constexpr int BM = 128, BN = 128, THREADS = 256;
-constexpr uint32_t LBO_QK = 16 * 128 + 16;   // 2 chunks (hd = 16) x 128 rows
-constexpr uint32_t QK_TILE = 2 * LBO_QK;
-constexpr uint32_t LBO_P = 16 * 128;         // 16 chunks (128 keys) x 128 rows
-constexpr uint32_t P_TILE = 16 * LBO_P;      // 32 KB
-constexpr uint32_t LBO_V = 2 * 128 + 16;     // 16 chunks (128 keys) x 16 rows (head dims)
-constexpr uint32_t V_TILE = 16 * LBO_V;
-// Q (hi,lo) | K ring 2 x (hi,lo) | V^T ring 2 x (hi,lo) | P (hi,lo) | row-max exchange [2][128] | barriers
-constexpr uint32_t OFF_Q = 0, OFF_K = 2 * QK_TILE, OFF_V = OFF_K + 4 * QK_TILE, OFF_P = OFF_V + 4 * V_TILE,
-                   OFF_X = OFF_P + 2 * P_TILE, OFF_BAR = OFF_X + 1024;
-constexpr uint32_t SMEM = OFF_BAR + 64;
-}  // namespace fa5
-
-// 256 threads: thread (warp w, lane) owns query row (w%4)*32+lane and the key columns [64*(w/4), 64*(w/4)+64) of each
-// tile; the two threads of a row exchange their partial row maxima through shared memory.  The normaliser l is summed
-// per tile and folded like the outputs (l = l*corr + tile_sum): a single running fp32 sum over 27k keys is 5x noisier.
-__global__ void __launch_bounds__(256, 2)
-attention_tc_kernel(const __half* __restrict__ split, float* __restrict__ out, __half* __restrict__ out2, int N, int Np) {
-  using namespace fa5;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = warp >> 2;                       // which 64 key columns of a tile
-  const int row = (warp & 3) * 32 + lane;           // query row == TMEM lane
-  const int h = blockIdx.y;
-  const int q0 = blockIdx.x * BM;
-  const size_t plane = (size_t)4 * 16 * Np;
-  const __half* Qg[2] = {split + 0 * plane + (size_t)h * Np * 16, split + 1 * plane + (size_t)h * Np * 16};
-  const __half* Kg[2] = {split + 2 * plane + (size_t)h * Np * 16, split + 3 * plane + (size_t)h * Np * 16};
-  const __half* Vg[2] = {split + 4 * plane + (size_t)h * 16 * Np, split + 5 * plane + (size_t)h * 16 * Np};  // [16][Np]
-  const uint32_t sb = smem_u32(smem);
-  const uint32_t bar_s = sb + OFF_BAR, bar_o = sb + OFF_BAR + 8;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 32);
-  volatile float* xchg = reinterpret_cast<volatile float*>(smem + OFF_X);  // [2][128]
-
-  if (tid == 0) {
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(sb + OFF_BAR + 32, 256);
-
-  auto load_qk_tile = [&](uint32_t dst, const __half* g, int row0) {  // 128 rows x 2 chunks, zero fill beyond N
-    int r = tid >> 1, c = tid & 1;
-    bool ok = row0 + r < N;
-    cp_async16_zfill(dst + c * LBO_QK + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)(ok ? row0 + r : 0) * 16 + c * 8, ok);
-  };
-  auto load_v_tile = [&](uint32_t dst, const __half* g, int key0) {   // 16 rows (dims) x 16 chunks of 8 keys
-    {
-      int r = tid >> 4, c = tid & 15;
-      bool ok = key0 + c * 8 < Np;  // rows are padded to Np (multiple of 8) with zeros: chunks are whole
-      cp_async16_zfill(dst + c * LBO_V + (r >> 3) * 128 + (r & 7) * 16, g + (size_t)r * Np + (ok ? key0 + c * 8 : 0), ok);
-    }
-  };
-  const int ntiles = (N + BN - 1) / BN;
-  auto load_k = [&](int tile) {  // always commits a group (possibly empty) to keep the group accounting uniform
-    if (tile < ntiles) {
-      const uint32_t s0 = sb + OFF_K + (tile & 1) * 2 * QK_TILE;
-      load_qk_tile(s0, Kg[0], tile * BN);
-      load_qk_tile(s0 + QK_TILE, Kg[1], tile * BN);
-    }
-    cp_async_commit_group();
-  };
-  auto load_v = [&](int tile) {
-    if (tile < ntiles) {
-      const uint32_t s0 = sb + OFF_V + (tile & 1) * 2 * V_TILE;
-      load_v_tile(s0, Vg[0], tile * BN);
-      load_v_tile(s0 + V_TILE, Vg[1], tile * BN);
-    }
-    cp_async_commit_group();
-  };
-  const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 16);
-  auto issue_s = [&](uint32_t tS, int tile) {  // thread 0 only
-    const uint32_t sK = sb + OFF_K + (tile & 1) * 2 * QK_TILE;
-    const uint64_t qh = make_desc(sb + OFF_Q, LBO_QK, 128), ql = make_desc(sb + OFF_Q + QK_TILE, LBO_QK, 128);
-    const uint64_t kh = make_desc(sK, LBO_QK, 128), kl = make_desc(sK + QK_TILE, LBO_QK, 128);
-    mma_f16_ss(tS, ql, kh, idesc_s, 0u);
-    mma_f16_ss(tS, qh, kl, idesc_s, 1u);
-    mma_f16_ss(tS, qh, kh, idesc_s, 1u);
-    commit(bar_s);
-  };
-
-  load_qk_tile(sb + OFF_Q, Qg[0], q0);
-  load_qk_tile(sb + OFF_Q + QK_TILE, Qg[1], q0);
-  load_k(0);   // group: Q + K(0)
-  load_v(0);
-  load_k(1);
-  cp_async_wait_group<0>();
-  fence_proxy_async();
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
-  const uint32_t trow = ((uint32_t)((warp & 3) * 32)) << 16;
-  const uint32_t prow = sb + OFF_P + (row >> 3) * 128 + (row & 7) * 16;  // this thread's row inside every P chunk
-  if (tid == 0) issue_s(tS, 0);
-
-  float o[8];   // this thread's 8 of the 16 head dims: dims [8*half, 8*half+8)
-#pragma unroll
-  for (int d = 0; d < 8; ++d) o[d] = 0.f;
-  float m = -1e30f, l = 0.f, corr_prev = 1.0f;
-
-  for (int j = 0; j < ntiles; ++j) {
-    // ---- 1. this thread's 64 columns of S(j) -> registers (single wait), partial row maximum -> exchange buffer
-    FA_TRACE(0);
-    mbar_wait(bar_s, (uint32_t)(j & 1));
-    tc_fence_after_sync();
-    FA_TRACE(1);
-    uint32_t sr[2][32];
-    tmem_ld32_nowait(tS + trow + half * 64, sr[0]);
-    tmem_ld32_nowait(tS + trow + half * 64 + 32, sr[1]);
-    tmem_ld_wait();
-    if (j * BN + BN > N) {  // last, partial tile only (uniform branch): keys >= N never win the max and get P = 0
-      const int kbase = j * BN + half * 64;
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (kbase + c * 32 + e >= N) sr[c][e] = 0xf149f2caU;  // -1e30f
-    }
-    float pmax = -1e30f;
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-      for (int e = 0; e < 32; ++e) pmax = fmaxf(pmax, __uint_as_float(sr[c][e]));
-    xchg[half * 128 + row] = pmax;
-    // ---- 2. K(j+2) prefetch; S(j+1) starts as soon as everybody has S(j) in registers
-    load_k(j + 2);
-    cp_async_wait_group<1>();   // K(j+1) and V(j) have landed
-    fence_proxy_async();
-    tc_fence_before_sync();
-    FA_TRACE(2);
-    __syncthreads();
-    FA_TRACE(3);
-    if (tid == 0 && j + 1 < ntiles) { tc_fence_after_sync(); issue_s(tS, j + 1); }
-    // ---- 3. row maximum, fold O_tile(j-1)
-    const float mx = fmaxf(m, fmaxf(pmax, xchg[(half ^ 1) * 128 + row]));
-    const float corr = ex2f(m - mx);
-    m = mx;
-    FA_TRACE(4);
-    if (j > 0) {
-      mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
-      tc_fence_after_sync();
-      float ot[16];
-      tmem_ld16(tO + trow, ot);
-#pragma unroll
-      for (int d = 0; d < 8; ++d) o[d] = fmaf(o[d], corr_prev, half ? ot[8 + d] : ot[d]);
-    }
-    corr_prev = corr;
-    FA_TRACE(5);
-    float tsum = 0.f;
-    load_v(j + 1);   // its stage held V(j-1), released by the P*V product we just waited for
-    // ---- 4. P = exp2(S - m), hi/lo split -> shared memory (A operand of P*V); chunk = 8 keys
-#pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-      uint32_t ph[4], pl[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = c8 * 8 + 2 * e;
-        const float p0 = ex2f(__uint_as_float(sr[col >> 5][col & 31]) - m);
-        const float p1 = ex2f(__uint_as_float(sr[(col + 1) >> 5][(col + 1) & 31]) - m);
-        tsum += p0 + p1;
-        const __half2 hh = __floats2half2_rn(p0, p1);
-        const float2 hf = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
-        ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
-        pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
-      }
-      const uint32_t dst = prow + (half * 8 + c8) * LBO_P;
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + P_TILE), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
-    }
-    l = fmaf(l, corr, tsum);
-    // ---- 5. O_tile(j) = P(j) V(j)
-    fence_proxy_async();
-    tc_fence_before_sync();
-    FA_TRACE(6);
-    __syncthreads();
-    FA_TRACE(7);
-    if (tid == 0) {
-      tc_fence_after_sync();
-      const uint32_t sV = sb + OFF_V + (j & 1) * 2 * V_TILE;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint64_t pH = make_desc(sb + OFF_P + 2 * i * LBO_P, LBO_P, 128);
-        const uint64_t pL = make_desc(sb + OFF_P + P_TILE + 2 * i * LBO_P, LBO_P, 128);
-        const uint64_t vH = make_desc(sV + 2 * i * LBO_V, LBO_V, 128);
-        const uint64_t vL = make_desc(sV + V_TILE + 2 * i * LBO_V, LBO_V, 128);
-        mma_f16_ss(tO, pL, vH, idesc_o, i > 0 ? 1u : 0u);
-        mma_f16_ss(tO, pH, vL, idesc_o, 1u);
-        mma_f16_ss(tO, pH, vH, idesc_o, 1u);
-      }
-      commit(bar_o);
-    }
-  }
-  {  // fold the last tile
-    mbar_wait(bar_o, (uint32_t)((ntiles - 1) & 1));
-    tc_fence_after_sync();
-    float ot[16];
-    tmem_ld16(tO + trow, ot);
-#pragma unroll
-    for (int d = 0; d < 8; ++d) o[d] = fmaf(o[d], corr_prev, half ? ot[8 + d] : ot[d]);
-  }
-  cp_async_wait_group<0>();
-  // the two threads of a row summed disjoint key columns: combine the normalisers
-  xchg[half * 128 + row] = l;
-  __syncthreads();
-  l += xchg[(half ^ 1) * 128 + row];
-
-  const int r = q0 + row;
-  if (r < N) {
-    const float inv = __fdiv_rn(1.0f, l);
-    float res[8];
-#pragma unroll
-    for (int d = 0; d < 8; ++d) res[d] = o[d] * inv;
-    const int col = h * 16 + half * 8;
-    if (out) {
-      *reinterpret_cast<float4*>(out + (size_t)r * 64 + col) = make_float4(res[0], res[1], res[2], res[3]);
-      *reinterpret_cast<float4*>(out + (size_t)r * 64 + col + 4) = make_float4(res[4], res[5], res[6], res[7]);
-    }
-    if (out2) split_store8(out2 + (size_t)r * 128 + col, out2 + (size_t)r * 128 + 64 + col, res);
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
-}
 
 // un-patchify epilogue: u [N][256] (n = vox*8+co) -> LayerNorm3D over the 8 channels of each voxel (eps 1e-6)
 // -> prob 1x1x1 (8 -> 1) + bias -> logits [D][H][W]
@@ -419,33 +136,17 @@ __global__ void unpatch_ln_prob_kernel(const float* __restrict__ u, const float*
 }
 
 
-static int run_attention(const float* qkv, float* o, __half* o2, __half* split, int N, float scale_log2e, cudaStream_t s) {
-  static int use_v3 = -1;
-  if (use_v3 < 0) { const char* e = getenv("MVSF_ATTENTION_V3"); use_v3 = (e && e[0] == '1') ? 1 : 0; }
-  cudaEvent_t kt = nullptr;
-  if (use_v3) {
-    const int Np = (N + 7) & ~7;
-    qkv_split_kernel<<<cdiv((long long)Np * 48, 256), 256, 0, s>>>(qkv, split, N, Np, scale_log2e);
-    MVSF_LAUNCH_CHECK("qkv_split");
-    static bool configured = false;
-    if (!configured) {
-      MVSF_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa5::SMEM));
-      configured = true;
-    }
-    kt = ktimer_enabled() ? ktimer_begin("attention_tc", s) : nullptr;
-    attention_tc_kernel<<<dim3(cdiv(N, fa5::BM), 4), fa5::THREADS, fa5::SMEM, s>>>(split, o, o2, N, Np);
-  } else {
-    const int ntiles = cdiv(N, 128);
-    qkv_tile_kernel<<<cdiv((long long)ntiles * 128 * 24, 256), 256, 0, s>>>(qkv, split, N, ntiles, scale_log2e);
-    MVSF_LAUNCH_CHECK("qkv_tile");
-    static bool configured = false;
-    if (!configured) {
-      MVSF_CUDA_OK(cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa6::SMEM));
-      configured = true;
-    }
-    kt = ktimer_enabled() ? ktimer_begin("attention_tc", s) : nullptr;
-    attention_fa_kernel<<<dim3(cdiv(ntiles, 2), 4), fa6::THREADS, fa6::SMEM, s>>>(split, o, o2, N, ntiles);
+static int run_attention(const float* qkv, float* o, __half* o2, __half* tiled, int N, float scale_log2e, cudaStream_t s) {
+  const int ntiles = cdiv(N, 128);
+  qkv_tile_kernel<<<cdiv((long long)ntiles * 128 * 24, 256), 256, 0, s>>>(qkv, tiled, N, ntiles, scale_log2e);
+  MVSF_LAUNCH_CHECK("qkv_tile");
+  static bool configured = false;
+  if (!configured) {
+    MVSF_CUDA_OK(cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa6::SMEM));
+    configured = true;
   }
+  cudaEvent_t kt = ktimer_enabled() ? ktimer_begin("attention_tc", s) : nullptr;
+  attention_fa_kernel<<<dim3(cdiv(ntiles, 2), 4), fa6::THREADS, fa6::SMEM, s>>>(tiled, o, o2, N, ntiles);
   if (kt) ktimer_end(kt, s);
   MVSF_LAUNCH_CHECK("attention_tc");
   return MVSF_OK;
@@ -454,14 +155,6 @@ static int run_attention(const float* qkv, float* o, __half* o2, __half* split, 
 }  // namespace mvsf
 
 using namespace mvsf;
-
-#ifdef MVSF_FA_TRACE
-extern "C" int mvsf_debug_fa_trace(long long* out) {
-  MVSF_CUDA_OK(cudaDeviceSynchronize());
-  MVSF_CUDA_OK(cudaMemcpyFromSymbol(out, mvsf::g_fa_trace, sizeof(long long) * 64 * 8));
-  return MVSF_OK;
-}
-#endif
 
 extern "C" {
 
