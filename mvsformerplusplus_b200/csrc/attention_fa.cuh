@@ -12,15 +12,16 @@
 //                 waiting for their MMAs (ping-pong)
 // S_w(t) = Q_w K(t)^T is issued as soon as warpgroup w has pulled S_w(t-1) out of TMEM, O_w(t) = P_w(t) V(t) as soon as
 // P_w(t) is complete.  P_hi is written back to TENSOR MEMORY (tcgen05.st) and consumed as the A operand of two of the
-// three P*V products; only P_lo travels through shared memory.  The three products accumulate in three separate TMEM
-// accumulators that the softmax thread adds (round to nearest) while folding the tile into its running output.
+// three P*V products (issued as ONE N = 32 MMA against [V_hi | V_lo]); only P_lo travels through shared memory.  The three
+// partial products sit in separate TMEM columns that the softmax thread adds (round to nearest) while folding the tile
+// into its running output.
 #pragma once
 
 namespace fa6 {
 using namespace umma;
 constexpr int NSOFT = 256, THREADS = 64 + NSOFT, NKV = 3;   // 320 threads -> 204 registers: the 128 scores of a row stay in registers
 constexpr uint32_t TILE = 4096;                 // one canonical 128 x 16 (Q, K) or 16 x 128 (V^T) fp16 tile
-constexpr uint32_t LBO_QK = 2048, LBO_V = 256;  // k-chunk strides inside those tiles
+constexpr uint32_t LBO_QK = 2048, LBO_V = 512;  // k-chunk strides: Q/K 128 rows; V^T 32 rows = V_hi dims 0-15 | V_lo dims 0-15
 constexpr uint32_t LBO_P = 2048, P_TILE = 16 * LBO_P;
 // Q (2 tiles x hi,lo) | K ring (hi,lo) | V ring (hi,lo) | P_lo (2 warpgroups) | barriers
 constexpr uint32_t OFF_Q = 0, OFF_K = 4 * TILE, OFF_V = OFF_K + NKV * 2 * TILE, OFF_P = OFF_V + NKV * 2 * TILE,
@@ -53,8 +54,9 @@ __device__ __forceinline__ void mma_ts(uint32_t el, uint32_t d, uint32_t ta, uin
 __device__ __forceinline__ void commit_e(uint32_t el, uint32_t bar) { commit_el(el, bar); }
 }  // namespace fa6
 
-// tiled layout: 6 planes [Qh, Ql, Kh, Kl, Vh, Vl] of 4 heads x ntiles x 2048 halves.  Q/K tile = [2 k-chunks][128 rows][8];
-// V^T tile = [16 k-chunks of 8 keys][16 dims][8 keys].  Rows / keys >= N are zero.
+// tiled layout: planes Qh, Ql, Kh, Kl of 4 heads x ntiles x 2048 halves (tile = [2 k-chunks][128 rows][8]) and one V plane
+// of 4 heads x ntiles x 4096 halves: V^T tile = [16 k-chunks of 8 keys][32 rows: 16 dims of V_hi, 16 dims of V_lo][8 keys]
+// - the N = 32 operand [V_hi | V_lo] whose first 16 rows are the N = 16 operand V_hi.  Rows / keys >= N are zero.
 __global__ void qkv_tile_kernel(const float* __restrict__ qkv, __half* __restrict__ tiled, int N, int ntiles, float qscale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (token, which, head, octet of 8 dims)
   const int total = ntiles * 128 * 3 * 4 * 2;
@@ -75,18 +77,19 @@ __global__ void qkv_tile_kernel(const float* __restrict__ qkv, __half* __restric
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
   }
-  __half* ph = tiled + (size_t)(which * 2) * plane + ((size_t)h * ntiles + tile) * 2048;
-  __half* pl = ph + plane;
   if (which < 2) {
+    __half* ph = tiled + (size_t)(which * 2) * plane + ((size_t)h * ntiles + tile) * 2048;
+    __half* pl = ph + plane;
     split_store8(ph + oct * 1024 + r * 8, pl + oct * 1024 + r * 8, v);
   } else {
+    __half* pv = tiled + (size_t)4 * plane + ((size_t)h * ntiles + tile) * 4096;
     const int kc = r >> 3, e = r & 7;
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
       __half hi, lo;
       split_f16(v[d], hi, lo);
-      ph[kc * 128 + (oct * 8 + d) * 8 + e] = hi;
-      pl[kc * 128 + (oct * 8 + d) * 8 + e] = lo;
+      pv[kc * 256 + (oct * 8 + d) * 8 + e] = hi;
+      pv[kc * 256 + (16 + oct * 8 + d) * 8 + e] = lo;
     }
   }
 }
@@ -136,13 +139,12 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
         bulk_load(sb + OFF_K + (2 * s + 1) * TILE, base + 3 * plane + (size_t)t * 2048, TILE, bar_kf + 8 * s);
         mbar_wait(bar_ve + 8 * s, par);
         expect_tx(bar_vf + 8 * s, 2 * TILE);
-        bulk_load(sb + OFF_V + (2 * s) * TILE, base + 4 * plane + (size_t)t * 2048, TILE, bar_vf + 8 * s);
-        bulk_load(sb + OFF_V + (2 * s + 1) * TILE, base + 5 * plane + (size_t)t * 2048, TILE, bar_vf + 8 * s);
+        bulk_load(sb + OFF_V + (2 * s) * TILE, tiled + 4 * plane + ((size_t)h * ntiles + t) * 4096, 2 * TILE, bar_vf + 8 * s);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer (converged warp)
-    const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 16);
+    const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 16), idesc_o2 = make_idesc_f16(128, 32);
     const uint32_t el = elect_one();
     // low descriptor words of everything that does not move
     const uint32_t q_hi[2] = {desc_lo(sb + OFF_Q, LBO_QK), desc_lo(sb + OFF_Q + 2 * TILE, LBO_QK)};
@@ -162,14 +164,15 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
     };
     auto issue_pv = [&](int w, int u) {          // O_w(u) = P_w(u) V(u)  (V(u) has landed, P_w(u) is complete)
       tc_fence_after_sync();
-      const uint32_t vh = v0 + (uint32_t)(u % NKV) * (2 * TILE >> 4), vl = vh + (TILE >> 4);
+      const uint32_t vv = v0 + (uint32_t)(u % NKV) * (2 * TILE >> 4);
       const uint32_t tO = tmem_base + col_o(w), tP = tmem_base + col_p(w);
+      // two MMAs per 16 keys: P_hi (tensor memory) x [V_hi | V_lo] (N = 32: both products side by side) and P_lo (shared
+      // memory) x V_hi (N = 16).  An MMA costs ~50 clk whatever N <= 64 is, so fewer instructions is what counts.
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t acc = i > 0 ? 1u : 0u;
-        mma_ss(el, tO, p_lo[w] + i * (2 * LBO_P >> 4), vh + i * (2 * LBO_V >> 4), idesc_o, acc);      // P_lo (smem) x V_hi
-        mma_ts(el, tO + 16, tP + i * 8, vl + i * (2 * LBO_V >> 4), idesc_o, acc);                    // P_hi (TMEM) x V_lo
-        mma_ts(el, tO + 32, tP + i * 8, vh + i * (2 * LBO_V >> 4), idesc_o, acc);                    // P_hi x V_hi
+        mma_ts(el, tO, tP + i * 8, vv + i * (2 * LBO_V >> 4), idesc_o2, acc);
+        mma_ss(el, tO + 32, p_lo[w] + i * (2 * LBO_P >> 4), vv + i * (2 * LBO_V >> 4), idesc_o, acc);
       }
       commit_e(el, bar_of + 8 * w);
     };
