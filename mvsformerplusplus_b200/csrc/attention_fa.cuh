@@ -7,8 +7,8 @@
 //   warp 1        MMA issuer for both tiles, fully converged, one elected lane per tcgen05 instruction, every shared-memory
 //                 descriptor reduced to "precomputed low word + constant": the issuing warp is the critical resource
 //                 (a tcgen05.mma costs ~50 clk even stand-alone, profiles/r1_ncu_and_microbench_tcgen05.md)
-//   warps 2-5 / 6-9   softmax warpgroup 0 / 1: thread = query row = TMEM lane, 128 key columns in registers, no
-//                 cross-thread traffic; warpgroup 1 starts one phase late so that the two alternate between softmax and
+//   warps 2-9 / 10-17   softmax warps of query tile 0 / 1: two threads per query row (64 key columns each in registers),
+//                 row max exchanged through shared memory + a named barrier of the tile's 256 threads; tile 1 starts one phase late so that the two alternate between softmax and
 //                 waiting for their MMAs (ping-pong)
 // S_w(t) = Q_w K(t)^T is issued as soon as warpgroup w has pulled S_w(t-1) out of TMEM, O_w(t) = P_w(t) V(t) as soon as
 // P_w(t) is complete.  P_hi is written back to TENSOR MEMORY (tcgen05.st) and consumed as the A operand of two of the
@@ -19,13 +19,13 @@
 
 namespace fa6 {
 using namespace umma;
-constexpr int NSOFT = 256, THREADS = 64 + NSOFT, NKV = 3;   // 320 threads -> 204 registers: the 128 scores of a row stay in registers
+constexpr int NSOFT = 512, THREADS = 64 + NSOFT, NKV = 3;   // two threads per query row: 4 softmax warps per scheduler
 constexpr uint32_t TILE = 4096;                 // one canonical 128 x 16 (Q, K) or 16 x 128 (V^T) fp16 tile
 constexpr uint32_t LBO_QK = 2048, LBO_V = 512;  // k-chunk strides: Q/K 128 rows; V^T 32 rows = V_hi dims 0-15 | V_lo dims 0-15
 constexpr uint32_t LBO_P = 2048, P_TILE = 16 * LBO_P;
 // Q (2 tiles x hi,lo) | K ring (hi,lo) | V ring (hi,lo) | P_lo (2 warpgroups) | barriers
 constexpr uint32_t OFF_Q = 0, OFF_K = 4 * TILE, OFF_V = OFF_K + NKV * 2 * TILE, OFF_P = OFF_V + NKV * 2 * TILE,
-                   OFF_BAR = OFF_P + 2 * P_TILE;
+                   OFF_X = OFF_P + 2 * P_TILE, OFF_BAR = OFF_X + 4096;   // OFF_X: row-max / row-sum exchange [2 parity][2 tiles][2 halves][128]
 constexpr uint32_t SMEM = OFF_BAR + 256;
 // TMEM columns: S_w at 128 w; O_w (3 accumulators x 16) at 256 + 64 w; P_hi_w (64) at 384 + 64 w
 __device__ __forceinline__ uint32_t col_s(int w) { return 128u * w; }
@@ -112,7 +112,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
   if (tid == 0) {
     mbar_init(bar_q, 1);
     for (int i = 0; i < NKV; ++i) { mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, 1); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, 1); }
-    for (int w = 0; w < 2; ++w) { mbar_init(bar_sf + 8 * w, 1); mbar_init(bar_sfree + 8 * w, 128); mbar_init(bar_pf + 8 * w, 128); mbar_init(bar_of + 8 * w, 1); }
+    for (int w = 0; w < 2; ++w) { mbar_init(bar_sf + 8 * w, 1); mbar_init(bar_sfree + 8 * w, 256); mbar_init(bar_pf + 8 * w, 256); mbar_init(bar_of + 8 * w, 1); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
@@ -203,53 +203,65 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
     }
   } else {
     // ------------------------------------------------------------------------------------------ softmax warpgroups
-    const int w = (warp - 2) >> 2, quarter = warp & 3;
+    // 16 warps: query tile w = sw / 8, key-column half = (sw / 4) % 2, TMEM lane quarter = warp % 4.  The two threads of a
+    // row exchange their partial row maxima through shared memory (double buffered by tile parity) and meet at a named
+    // barrier of their tile's 256 threads - the other tile's warps are not involved.
+    const int sw = warp - 2;
+    const int w = sw >> 3, half = (sw >> 2) & 1, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = ((uint32_t)(quarter * 32)) << 16;
-    const uint32_t tS = tmem_base + col_s(w) + lane_off, tO = tmem_base + col_o(w) + lane_off, tP = tmem_base + col_p(w) + lane_off;
+    const uint32_t tS = tmem_base + col_s(w) + lane_off + half * 64, tO = tmem_base + col_o(w) + lane_off + half * 8,
+                   tP = tmem_base + col_p(w) + lane_off + half * 32;
     const uint32_t prow = sb + OFF_P + w * P_TILE + (row >> 3) * 128 + (row & 7) * 16;   // this row inside every P_lo k-chunk
-    float o[16];
+    volatile float* xchg = reinterpret_cast<volatile float*>(smem + OFF_X) + w * 256;    // [parity][tile][half][128]
+    float o[8];    // this thread's 8 of the 16 head dims: [8 half, 8 half + 8)
 #pragma unroll
-    for (int d = 0; d < 16; ++d) o[d] = 0.f;
+    for (int d = 0; d < 8; ++d) o[d] = 0.f;
     float m = -1e30f, l = 0.f, corr_prev = 1.0f;
     auto fold = [&](int t) {   // o = o * corr_prev + (three partial products of tile t)
       mbar_wait(bar_of + 8 * w, (uint32_t)(t & 1));
       tc_fence_after_sync();
-      float a0[16], a1[16], a2[16];
-      tmem_ld16(tO, a0);
-      tmem_ld16(tO + 16, a1);
-      tmem_ld16(tO + 32, a2);
+      uint32_t a0[8], a1[8], a2[8];
+      tmem_ld8_nowait(tO, a0);
+      tmem_ld8_nowait(tO + 16, a1);
+      tmem_ld8_nowait(tO + 32, a2);
+      tmem_ld_wait();
 #pragma unroll
-      for (int d = 0; d < 16; ++d) o[d] = fmaf(o[d], corr_prev, (a0[d] + a1[d]) + a2[d]);
+      for (int d = 0; d < 8; ++d)
+        o[d] = fmaf(o[d], corr_prev, (__uint_as_float(a0[d]) + __uint_as_float(a1[d])) + __uint_as_float(a2[d]));
     };
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(bar_sf + 8 * w, (uint32_t)(j & 1));
       tc_fence_after_sync();
-      uint32_t sr[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32_nowait(tS + c * 32, sr[c]);
+      uint32_t sr[2][32];
+      tmem_ld32_nowait(tS, sr[0]);
+      tmem_ld32_nowait(tS + 32, sr[1]);
       tmem_ld_wait();
       tc_fence_before_sync();
       mbar_arrive(bar_sfree + 8 * w);          // S_w may be overwritten by the next tile's product
       if (j * 128 + 128 > N) {                 // last, partial tile only: keys >= N never win the max and get P = 0
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (j * 128 + c * 32 + e >= N) sr[c][e] = 0xf149f2caU;  // -1e30f
+            if (j * 128 + half * 64 + c * 32 + e >= N) sr[c][e] = 0xf149f2caU;  // -1e30f
       }
-      float mx = m;
+      float pmax = -1e30f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(sr[c][e]));
+        for (int e = 0; e < 32; ++e) pmax = fmaxf(pmax, __uint_as_float(sr[c][e]));
+      volatile float* xj = xchg + (j & 1) * 512;
+      xj[half * 128 + row] = pmax;
+      named_bar_sync(1 + w, 256);
+      const float mx = fmaxf(m, fmaxf(pmax, xj[(half ^ 1) * 128 + row]));
       const float corr = ex2f(m - mx);
       m = mx;
       if (j > 0) fold(j - 1);                  // also guarantees that P_w(j-1) has been consumed
       corr_prev = corr;
       float tsum = 0.f;
 #pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {      // 32 keys: one tcgen05.st of 16 packed columns, four P_lo chunks of 8 keys
+      for (int c16 = 0; c16 < 2; ++c16) {      // 32 keys: one tcgen05.st of 16 packed columns, four P_lo chunks of 8 keys
         uint32_t pw[16];
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
@@ -265,7 +277,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
             pw[c8 * 4 + e] = *reinterpret_cast<const uint32_t*>(&hh);
             pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
           }
-          const uint32_t dst = prow + (c16 * 4 + c8) * LBO_P;
+          const uint32_t dst = prow + (half * 8 + c16 * 4 + c8) * LBO_P;
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
         }
         tmem_st16(tP + c16 * 16, pw);
@@ -277,26 +289,24 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       mbar_arrive(bar_pf + 8 * w);
     }
     fold(ntiles - 1);
+    // the two threads of a row summed disjoint key columns: combine the normalisers
+    volatile float* xl = xchg + (ntiles & 1) * 512;
+    xl[half * 128 + row] = l;
+    named_bar_sync(1 + w, 256);
+    l += xl[(half ^ 1) * 128 + row];
     const int qt = qt0 + w;
     const int r = qt * 128 + row;
     if (qt < ntiles && r < N) {
       const float inv = __fdiv_rn(1.0f, l);
-      float res[16];
+      float res[8];
 #pragma unroll
-      for (int d = 0; d < 16; ++d) res[d] = o[d] * inv;
-      const int col = h * 16;
+      for (int d = 0; d < 8; ++d) res[d] = o[d] * inv;
+      const int col = h * 16 + half * 8;
       if (out) {
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<float4*>(out + (size_t)r * 64 + col + q4 * 4) = make_float4(res[q4 * 4], res[q4 * 4 + 1], res[q4 * 4 + 2], res[q4 * 4 + 3]);
+        *reinterpret_cast<float4*>(out + (size_t)r * 64 + col) = make_float4(res[0], res[1], res[2], res[3]);
+        *reinterpret_cast<float4*>(out + (size_t)r * 64 + col + 4) = make_float4(res[4], res[5], res[6], res[7]);
       }
-      if (out2) {
-        float r0[8], r1[8];
-#pragma unroll
-        for (int d = 0; d < 8; ++d) { r0[d] = res[d]; r1[d] = res[8 + d]; }
-        split_store8(out2 + (size_t)r * 128 + col, out2 + (size_t)r * 128 + 64 + col, r0);
-        split_store8(out2 + (size_t)r * 128 + col + 8, out2 + (size_t)r * 128 + 64 + col + 8, r1);
-      }
+      if (out2) split_store8(out2 + (size_t)r * 128 + col, out2 + (size_t)r * 128 + 64 + col, res);
     }
   }
   tc_fence_before_sync();
