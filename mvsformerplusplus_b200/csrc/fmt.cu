@@ -161,25 +161,26 @@ linattn_apply_kernel(const float* __restrict__ q, int ldq, const float* __restri
 template <int C>
 __global__ void __launch_bounds__(256)
 upsample_add_kernel(const float* __restrict__ red, const float* __restrict__ lat, float* __restrict__ pre, int h, int w) {
-  __shared__ float tile[C][33];
+  constexpr int RY = 8;                       // output rows per CTA (fewer, fatter CTAs: 35k instead of 276k at DTU stage 4)
+  __shared__ float tile[RY][C][33];
   const int H = 2 * h, W = 2 * w;
-  const int v = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 32;
+  const int v = blockIdx.z, yb = blockIdx.y * RY, x0 = blockIdx.x * 32;
   const float* lv = lat + (size_t)v * C * H * W;
-  for (int i = threadIdx.x; i < C * 32; i += 256) {
-    int c = i >> 5, xx = i & 31;
-    if (x0 + xx < W) tile[c][xx] = __ldg(lv + ((size_t)c * H + y) * W + x0 + xx);
+  for (int i = threadIdx.x; i < RY * C * 32; i += 256) {   // NCHW lateral -> shared memory (coalesced along x)
+    int xx = i & 31, c = (i >> 5) % C, ry = i / (32 * C);
+    if (x0 + xx < W && yb + ry < H) tile[ry][c][xx] = __ldg(lv + ((size_t)c * H + yb + ry) * W + x0 + xx);
   }
   __syncthreads();
-  // ATen area_pixel_compute_source_index(scale=0.5, align_corners=False): src = 0.5*(dst+0.5)-0.5, clamped at 0
-  float sy = fmaxf(0.5f * ((float)y + 0.5f) - 0.5f, 0.0f);
-  int y0 = (int)sy;
-  int y1 = y0 + ((y0 < h - 1) ? 1 : 0);
-  float ly1 = sy - (float)y0, ly0 = 1.0f - ly1;
   const float* rv = red + (size_t)v * h * w * C;
-  for (int i = threadIdx.x; i < 32 * C; i += 256) {
-    int xx = i / C, c = i - xx * C;
-    int x = x0 + xx;
-    if (x >= W) continue;
+  for (int i = threadIdx.x; i < RY * 32 * C; i += 256) {
+    int c = i % C, xx = (i / C) & 31, ry = i / (32 * C);
+    int x = x0 + xx, y = yb + ry;
+    if (x >= W || y >= H) continue;
+    // ATen area_pixel_compute_source_index(scale=0.5, align_corners=False): src = 0.5*(dst+0.5)-0.5, clamped at 0
+    float sy = fmaxf(0.5f * ((float)y + 0.5f) - 0.5f, 0.0f);
+    int y0 = (int)sy;
+    int y1 = y0 + ((y0 < h - 1) ? 1 : 0);
+    float ly1 = sy - (float)y0, ly0 = 1.0f - ly1;
     float sx = fmaxf(0.5f * ((float)x + 0.5f) - 0.5f, 0.0f);
     int xa = (int)sx;
     int xb = xa + ((xa < w - 1) ? 1 : 0);
@@ -187,7 +188,7 @@ upsample_add_kernel(const float* __restrict__ red, const float* __restrict__ lat
     float v00 = __ldg(rv + ((size_t)y0 * w + xa) * C + c), v01 = __ldg(rv + ((size_t)y0 * w + xb) * C + c);
     float v10 = __ldg(rv + ((size_t)y1 * w + xa) * C + c), v11 = __ldg(rv + ((size_t)y1 * w + xb) * C + c);
     float up = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-    pre[(((size_t)v * H + y) * W + x) * C + c] = up + tile[c][xx];
+    pre[(((size_t)v * H + y) * W + x) * C + c] = up + tile[ry][c][xx];
   }
 }
 
@@ -361,7 +362,7 @@ static int run_pathway_level(const float* prev, const float* lat, const float* d
   if ((rc = launch_linear(a, LIN_BIAS, s))) return rc;
   const int H = 2 * h, W = 2 * w;
   MVSF_REQUIRE(H <= 65535 && V <= 65535, "fmt pathway: image too large");
-  upsample_add_kernel<COUT><<<dim3(cdiv(W, 32), H, V), 256, 0, s>>>(red, lat, pre, h, w);
+  upsample_add_kernel<COUT><<<dim3(cdiv(W, 32), cdiv(H, 8), V), 256, 0, s>>>(red, lat, pre, h, w);
   MVSF_LAUNCH_CHECK("fmt_upsample_add");
   conv2d_k3_kernel<COUT><<<dim3(cdiv(W, 32), cdiv(H, Conv2Cfg<COUT>::TH), V), 128, 0, s>>>(pre, sm_w, out, H, W);
   MVSF_LAUNCH_CHECK("fmt_smooth");
