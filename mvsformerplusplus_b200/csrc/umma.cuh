@@ -38,7 +38,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // bounded wait: a mis-programmed pipeline traps (sticky CUDA error) instead of hanging the device
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t it = 0; it < (1u << 24); ++it)
+  for (uint32_t it = 0; it < (1u << 26); ++it)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }

@@ -3,8 +3,9 @@
 // One fused kernel: a CTA owns a 30x30 output tile, keeps the 16-channel intermediates of all three 3x3
 // layers in shared memory (34x34 and 32x32 halo regions) and never writes them to HBM.
 // HBM traffic = 4 B in + 4 B out per pixel; the kernel is fp32-FMA bound (7216 FLOP / pixel).
-// Register tile for the 16->16 and 16->8 layers: 4 consecutive x-pixels x all output channels per thread, inputs
-// fetched with one LDS.128 + one LDS.64 per (ic, ky), weights with broadcast LDS.128.
+// Register tile for the 16->16 and 16->8 layers: 4 consecutive x-pixels x HALF of the output channels per thread (512
+// threads = 16 warps: the kernel runs one CTA per SM, so latency has to be hidden inside the CTA), inputs fetched with one
+// LDS.128 + one LDS.64 per (ic, ky), weights with broadcast LDS.128.
 #include "common.cuh"
 
 namespace mvsf {
@@ -25,7 +26,7 @@ struct VisSmem {
   float w[VIS_WTS + 3];
 };
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts, float* __restrict__ vis, int H, int W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VisSmem& S = *reinterpret_cast<VisSmem*>(smem_raw);
@@ -34,8 +35,8 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
   const int gx0 = blockIdx.x * VT, gy0 = blockIdx.y * VT;
   const float* __restrict__ E = entropy + (size_t)n * H * W;
 
-  for (int i = tid; i < VIS_WTS; i += 256) S.w[i] = __ldg(wts + i);
-  for (int i = tid; i < V_IN * V_IN; i += 256) {
+  for (int i = tid; i < VIS_WTS; i += 512) S.w[i] = __ldg(wts + i);
+  for (int i = tid; i < V_IN * V_IN; i += 512) {
     int yy = i / V_IN, xx = i - yy * V_IN;
     int gy = gy0 - 3 + yy, gx = gx0 - 3 + xx;
     S.in[yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(E + (size_t)gy * W + gx) : 0.0f;
@@ -43,7 +44,7 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
   __syncthreads();
 
   // ---- layer 1: 1 -> 16 on the 34x34 region (zero outside the image: that is layer 2's zero padding)
-  for (int i = tid; i < V_A1 * V_A1; i += 256) {
+  for (int i = tid; i < V_A1 * V_A1; i += 512) {
     int yy = i / V_A1, xx = i - yy * V_A1;
     int gy = gy0 - 2 + yy, gx = gx0 - 2 + xx;
     bool inside = (gy >= 0 && gy < H && gx >= 0 && gx < W);
@@ -64,15 +65,16 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
   }
   __syncthreads();
 
-  // ---- layer 2: 16 -> 16 on the 32x32 region; thread = (row, 4-pixel strip) x 16 output channels
+  // ---- layer 2: 16 -> 16 on the 32x32 region; thread = (row, 4-pixel strip) x 8 output channels (oh = channel half)
   {
-    const int r = tid >> 3, j = tid & 7;
+    const int oh = tid >> 8, t = tid & 255;
+    const int r = t >> 3, j = t & 7;
     const int xs = j * 4;
-    float acc[4][16];
+    float acc[4][8];
 #pragma unroll
     for (int px = 0; px < 4; ++px)
 #pragma unroll
-      for (int oc = 0; oc < 16; ++oc) acc[px][oc] = S.w[OFF_B2 + oc];
+      for (int oc = 0; oc < 8; ++oc) acc[px][oc] = S.w[OFF_B2 + oh * 8 + oc];
     for (int ic = 0; ic < 16; ++ic) {
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
@@ -82,9 +84,9 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
         float in[6] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y};
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float4* wp = reinterpret_cast<const float4*>(&S.w[OFF_W2 + (ic * 9 + ky * 3 + kx) * 16]);
+          const float4* wp = reinterpret_cast<const float4*>(&S.w[OFF_W2 + (ic * 9 + ky * 3 + kx) * 16 + oh * 8]);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 2; ++q) {
             float4 w4 = wp[q];
 #pragma unroll
             for (int px = 0; px < 4; ++px) {
@@ -104,27 +106,30 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
 #pragma unroll
     for (int px = 0; px < 4; ++px) { int gx = gx0 - 1 + xs + px; colin[px] = rowin && gx >= 0 && gx < W; }
 #pragma unroll
-    for (int oc = 0; oc < 16; ++oc) {
+    for (int oc = 0; oc < 8; ++oc) {
       float4 o;
       o.x = colin[0] ? fmaxf(acc[0][oc], 0.f) : 0.f;
       o.y = colin[1] ? fmaxf(acc[1][oc], 0.f) : 0.f;
       o.z = colin[2] ? fmaxf(acc[2][oc], 0.f) : 0.f;
       o.w = colin[3] ? fmaxf(acc[3][oc], 0.f) : 0.f;
-      *reinterpret_cast<float4*>(&S.a2[oc][r][xs]) = o;
+      *reinterpret_cast<float4*>(&S.a2[oh * 8 + oc][r][xs]) = o;
     }
   }
   __syncthreads();
 
-  // ---- layer 3 (16 -> 8) + layer 4 (1x1, 8 -> 1) + sigmoid on the 30x30 tile
+  // ---- layer 3 (16 -> 8) + layer 4 (1x1, 8 -> 1) + sigmoid on the 30x30 tile; thread = (row, strip) x 4 output
+  //      channels; the two channel halves meet through shared memory (the input tile is dead by now)
   {
-    const int r = tid >> 3, j = tid & 7;
+    const int oh = tid >> 8, t = tid & 255;
+    const int r = t >> 3, j = t & 7;
     const int xs = j * 4;
+    float part[4] = {0.f, 0.f, 0.f, 0.f};
     if (r < VT) {
-      float acc[4][8];
+      float acc[4][4];
 #pragma unroll
       for (int px = 0; px < 4; ++px)
 #pragma unroll
-        for (int oc = 0; oc < 8; ++oc) acc[px][oc] = S.w[OFF_B3 + oc];
+        for (int oc = 0; oc < 4; ++oc) acc[px][oc] = S.w[OFF_B3 + oh * 4 + oc];
       for (int ic = 0; ic < 16; ++ic) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -134,32 +139,40 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
           float in[6] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y};
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const float4* wp = reinterpret_cast<const float4*>(&S.w[OFF_W3 + (ic * 9 + ky * 3 + kx) * 8]);
+            const float4 w4 = *reinterpret_cast<const float4*>(&S.w[OFF_W3 + (ic * 9 + ky * 3 + kx) * 8 + oh * 4]);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              float4 w4 = wp[q];
-#pragma unroll
-              for (int px = 0; px < 4; ++px) {
-                float v = in[px + kx];
-                acc[px][q * 4 + 0] = fmaf(v, w4.x, acc[px][q * 4 + 0]);
-                acc[px][q * 4 + 1] = fmaf(v, w4.y, acc[px][q * 4 + 1]);
-                acc[px][q * 4 + 2] = fmaf(v, w4.z, acc[px][q * 4 + 2]);
-                acc[px][q * 4 + 3] = fmaf(v, w4.w, acc[px][q * 4 + 3]);
-              }
+            for (int px = 0; px < 4; ++px) {
+              float v = in[px + kx];
+              acc[px][0] = fmaf(v, w4.x, acc[px][0]);
+              acc[px][1] = fmaf(v, w4.y, acc[px][1]);
+              acc[px][2] = fmaf(v, w4.z, acc[px][2]);
+              acc[px][3] = fmaf(v, w4.w, acc[px][3]);
             }
           }
         }
       }
+      // layer 4 in the reference's channel order: s = b4 + sum_{oc = 0..7} relu(x_oc) * w_oc  (half 0 first, then half 1)
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        float sacc = oh == 0 ? S.w[OFF_B4] : 0.f;
+#pragma unroll
+        for (int oc = 0; oc < 4; ++oc) sacc = fmaf(fmaxf(acc[px][oc], 0.f), S.w[OFF_W4 + oh * 4 + oc], sacc);
+        part[px] = sacc;
+      }
+      if (oh == 1) *reinterpret_cast<float4*>(&S.in[r][xs]) = make_float4(part[0], part[1], part[2], part[3]);
+    }
+    __syncthreads();
+    if (oh == 0 && r < VT) {
       const int gy = gy0 + r;
       if (gy < H) {
+        const float4 other = *reinterpret_cast<const float4*>(&S.in[r][xs]);
+        const float o4[4] = {other.x, other.y, other.z, other.w};
 #pragma unroll
         for (int px = 0; px < 4; ++px) {
           int lx = xs + px, gx = gx0 + lx;
           if (lx < VT && gx < W) {
-            float s = S.w[OFF_B4];
-#pragma unroll
-            for (int oc = 0; oc < 8; ++oc) s = fmaf(fmaxf(acc[px][oc], 0.f), S.w[OFF_W4 + oc], s);
-            vis[((size_t)n * H + gy) * W + gx] = __fdiv_rn(1.0f, 1.0f + expf(-s));
+            const float sv = part[px] + o4[px];
+            vis[((size_t)n * H + gy) * W + gx] = __fdiv_rn(1.0f, 1.0f + expf(-sv));
           }
         }
       }
@@ -182,7 +195,7 @@ extern "C" int mvsf_vis_cnn(const float* entropy, const float* wts, float* vis, 
     configured = true;
   }
   dim3 grid(cdiv(W, VT), cdiv(H, VT), N);
-  vis_cnn_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(entropy, wts, vis, H, W);
+  vis_cnn_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(entropy, wts, vis, H, W);
   MVSF_LAUNCH_CHECK("vis_cnn");
   return MVSF_OK;
 }
