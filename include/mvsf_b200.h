@@ -84,6 +84,13 @@ int mvsf_vis_cnn(const float* entropy, const float* wts, float* vis, int N, int 
  * models/cost_volume.py:72-101 -> volume [D][H][W][G] = sum_v w_v*inprod_v / (sum_v w_v + 1e-6) */
 int mvsf_warp_corr_aggregate(const float* feat, const float* homs, const float* depth, const float* vis,
                              float* volume, int V, int C, int G, int D, int H, int W, mvsf_stream_t stream);
+/* Faster variant of the two calls above (the one hotpath.py uses): pass A additionally stores the per-view group
+ * correlations corr [V-1][D][H*W][G] (G must be 8; 4*G*D*H*W*(V-1) bytes), the view aggregation then streams them
+ * instead of gathering the source features a second time (the gather is L1-request bound, HBM has headroom). */
+int mvsf_warp_corr_entropy_store(const float* feat, const float* homs, const float* depth, float* entropy, float* corr,
+                                 int V, int C, int G, int D, int H, int W, mvsf_stream_t stream);
+int mvsf_corr_aggregate(const float* corr, const float* vis, float* volume, int V, int G, int D, int H, int W,
+                        mvsf_stream_t stream);
 
 /* ---- R2-R4: models/module.py:367-408 (kind 0: CostRegNet, stride 2, 3^3 prob no bias) and
  *      :453-504 (kind 1: CostRegNet3D, stride (1,2,2), 1^3 prob + bias).  volume [D][H][W][C] -> logits [D][H][W].

@@ -23,6 +23,8 @@ SIGNATURES = {
     "mvsf_warp_corr_entropy": ([P, P, P, P, I, I, I, I, I, I, P], I),
     "mvsf_vis_cnn": ([P, P, P, I, I, I, P], I),
     "mvsf_warp_corr_aggregate": ([P, P, P, P, P, I, I, I, I, I, I, P], I),
+    "mvsf_warp_corr_entropy_store": ([P, P, P, P, P, I, I, I, I, I, I, P], I),
+    "mvsf_corr_aggregate": ([P, P, P, I, I, I, I, I, P], I),
     "mvsf_costreg_unet_workspace_bytes": ([I, I, I, I, I, ctypes.POINTER(Z)], I),
     "mvsf_costreg_unet_tc_bytes": ([ctypes.POINTER(Z)], I),
     "mvsf_costreg_unet_pack_tc": ([I, P, P, Z, P], I),

@@ -89,10 +89,14 @@ struct ReduceScatter {
 };
 
 // ---------------------------------------------------------------------------------------------- pass A
-template <int C, bool GENERIC>
+// CPGS > 0: also store the per-view GROUP correlations corr[v][d][pixel][g] (G = C / CPGS = 8 groups) so that the view
+// aggregation becomes a streaming pass (corr_aggregate_kernel) instead of a second gather: the gather is bound by L1
+// requests, the extra 4 * G * D * HW * (V-1) bytes of HBM traffic each way are cheaper.
+template <int C, bool GENERIC, int CPGS>
 __global__ void __launch_bounds__(256)
 warp_corr_entropy_kernel(const float* __restrict__ feat, const float* __restrict__ homs,
-                         const float* __restrict__ depth, float* __restrict__ entropy, int G, int D, int H, int W) {
+                         const float* __restrict__ depth, float* __restrict__ entropy, float* __restrict__ corr, int G,
+                         int D, int H, int W) {
   constexpr int LPP = WC<C>::LPP, P = WC<C>::P, DCH = WC<C>::DCH;
   constexpr int SPL = DCH / LPP;  // complete sims per lane per chunk (= 2)
   constexpr int MAXCH = GENERIC ? (kMaxGenericD + DCH - 1) / DCH : 1;
@@ -134,6 +138,20 @@ warp_corr_entropy_kernel(const float* __restrict__ feat, const float* __restrict
       const float4 w = tb.wt[di * P + pi];
       const float4 s = gather4(src, o, w);
       part[di] = fmaf(r.w, s.w, fmaf(r.z, s.z, fmaf(r.y, s.y, r.x * s.x)));
+      if (CPGS > 0 && d0 + di < D) {   // group correlations exactly as the aggregation pass forms them
+        constexpr float inv_cpg = 1.0f / (float)(CPGS > 0 ? CPGS : 1);
+        float* cp = corr + (((size_t)v * D + d0 + di) * HW + p2) * 8;
+        if (CPGS == 1) {
+          if (active) *reinterpret_cast<float4*>(cp + lip * 4) = make_float4(r.x * s.x, r.y * s.y, r.z * s.z, r.w * s.w);
+        } else if (CPGS == 2) {
+          if (active) *reinterpret_cast<float2*>(cp + lip * 2) = make_float2(fmaf(r.y, s.y, r.x * s.x) * inv_cpg, fmaf(r.w, s.w, r.z * s.z) * inv_cpg);
+        } else if (CPGS == 4) {
+          if (active) cp[lip] = part[di] * inv_cpg;
+        } else {  // 8 channels per group: two lanes share a group
+          const float both = part[di] + __shfl_xor_sync(0xffffffffu, part[di], 1);
+          if (active && (lip & 1) == 0) cp[lip >> 1] = both * inv_cpg;
+        }
+      }
     }
     __syncwarp();
     ReduceScatter<DCH, LPP>::run(part, lip);
@@ -293,15 +311,43 @@ __global__ void homo_warp_kernel(const float* __restrict__ src, const float* __r
 }
 
 template <int C>
-static int launch_entropy(const float* feat, const float* homs, const float* depth, float* entropy, int V, int G, int D,
-                          int H, int W, cudaStream_t s) {
+static int launch_entropy(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V, int G,
+                          int D, int H, int W, cudaStream_t s) {
   constexpr int P = WC<C>::P;
   dim3 grid(cdiv((long long)H * W, 8 * P), V - 1);
-  if (D == WC<C>::DCH)
-    warp_corr_entropy_kernel<C, false><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, G, D, H, W);
-  else
-    warp_corr_entropy_kernel<C, true><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, G, D, H, W);
+  if (corr) {   // G == 8 (checked by the caller)
+    if (D == WC<C>::DCH)
+      warp_corr_entropy_kernel<C, false, C / 8><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, corr, G, D, H, W);
+    else
+      warp_corr_entropy_kernel<C, true, C / 8><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, corr, G, D, H, W);
+  } else if (D == WC<C>::DCH) {
+    warp_corr_entropy_kernel<C, false, 0><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, nullptr, G, D, H, W);
+  } else {
+    warp_corr_entropy_kernel<C, true, 0><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, nullptr, G, D, H, W);
+  }
   return 0;
+}
+
+// volume[d][p][g] = sum_v vis[v][p] * corr[v][d][p][g] / (sum_v vis[v][p] + 1e-6)   (cost_volume.py:95-101), G = 8
+__global__ void __launch_bounds__(256)
+corr_aggregate_kernel(const float* __restrict__ corr, const float* __restrict__ vis, float* __restrict__ volume, int V, int D,
+                      int HW) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (d, pixel, half of the 8 groups)
+  const size_t total = (size_t)D * HW * 2;
+  if (i >= total) return;
+  const size_t dp = i >> 1;
+  const int p = (int)(dp % HW);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float wsum = 0.f;
+  for (int v = 0; v < V - 1; ++v) {
+    const float w = __ldg(vis + (size_t)v * HW + p);
+    const float4 c = ldg4(corr + ((size_t)v * D * HW + dp) * 8 + (i & 1) * 4);
+    wsum = __fadd_rn(wsum, w);
+    acc.x = fmaf(c.x, w, acc.x); acc.y = fmaf(c.y, w, acc.y); acc.z = fmaf(c.z, w, acc.z); acc.w = fmaf(c.w, w, acc.w);
+  }
+  const float den = __fadd_rn(wsum, 1e-6f);
+  *reinterpret_cast<float4*>(volume + dp * 8 + (i & 1) * 4) =
+      make_float4(__fdiv_rn(acc.x, den), __fdiv_rn(acc.y, den), __fdiv_rn(acc.z, den), __fdiv_rn(acc.w, den));
 }
 
 template <int C, int CPG>
@@ -319,8 +365,31 @@ using namespace mvsf;
 
 extern "C" {
 
+static int warp_corr_entropy_impl(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
+                                  int C, int G, int D, int H, int W, mvsf_stream_t stream);
+
 int mvsf_warp_corr_entropy(const float* feat, const float* homs, const float* depth, float* entropy, int V, int C,
                            int G, int D, int H, int W, mvsf_stream_t stream) {
+  return warp_corr_entropy_impl(feat, homs, depth, entropy, nullptr, V, C, G, D, H, W, stream);
+}
+
+int mvsf_warp_corr_entropy_store(const float* feat, const float* homs, const float* depth, float* entropy, float* corr,
+                                 int V, int C, int G, int D, int H, int W, mvsf_stream_t stream) {
+  MVSF_REQUIRE(corr && ((uintptr_t)corr & 15) == 0 && G == 8, "warp_corr_entropy_store: corr must be 16-byte aligned and G == 8");
+  return warp_corr_entropy_impl(feat, homs, depth, entropy, corr, V, C, G, D, H, W, stream);
+}
+
+int mvsf_corr_aggregate(const float* corr, const float* vis, float* volume, int V, int G, int D, int H, int W,
+                        mvsf_stream_t stream) {
+  MVSF_REQUIRE(corr && vis && volume && V >= 2 && G == 8 && D >= 1 && H > 0 && W > 0, "corr_aggregate: bad arguments (G must be 8)");
+  const size_t total = (size_t)D * H * W * 2;
+  corr_aggregate_kernel<<<cdiv((long long)total, 256), 256, 0, (cudaStream_t)stream>>>(corr, vis, volume, V, D, H * W);
+  MVSF_LAUNCH_CHECK("corr_aggregate");
+  return MVSF_OK;
+}
+
+static int warp_corr_entropy_impl(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
+                                  int C, int G, int D, int H, int W, mvsf_stream_t stream) {
   MVSF_REQUIRE(feat && homs && depth && entropy, "warp_corr_entropy: null pointer");
   MVSF_REQUIRE(V >= 2 && H > 0 && W > 0 && D >= 1, "warp_corr_entropy: bad shape");
   MVSF_REQUIRE(G <= C, "G must <= C!");  // models/cost_volume.py:87
@@ -328,10 +397,10 @@ int mvsf_warp_corr_entropy(const float* feat, const float* homs, const float* de
   MVSF_REQUIRE(D <= kMaxGenericD, "warp_corr_entropy: D <= %d", kMaxGenericD);
   cudaStream_t s = (cudaStream_t)stream;
   switch (C) {
-    case 8: launch_entropy<8>(feat, homs, depth, entropy, V, G, D, H, W, s); break;
-    case 16: launch_entropy<16>(feat, homs, depth, entropy, V, G, D, H, W, s); break;
-    case 32: launch_entropy<32>(feat, homs, depth, entropy, V, G, D, H, W, s); break;
-    default: launch_entropy<64>(feat, homs, depth, entropy, V, G, D, H, W, s); break;
+    case 8: launch_entropy<8>(feat, homs, depth, entropy, corr, V, G, D, H, W, s); break;
+    case 16: launch_entropy<16>(feat, homs, depth, entropy, corr, V, G, D, H, W, s); break;
+    case 32: launch_entropy<32>(feat, homs, depth, entropy, corr, V, G, D, H, W, s); break;
+    default: launch_entropy<64>(feat, homs, depth, entropy, corr, V, G, D, H, W, s); break;
   }
   MVSF_LAUNCH_CHECK("warp_corr_entropy");
   return MVSF_OK;

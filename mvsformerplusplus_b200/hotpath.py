@@ -163,13 +163,22 @@ class StageNet(_PackedMixin, nn.Module):
         kinv = torch.empty(9, **f32)
         _lib.check(L.mvsf_compose_geometry(_ptr(proj), V, _ptr(homs), _ptr(kinv), st), "compose_geometry")
         entropy = torch.empty((V - 1, H, W), **f32)
-        _lib.check(L.mvsf_warp_corr_entropy(_ptr(feat_nhwc), _ptr(homs), _ptr(depth_values), _ptr(entropy),
-                                            V, C, G, D, H, W, st), "warp_corr_entropy")
         vis = torch.empty((V - 1, H, W), **f32)
-        _lib.check(L.mvsf_vis_cnn(_ptr(entropy), _ptr(pk["vis"]), _ptr(vis), V - 1, H, W, st), "vis_cnn")
         volume = torch.empty((D, H, W, G), **f32)
-        _lib.check(L.mvsf_warp_corr_aggregate(_ptr(feat_nhwc), _ptr(homs), _ptr(depth_values), _ptr(vis),
-                                              _ptr(volume), V, C, G, D, H, W, st), "warp_corr_aggregate")
+        if G == 8:
+            # pass A also stores the per-view group correlations; the view aggregation then streams them (no second gather)
+            corr = torch.empty((V - 1, D, H, W, G), **f32)
+            _lib.check(L.mvsf_warp_corr_entropy_store(_ptr(feat_nhwc), _ptr(homs), _ptr(depth_values), _ptr(entropy),
+                                                      _ptr(corr), V, C, G, D, H, W, st), "warp_corr_entropy_store")
+            _lib.check(L.mvsf_vis_cnn(_ptr(entropy), _ptr(pk["vis"]), _ptr(vis), V - 1, H, W, st), "vis_cnn")
+            _lib.check(L.mvsf_corr_aggregate(_ptr(corr), _ptr(vis), _ptr(volume), V, G, D, H, W, st), "corr_aggregate")
+            del corr
+        else:
+            _lib.check(L.mvsf_warp_corr_entropy(_ptr(feat_nhwc), _ptr(homs), _ptr(depth_values), _ptr(entropy),
+                                                V, C, G, D, H, W, st), "warp_corr_entropy")
+            _lib.check(L.mvsf_vis_cnn(_ptr(entropy), _ptr(pk["vis"]), _ptr(vis), V - 1, H, W, st), "vis_cnn")
+            _lib.check(L.mvsf_warp_corr_aggregate(_ptr(feat_nhwc), _ptr(homs), _ptr(depth_values), _ptr(vis),
+                                                  _ptr(volume), V, C, G, D, H, W, st), "warp_corr_aggregate")
         kept = dict(entropy=entropy, vis_weight=vis, volume_mean=volume.clone() if keep else None) if keep else None
         logits = torch.empty((D, H, W), **f32)
         need = ctypes.c_size_t(0)

@@ -192,6 +192,16 @@ def test_cost_volume_kernels(dev, L, C, D, H, W, V, th):
     ck(L.mvsf_vis_cnn(P(ent), P(wts), P(vis), V - 1, H, W, S()), "vis_cnn")
     vol = torch.empty(D, H, W, 8, device=dev)
     ck(L.mvsf_warp_corr_aggregate(P(f), P(homs), P(dd), P(vis), P(vol), V, C, 8, D, H, W, S()), "warp_corr_aggregate")
+    # the path hotpath.py uses: pass A stores the per-view group correlations, the aggregation streams them
+    ent_s = torch.empty(V - 1, H, W, device=dev)
+    corr = torch.empty(V - 1, D, H, W, 8, device=dev)
+    vol_s = torch.empty(D, H, W, 8, device=dev)
+    ck(L.mvsf_warp_corr_entropy_store(P(f), P(homs), P(dd), P(ent_s), P(corr), V, C, 8, D, H, W, S()), "warp_corr_entropy_store")
+    ck(L.mvsf_corr_aggregate(P(corr), P(vis), P(vol_s), V, 8, D, H, W, S()), "corr_aggregate")
+    assert torch.equal(ent_s, ent)
+    e_paths = max_abs(vol_s.cpu(), vol.cpu())
+    assert e_paths <= 2e-6 * max(1.0, float(vol.abs().max())), e_paths   # identical up to the pair sum of 8-channel groups
+    vol = vol_s
     e_ent = max_abs(ent.cpu(), want["entropy"][0])
     e_vis = max_abs(vis.cpu(), want["vis_weight"][0])
     e_vol = max_abs(vol.cpu().permute(3, 0, 1, 2), want["volume_mean"][0])
