@@ -245,9 +245,13 @@ def run_ours(a, wl, rank, world, local_rank):
         tf_which = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel runs inside a long step)"
                     if peaks else "fallback (B200_PROFILING.md)")
         achieved_tf = att_flops / 1e12 / (att_launch_ms / 1e3) if att_launch_ms > 0 else 0.0
-        line_extra["roofline"] = {"bound": "tensor", "kernel": "attention_tc_kernel (stage-1 transformer regulariser, 1 launch / layer)",
+        traffic = None   # dram bytes per launch of the same kernel from the committed ncu capture (profiles/)
+        tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        if os.path.exists(tpath) and wl is WORKLOADS["dtu"]:
+            traffic = json.load(open(tpath)).get("attention_fa_kernel", {}).get("dram_bytes_per_launch")
+        line_extra["roofline"] = {"bound": "tensor", "kernel": "attention_fa_kernel (stage-1 transformer regulariser, 1 launch / layer)",
                                   "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
-                                  "traffic": None, "peak_source": tf_which, "algorithmic_flops_per_launch": att_flops,
+                                  "traffic": traffic, "peak_source": tf_which, "algorithmic_flops_per_launch": att_flops,
                                   "launch_ms": att_launch_ms, "launches_per_depth_map": att_n // reps,
                                   "share_of_step": att_ms / reps / ms_step if ms_step > 0 else None,
                                   "note": "fp32-class accuracy costs 3 fp16 products per GEMM and the kernel is bound by the "
