@@ -121,7 +121,7 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, c
 int mvsf_split_weights_f16(const float* wts, void* out16, size_t n, mvsf_stream_t stream);
 
 /* softmax attention of R1 alone: models/dino/layers/attention.py:141-170 (FlashAttention2.forward after the qkv linear).
- * qkv [N][3][4][16] fp32 -> out [N][64]; workspace >= (N+128)*768 bytes.  tcgen05 tensor cores, 3-term split-fp16 operands,
+ * qkv [N][3][4][16] fp32 -> out [N][64]; workspace >= (N+128)*896 bytes.  tcgen05 tensor cores, 3-term split-fp16 operands,
  * fp32 accumulation in TMEM; |q*scale|, |k|, |v| must be < 65504. */
 int mvsf_attention_forward(const float* qkv, float* out, void* workspace, size_t workspace_bytes, int N,
                            float softmax_scale, mvsf_stream_t stream);

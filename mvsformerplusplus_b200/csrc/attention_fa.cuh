@@ -12,19 +12,21 @@
 //                 waiting for their MMAs (ping-pong)
 // S_w(t) = Q_w K(t)^T is issued as soon as warpgroup w has pulled S_w(t-1) out of TMEM, O_w(t) = P_w(t) V(t) as soon as
 // P_w(t) is complete.  P_hi is written back to TENSOR MEMORY (tcgen05.st) and consumed as the A operand of two of the
-// three P*V products (issued as ONE N = 32 MMA against [V_hi | V_lo]); only P_lo travels through shared memory.  The three
-// partial products sit in separate TMEM columns that the softmax thread adds (round to nearest) while folding the tile
-// into its running output.
+// three P*V products (issued as ONE MMA against [V_lo | V_hi | 1]); only P_lo travels through shared memory.  The ones
+// row of V makes the tensor core produce the softmax normaliser of the tile as well (no per-element add in the softmax
+// threads).  The partial products sit in TMEM columns that the softmax thread adds (round to nearest) while folding the
+// tile into its running output.
 #pragma once
 
 namespace fa6 {
 using namespace umma;
 constexpr int NSOFT = 512, THREADS = 64 + NSOFT, NKV = 3;   // two threads per query row: 4 softmax warps per scheduler
 constexpr uint32_t TILE = 4096;                 // one canonical 128 x 16 (Q, K) or 16 x 128 (V^T) fp16 tile
-constexpr uint32_t LBO_QK = 2048, LBO_V = 512;  // k-chunk strides: Q/K 128 rows; V^T 32 rows = V_hi dims 0-15 | V_lo dims 0-15
+constexpr uint32_t LBO_QK = 2048, LBO_V = 768;  // k-chunk strides: Q/K 128 rows; V^T 48 rows = V_lo dims | V_hi dims | ones row + 15 zero rows
+constexpr uint32_t V_TILE = 16 * LBO_V;         // 12 KB
 constexpr uint32_t LBO_P = 2048, P_TILE = 16 * LBO_P;
 // Q (2 tiles x hi,lo) | K ring (hi,lo) | V ring (hi,lo) | P_lo (2 warpgroups) | barriers
-constexpr uint32_t OFF_Q = 0, OFF_K = 4 * TILE, OFF_V = OFF_K + NKV * 2 * TILE, OFF_P = OFF_V + NKV * 2 * TILE,
+constexpr uint32_t OFF_Q = 0, OFF_K = 4 * TILE, OFF_V = OFF_K + NKV * 2 * TILE, OFF_P = OFF_V + NKV * V_TILE,
                    OFF_X = OFF_P + 2 * P_TILE, OFF_BAR = OFF_X + 4096;   // OFF_X: row-max / row-sum exchange [2 parity][2 tiles][2 halves][128]
 constexpr uint32_t SMEM = OFF_BAR + 256;
 // TMEM columns: S_w at 128 w; O_w (3 accumulators x 16) at 256 + 64 w; P_hi_w (64) at 384 + 64 w
@@ -55,8 +57,9 @@ __device__ __forceinline__ void commit_e(uint32_t el, uint32_t bar) { commit_el(
 }  // namespace fa6
 
 // tiled layout: planes Qh, Ql, Kh, Kl of 4 heads x ntiles x 2048 halves (tile = [2 k-chunks][128 rows][8]) and one V plane
-// of 4 heads x ntiles x 4096 halves: V^T tile = [16 k-chunks of 8 keys][32 rows: 16 dims of V_hi, 16 dims of V_lo][8 keys]
-// - the N = 32 operand [V_hi | V_lo] whose first 16 rows are the N = 16 operand V_hi.  Rows / keys >= N are zero.
+// of 4 heads x ntiles x 6144 halves: V^T tile = [16 k-chunks of 8 keys][48 rows][8 keys] with rows 0-15 = dims of V_lo,
+// 16-31 = dims of V_hi, row 32 = ones (its product with P is the softmax normaliser of the tile), rows 33-47 = zero.
+// P_hi multiplies all 48 rows (N = 48), P_lo rows 16-47 (N = 32: V_hi and the ones row).  Rows / keys >= N of Q, K, V are zero.
 __global__ void qkv_tile_kernel(const float* __restrict__ qkv, __half* __restrict__ tiled, int N, int ntiles, float qscale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (token, which, head, octet of 8 dims)
   const int total = ntiles * 128 * 3 * 4 * 2;
@@ -82,14 +85,22 @@ __global__ void qkv_tile_kernel(const float* __restrict__ qkv, __half* __restric
     __half* pl = ph + plane;
     split_store8(ph + oct * 1024 + r * 8, pl + oct * 1024 + r * 8, v);
   } else {
-    __half* pv = tiled + (size_t)4 * plane + ((size_t)h * ntiles + tile) * 4096;
+    __half* pv = tiled + (size_t)4 * plane + ((size_t)h * ntiles + tile) * 6144;
     const int kc = r >> 3, e = r & 7;
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
       __half hi, lo;
       split_f16(v[d], hi, lo);
-      pv[kc * 256 + (oct * 8 + d) * 8 + e] = hi;
-      pv[kc * 256 + (16 + oct * 8 + d) * 8 + e] = lo;
+      pv[kc * 384 + (oct * 8 + d) * 8 + e] = lo;
+      pv[kc * 384 + (16 + oct * 8 + d) * 8 + e] = hi;
+    }
+    if (oct == 0) {
+      pv[kc * 384 + 32 * 8 + e] = __float2half_rn(1.0f);
+#pragma unroll
+      for (int z = 33; z < 40; ++z) pv[kc * 384 + z * 8 + e] = __float2half_rn(0.f);
+    } else {
+#pragma unroll
+      for (int z = 40; z < 48; ++z) pv[kc * 384 + z * 8 + e] = __float2half_rn(0.f);
     }
   }
 }
@@ -138,13 +149,13 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
         bulk_load(sb + OFF_K + (2 * s) * TILE, base + 2 * plane + (size_t)t * 2048, TILE, bar_kf + 8 * s);
         bulk_load(sb + OFF_K + (2 * s + 1) * TILE, base + 3 * plane + (size_t)t * 2048, TILE, bar_kf + 8 * s);
         mbar_wait(bar_ve + 8 * s, par);
-        expect_tx(bar_vf + 8 * s, 2 * TILE);
-        bulk_load(sb + OFF_V + (2 * s) * TILE, tiled + 4 * plane + ((size_t)h * ntiles + t) * 4096, 2 * TILE, bar_vf + 8 * s);
+        expect_tx(bar_vf + 8 * s, V_TILE);
+        bulk_load(sb + OFF_V + s * V_TILE, tiled + 4 * plane + ((size_t)h * ntiles + t) * 6144, V_TILE, bar_vf + 8 * s);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer (converged warp)
-    const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 16), idesc_o2 = make_idesc_f16(128, 32);
+    const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 32), idesc_o2 = make_idesc_f16(128, 48);
     const uint32_t el = elect_one();
     // low descriptor words of everything that does not move
     const uint32_t q_hi[2] = {desc_lo(sb + OFF_Q, LBO_QK), desc_lo(sb + OFF_Q + 2 * TILE, LBO_QK)};
@@ -164,15 +175,14 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
     };
     auto issue_pv = [&](int w, int u) {          // O_w(u) = P_w(u) V(u)  (V(u) has landed, P_w(u) is complete)
       tc_fence_after_sync();
-      const uint32_t vv = v0 + (uint32_t)(u % NKV) * (2 * TILE >> 4);
+      const uint32_t vv = v0 + (uint32_t)(u % NKV) * (V_TILE >> 4);
       const uint32_t tO = tmem_base + col_o(w), tP = tmem_base + col_p(w);
-      // two MMAs per 16 keys: P_hi (tensor memory) x [V_hi | V_lo] (N = 32: both products side by side) and P_lo (shared
-      // memory) x V_hi (N = 16).  An MMA costs ~50 clk whatever N <= 64 is, so fewer instructions is what counts.
+      // two MMAs per 16 keys: P_hi (tensor memory) x [V_lo | V_hi | 1] (N = 48) -> columns [P_hi V_lo | P_hi V_hi | sum P_hi],
+      // then P_lo (shared memory) x [V_hi | 1] (N = 32) accumulated onto columns 16..47.  An MMA costs ~50 clk whatever N <= 64.
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const uint32_t acc = i > 0 ? 1u : 0u;
-        mma_ts(el, tO, tP + i * 8, vv + i * (2 * LBO_V >> 4), idesc_o2, acc);
-        mma_ss(el, tO + 32, p_lo[w] + i * (2 * LBO_P >> 4), vv + i * (2 * LBO_V >> 4), idesc_o, acc);
+        mma_ts(el, tO, tP + i * 8, vv + i * (2 * LBO_V >> 4), idesc_o2, i > 0 ? 1u : 0u);
+        mma_ss(el, tO + 16, p_lo[w] + i * (2 * LBO_P >> 4), vv + i * (2 * LBO_V >> 4) + (256 >> 4), idesc_o, 1u);
       }
       commit_e(el, bar_of + 8 * w);
     };
@@ -211,7 +221,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = ((uint32_t)(quarter * 32)) << 16;
     const uint32_t tS = tmem_base + col_s(w) + lane_off + half * 64, tO = tmem_base + col_o(w) + lane_off + half * 8,
-                   tP = tmem_base + col_p(w) + lane_off + half * 32;
+                   tP = tmem_base + col_p(w) + lane_off + half * 32, tOl = tmem_base + col_o(w) + lane_off + 32;
     const uint32_t prow = sb + OFF_P + w * P_TILE + (row >> 3) * 128 + (row & 7) * 16;   // this row inside every P_lo k-chunk
     volatile float* xchg = reinterpret_cast<volatile float*>(smem + OFF_X) + w * 256;    // [parity][tile][half][128]
     float o[8];    // this thread's 8 of the 16 head dims: [8 half, 8 half + 8)
@@ -221,14 +231,14 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
     auto fold = [&](int t) {   // o = o * corr_prev + (three partial products of tile t)
       mbar_wait(bar_of + 8 * w, (uint32_t)(t & 1));
       tc_fence_after_sync();
-      uint32_t a0[8], a1[8], a2[8];
-      tmem_ld8_nowait(tO, a0);
-      tmem_ld8_nowait(tO + 16, a1);
-      tmem_ld8_nowait(tO + 32, a2);
+      uint32_t a0[8], a1[8], ls;
+      tmem_ld8_nowait(tO, a0);                       // P_hi V_lo
+      tmem_ld8_nowait(tO + 16, a1);                  // P_hi V_hi + P_lo V_hi
+      tmem_ld1_nowait(tOl, ls);                      // sum of the tile's P (ones row of V): the normaliser
       tmem_ld_wait();
 #pragma unroll
-      for (int d = 0; d < 8; ++d)
-        o[d] = fmaf(o[d], corr_prev, (__uint_as_float(a0[d]) + __uint_as_float(a1[d])) + __uint_as_float(a2[d]));
+      for (int d = 0; d < 8; ++d) o[d] = fmaf(o[d], corr_prev, __uint_as_float(a0[d]) + __uint_as_float(a1[d]));
+      l = fmaf(l, corr_prev, __uint_as_float(ls));
     };
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(bar_sf + 8 * w, (uint32_t)(j & 1));
@@ -259,7 +269,10 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       m = mx;
       if (j > 0) fold(j - 1);                  // also guarantees that P_w(j-1) has been consumed
       corr_prev = corr;
-      float tsum = 0.f;
+      // P is stored as fp16 hi + lo: scale it by 2^14 (largest element 16384 < 65504) so that probabilities down to 4e-12
+      // survive - without the bias every p < 3e-8 underflows to zero, a SYSTEMATIC loss of up to N * 3e-8 in the
+      // normaliser for peaked rows.  The factor cancels in O / l.
+      const float mb = m - 14.0f;
 #pragma unroll
       for (int c16 = 0; c16 < 2; ++c16) {      // 32 keys: one tcgen05.st of 16 packed columns, four P_lo chunks of 8 keys
         uint32_t pw[16];
@@ -268,9 +281,8 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
           uint32_t pl[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float p0 = ex2f(__uint_as_float(sr[c16][c8 * 8 + 2 * e]) - m);
-            const float p1 = ex2f(__uint_as_float(sr[c16][c8 * 8 + 2 * e + 1]) - m);
-            tsum += p0 + p1;
+            const float p0 = ex2f(__uint_as_float(sr[c16][c8 * 8 + 2 * e]) - mb);
+            const float p1 = ex2f(__uint_as_float(sr[c16][c8 * 8 + 2 * e + 1]) - mb);
             const __half2 hh = __floats2half2_rn(p0, p1);
             const float2 hf = __half22float2(hh);
             const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
@@ -282,18 +294,12 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
         }
         tmem_st16(tP + c16 * 16, pw);
       }
-      l = fmaf(l, corr, tsum);
       tmem_st_wait();
       fence_proxy_async();
       tc_fence_before_sync();
       mbar_arrive(bar_pf + 8 * w);
     }
     fold(ntiles - 1);
-    // the two threads of a row summed disjoint key columns: combine the normalisers
-    volatile float* xl = xchg + (ntiles & 1) * 512;
-    xl[half * 128 + row] = l;
-    named_bar_sync(1 + w, 256);
-    l += xl[(half ^ 1) * 128 + row];
     const int qt = qt0 + w;
     const int r = qt * 128 + row;
     if (qt < ntiles && r < N) {

@@ -165,7 +165,7 @@ int mvsf_costreg_tr_workspace_bytes(int C, int D, int H, int W, size_t* bytes) {
   size_t N = (size_t)(D / 2) * (H / 4) * (W / 4);
   // per token (in floats): big 256 (patches2 / ffn hidden split / un-patchify out), x 64, y 64, x2 64, y2 64, o2 64,
   // qkv 192, attention operand split 192
-  *bytes = (N * (256 + 64 + 64 + 64 + 64 + 64 + 192) + (N + 128) * 192) * sizeof(float);
+  *bytes = (N * (256 + 64 + 64 + 64 + 64 + 64 + 192) + (N + 128) * 224) * sizeof(float);
   return MVSF_OK;
 }
 
@@ -247,7 +247,7 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, c
 int mvsf_attention_forward(const float* qkv, float* out, void* workspace, size_t workspace_bytes, int N,
                            float softmax_scale, mvsf_stream_t stream) {
   MVSF_REQUIRE(qkv && out && workspace && N > 0, "attention_forward: bad arguments");
-  if (workspace_bytes < (size_t)(N + 128) * 768) return fail(MVSF_ERR_WORKSPACE, "attention_forward: workspace %zu < %zu bytes", workspace_bytes, (size_t)(N + 128) * 768);
+  if (workspace_bytes < (size_t)(N + 128) * 896) return fail(MVSF_ERR_WORKSPACE, "attention_forward: workspace %zu < %zu bytes", workspace_bytes, (size_t)(N + 128) * 896);
   return run_attention(qkv, out, nullptr, reinterpret_cast<__half*>(workspace), N, softmax_scale * 1.4426950408889634f, (cudaStream_t)stream);
 }
 }

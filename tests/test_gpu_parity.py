@@ -496,7 +496,7 @@ def test_attention_tensor_core_vs_fp64(dev, L, N):
     qkv = torch.randn(N, 192, generator=g) * 1.5
     scale = 16 ** -0.5 * math.log(N, 12185)
     qd = qkv.to(dev)
-    ws = torch.empty((N + 128) * 192 + 16, device=dev)
+    ws = torch.empty((N + 128) * 224 + 16, device=dev)
     o0 = torch.empty(N, 64, device=dev)
     ck(L.mvsf_attention_forward(P(qd), P(o0), P(ws), ctypes.c_size_t(ws.numel() * 4), N, float(scale), S()), "attention")
     q, k, v = [qd[:, i * 64:(i + 1) * 64].double().view(N, 4, 16).transpose(0, 1) for i in range(3)]

@@ -10,7 +10,7 @@ bad = 0
 for N in (64, 128, 129, 255, 257, 384, 1000, 4097, 27648):
     torch.manual_seed(N)
     qkv = torch.randn(N, 192, device=dev)
-    ws = torch.empty((N + 128) * 192 + 16, device=dev)
+    ws = torch.empty((N + 128) * 224 + 16, device=dev)
     ref = None
     reps = 300 if N < 5000 else 60
     for i in range(reps):
