@@ -6,8 +6,9 @@
 //                                       PLANES in shared memory (plane[row][col] = 8 channels = 16 B), the layout in
 //                                       which a 3x3 tap is just another UMMA descriptor start address (see conv3d_tc.cu)
 //   layer 2 (16 -> 16) and 3 (16 -> 8)  implicit GEMMs on tcgen05: M-tile = 16 rows x 8 columns of pixels, N = 16, K = 16
-//                                       channels, 9 taps x 3 split-precision products (x_lo w_hi, x_hi w_lo, x_hi w_hi)
-//                                       with fp32 accumulators in TMEM; the layer-2 epilogue (bias, ReLU, zero outside the
+//                                       channels; per tap two MMAs: x_hi x [w_hi | w_lo] (N = 32, both products side by
+//                                       side) and x_lo x w_hi (N = 16, accumulated onto the first), fp32 accumulators in
+//                                       TMEM (a small-N tcgen05.mma costs ~50 clk whatever N is: fewer, wider MMAs); the layer-2 epilogue (bias, ReLU, zero outside the
 //                                       image = layer 3's padding) writes the planes of layer 3's input
 //   layer 4 + sigmoid                   in the layer-3 epilogue (one TMEM lane = one pixel per thread)
 // The 16 x 32 region of layer 2 and the 14 x 30 tile of layer 3 are both covered by four 16 x 8 M-tiles; rows / columns of
@@ -32,7 +33,7 @@ constexpr int IN_R = 20, IN_C = 36;             // input region (3-pixel halo)
 constexpr int OFF_W1 = 0, OFF_B1 = 144, OFF_W2 = 160, OFF_B2 = 160 + 2304, OFF_W3 = OFF_B2 + 16,
               OFF_B3 = OFF_W3 + 1152, OFF_W4 = OFF_B3 + 8, OFF_B4 = OFF_W4 + 8, VIS_WTS = OFF_B4 + 1;
 // shared memory (bytes): planes a1 [hi o0 | hi o1 | lo o0 | lo o1], planes a2, weight tiles, input, small params, barrier
-constexpr uint32_t OFF_A1 = 0, OFF_A2 = 4 * PLANE, OFF_B2T = 8 * PLANE, BT_LAYER = 9 * 2 * 512,   // [tap][hi|lo][2 kc][16][8]
+constexpr uint32_t OFF_A1 = 0, OFF_A2 = 4 * PLANE, OFF_B2T = 8 * PLANE, BT_LAYER = 9 * 1024,      // [tap][2 kc][32 rows: w_hi | w_lo][8]
                    OFF_B3T = OFF_B2T + BT_LAYER, OFF_IN = OFF_B3T + BT_LAYER, OFF_PAR = OFF_IN + IN_R * IN_C * 4,
                    OFF_BAR = OFF_PAR + 1024, SMEM = OFF_BAR + 32;
 // small parameter block (floats): w1[144] b1[16] b2[16] b3[8] w4[8] b4[1]
@@ -64,12 +65,12 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
     else if (n < 8) w = __ldg(wts + OFF_W3 + (ci * 9 + tap) * 8 + n);
     const __half hi = __float2half_rn(w), lo = __float2half_rn(w - __half2float(hi));
     __half* t = reinterpret_cast<__half*>(smem + (layer ? OFF_B3T : OFF_B2T) + tap * 1024);
-    t[kc * 128 + n * 8 + e] = hi;
-    t[256 + kc * 128 + n * 8 + e] = lo;
+    t[kc * 256 + n * 8 + e] = hi;
+    t[kc * 256 + (16 + n) * 8 + e] = lo;
   }
   for (int i = tid; i < (int)(4 * PLANE / 16); i += 256) reinterpret_cast<uint4*>(smem + OFF_A2)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-  if (warp == 0) tmem_alloc(sb + OFF_BAR + 16, 128);
+  if (warp == 0) tmem_alloc(sb + OFF_BAR + 16, 256);
   fence_proxy_async();
   tc_fence_before_sync();
   __syncthreads();
@@ -77,7 +78,7 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t el = elect_one();
   constexpr uint32_t a_hi = desc_hi(PITCH), b_hi = desc_hi(128);
-  const uint32_t idesc = make_idesc_f16(128, 16);
+  const uint32_t idesc16 = make_idesc_f16(128, 16), idesc32 = make_idesc_f16(128, 32);
   uint32_t phase = 0;
 
   // MMAs of one 3x3 layer over the four M-tiles: planes at `pl`, weight tiles at `bt`, accumulators at TMEM column `col`
@@ -88,14 +89,13 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
       for (int kw = 0; kw < 3; ++kw) {
         const uint32_t aoff = (uint32_t)(kh * PC + kw) * 16u;
         const uint32_t ah = desc_lo(pl + aoff, PLANE), al = desc_lo(pl + 2 * PLANE + aoff, PLANE);   // K = two octets
-        const uint32_t wh = desc_lo(bt + (kh * 3 + kw) * 1024, 256), wl = wh + (512 >> 4);
+        const uint32_t wb = desc_lo(bt + (kh * 3 + kw) * 1024, 512);
         const uint32_t acc = (kh | kw) ? 1u : 0u;
+        // accumulator columns of M-tile ct: [32 ct, +16) = x_hi w_hi + x_lo w_hi, [32 ct + 16, +16) = x_hi w_lo
 #pragma unroll
-        for (int ct = 0; ct < 4; ++ct) mma_f16_ss_lh(el, tmem_base + col + ct * 16, al + ct * 8, a_hi, wh, b_hi, idesc, acc);  // x_lo w_hi
+        for (int ct = 0; ct < 4; ++ct) mma_f16_ss_lh(el, tmem_base + col + ct * 32, ah + ct * 8, a_hi, wb, b_hi, idesc32, acc);
 #pragma unroll
-        for (int ct = 0; ct < 4; ++ct) mma_f16_ss_lh(el, tmem_base + col + ct * 16, ah + ct * 8, a_hi, wl, b_hi, idesc, 1u);   // x_hi w_lo
-#pragma unroll
-        for (int ct = 0; ct < 4; ++ct) mma_f16_ss_lh(el, tmem_base + col + ct * 16, ah + ct * 8, a_hi, wh, b_hi, idesc, 1u);   // x_hi w_hi
+        for (int ct = 0; ct < 4; ++ct) mma_f16_ss_lh(el, tmem_base + col + ct * 32, al + ct * 8, a_hi, wb, b_hi, idesc16, 1u);
       }
     }
     commit_el(el, bar);
@@ -104,7 +104,7 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
   // epilogue geometry: warp w reads TMEM lanes 32 (w % 4) ..., warps 0-3 take M-tiles 0 and 1, warps 4-7 M-tiles 2 and 3
   const int quarter = warp & 3, m = quarter * 32 + lane;
   const int er = m >> 3, ec0 = (warp >> 2) * 16 + (m & 7);     // row and first column (second M-tile: + 8)
-  const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((warp >> 2) * 32);
+  const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((warp >> 2) * 64);
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
@@ -153,8 +153,11 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
     tc_fence_after_sync();
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      float v[16];
-      tmem_ld16(trow + k * 16, v);
+      float v[16], v2[16];
+      tmem_ld16(trow + k * 32, v);
+      tmem_ld16(trow + k * 32 + 16, v2);
+#pragma unroll
+      for (int oc = 0; oc < 16; ++oc) v[oc] += v2[oc];
       const int c = ec0 + k * 8;
       const int gy = y0 - 1 + er, gx = x0 - 1 + c;
       const bool inside = gy >= 0 && gy < H && gx >= 0 && gx < W;
@@ -169,15 +172,18 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
     fence_proxy_async();
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) { tc_fence_after_sync(); issue_layer(sb + OFF_A2, sb + OFF_B3T, 64u); }
+    if (warp == 0) { tc_fence_after_sync(); issue_layer(sb + OFF_A2, sb + OFF_B3T, 128u); }
     // ---- layer-3 epilogue: bias, ReLU, 1x1 conv, sigmoid
     mbar_wait(bar, phase);
     phase ^= 1u;
     tc_fence_after_sync();
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      float v[16];
-      tmem_ld16(trow + 64 + k * 16, v);
+      float v[16], v2[16];
+      tmem_ld16(trow + 128 + k * 32, v);
+      tmem_ld16(trow + 128 + k * 32 + 16, v2);
+#pragma unroll
+      for (int oc = 0; oc < 8; ++oc) v[oc] += v2[oc];
       const int ox = ec0 + k * 8;
       const int gy = y0 + er, gx = x0 + ox;
       if (er < TH && ox < TW && gy < H && gx < W) {
@@ -192,7 +198,7 @@ vis_cnn_kernel(const float* __restrict__ entropy, const float* __restrict__ wts,
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace mvsf
