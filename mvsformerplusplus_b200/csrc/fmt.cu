@@ -7,6 +7,7 @@
 // summaries of the two cross layers depend only on the reference view and are computed once.
 #include "linear.cuh"
 #include "linear_tc.cuh"
+#include "umma.cuh"
 
 namespace mvsf {
 
@@ -157,120 +158,7 @@ linattn_apply_kernel(const float* __restrict__ q, int ldq, const float* __restri
   }
 }
 
-// pre[v][y][x][c] = lateral_nchw[v][c][y][x] + bilinear_up2(red)[v][y][x][c]   (F.interpolate bilinear, align_corners=False)
-template <int C>
-__global__ void __launch_bounds__(256)
-upsample_add_kernel(const float* __restrict__ red, const float* __restrict__ lat, float* __restrict__ pre, int h, int w) {
-  constexpr int RY = 8;                       // output rows per CTA (fewer, fatter CTAs: 35k instead of 276k at DTU stage 4)
-  __shared__ float tile[RY][C][33];
-  const int H = 2 * h, W = 2 * w;
-  const int v = blockIdx.z, yb = blockIdx.y * RY, x0 = blockIdx.x * 32;
-  const float* lv = lat + (size_t)v * C * H * W;
-  for (int i = threadIdx.x; i < RY * C * 32; i += 256) {   // NCHW lateral -> shared memory (coalesced along x)
-    int xx = i & 31, c = (i >> 5) % C, ry = i / (32 * C);
-    if (x0 + xx < W && yb + ry < H) tile[ry][c][xx] = __ldg(lv + ((size_t)c * H + yb + ry) * W + x0 + xx);
-  }
-  __syncthreads();
-  const float* rv = red + (size_t)v * h * w * C;
-  for (int i = threadIdx.x; i < RY * 32 * C; i += 256) {
-    int c = i % C, xx = (i / C) & 31, ry = i / (32 * C);
-    int x = x0 + xx, y = yb + ry;
-    if (x >= W || y >= H) continue;
-    // ATen area_pixel_compute_source_index(scale=0.5, align_corners=False): src = 0.5*(dst+0.5)-0.5, clamped at 0
-    float sy = fmaxf(0.5f * ((float)y + 0.5f) - 0.5f, 0.0f);
-    int y0 = (int)sy;
-    int y1 = y0 + ((y0 < h - 1) ? 1 : 0);
-    float ly1 = sy - (float)y0, ly0 = 1.0f - ly1;
-    float sx = fmaxf(0.5f * ((float)x + 0.5f) - 0.5f, 0.0f);
-    int xa = (int)sx;
-    int xb = xa + ((xa < w - 1) ? 1 : 0);
-    float lx1 = sx - (float)xa, lx0 = 1.0f - lx1;
-    float v00 = __ldg(rv + ((size_t)y0 * w + xa) * C + c), v01 = __ldg(rv + ((size_t)y0 * w + xb) * C + c);
-    float v10 = __ldg(rv + ((size_t)y1 * w + xa) * C + c), v11 = __ldg(rv + ((size_t)y1 * w + xb) * C + c);
-    float up = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
-    pre[(((size_t)v * H + y) * W + x) * C + c] = up + tile[ry][c][xx];
-  }
-}
-
-// smooth_k: Conv2d(C, C, 3, padding=1, bias=False), channels-last.  Same register tiling as the 3-D conv kernel.
-template <int C>
-struct Conv2Cfg {
-  static constexpr int CT = C < 16 ? C : 16;
-  static constexpr int NCG = C / CT;
-  static constexpr int WARPS_H = 4 / NCG;
-  static constexpr int TH = 4 * WARPS_H;
-  static constexpr int IH_T = TH + 2, IW_T = 34;
-};
-template <int C>
-__global__ void __launch_bounds__(128)
-conv2d_k3_kernel(const float* __restrict__ in, const float* __restrict__ wts, float* __restrict__ out, int H, int W) {
-  using Cfg = Conv2Cfg<C>;
-  constexpr int CT = Cfg::CT, NCG = Cfg::NCG, TH = Cfg::TH, IH_T = Cfg::IH_T, IW_T = Cfg::IW_T;
-  __shared__ __align__(16) float4 in_s[IH_T * IW_T];
-  __shared__ __align__(16) float wt_s[9 * 4 * C];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int cg = wid % NCG, hg = wid / NCG;
-  const int v = blockIdx.z, oh0 = blockIdx.y * TH, ow0 = blockIdx.x * 32;
-  const float* iv = in + (size_t)v * H * W * C;
-  float acc[4][CT];
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int c = 0; c < CT; ++c) acc[j][c] = 0.f;
-  for (int pc = 0; pc < C / 4; ++pc) {
-    __syncthreads();
-    for (int i = tid; i < IH_T * IW_T; i += 128) {
-      int iy = i / IW_T, ix = i - iy * IW_T;
-      int ih = oh0 - 1 + iy, iw = ow0 - 1 + ix;
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) t = ldg4(iv + ((size_t)ih * W + iw) * C + pc * 4);
-      in_s[i] = t;
-    }
-    for (int i = tid; i < 9 * 4 * C / 4; i += 128) {
-      int e = i * 4;
-      int tap = e / (4 * C), rem = e - tap * (4 * C);
-      int ci = rem / C, co = rem - ci * C;
-      *reinterpret_cast<float4*>(wt_s + e) = ldg4(wts + ((size_t)tap * C + pc * 4 + ci) * C + co);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        float4 a[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = in_s[(hg * 4 + j + kh) * IW_T + lane + kw];
-        const float* wp = wt_s + (size_t)((kh * 3 + kw) * 4) * C + cg * CT;
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-#pragma unroll
-          for (int q = 0; q < CT / 4; ++q) {
-            float4 w4 = *reinterpret_cast<const float4*>(wp + ci * C + q * 4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float x = (ci == 0) ? a[j].x : (ci == 1) ? a[j].y : (ci == 2) ? a[j].z : a[j].w;
-              acc[j][q * 4 + 0] = fmaf(x, w4.x, acc[j][q * 4 + 0]);
-              acc[j][q * 4 + 1] = fmaf(x, w4.y, acc[j][q * 4 + 1]);
-              acc[j][q * 4 + 2] = fmaf(x, w4.z, acc[j][q * 4 + 2]);
-              acc[j][q * 4 + 3] = fmaf(x, w4.w, acc[j][q * 4 + 3]);
-            }
-          }
-        }
-      }
-    }
-  }
-  const int ow = ow0 + lane;
-  if (ow >= W) return;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int oh = oh0 + hg * 4 + j;
-    if (oh >= H) continue;
-    float* o = out + (((size_t)v * H + oh) * W + ow) * C + cg * CT;
-#pragma unroll
-    for (int q = 0; q < CT / 4; ++q)
-      *reinterpret_cast<float4*>(o + q * 4) = make_float4(acc[j][q * 4], acc[j][q * 4 + 1], acc[j][q * 4 + 2], acc[j][q * 4 + 3]);
-  }
-}
+#include "fmt_smooth_tc.cuh"   // fused upsample + lateral add + 3x3 smooth conv on tcgen05
 
 struct FmtWs {
   __half *xn2, *att2, *hid2;   // fp16 hi|lo split activations: [M][128], [M][128], [M][512]
@@ -360,13 +248,8 @@ static int run_pathway_level(const float* prev, const float* lat, const float* d
   LinArgs a{};
   a.A = prev; a.lda = CIN; a.W = dr_w; a.C = red; a.ldc = COUT; a.M = V * h * w; a.N = COUT; a.K = CIN;
   if ((rc = launch_linear(a, LIN_BIAS, s))) return rc;
-  const int H = 2 * h, W = 2 * w;
-  MVSF_REQUIRE(H <= 65535 && V <= 65535, "fmt pathway: image too large");
-  upsample_add_kernel<COUT><<<dim3(cdiv(W, 32), cdiv(H, 8), V), 256, 0, s>>>(red, lat, pre, h, w);
-  MVSF_LAUNCH_CHECK("fmt_upsample_add");
-  conv2d_k3_kernel<COUT><<<dim3(cdiv(W, 32), cdiv(H, Conv2Cfg<COUT>::TH), V), 128, 0, s>>>(pre, sm_w, out, H, W);
-  MVSF_LAUNCH_CHECK("fmt_smooth");
-  return MVSF_OK;
+  (void)pre;
+  return launch_fmt_smooth_tc<COUT>(red, lat, sm_w, out, V, h, w, s);
 }
 
 }  // namespace mvsf

@@ -30,8 +30,8 @@ constexpr uint32_t PLANE = PR * PC * 16;        // 9792 B: one octet of channels
 constexpr uint32_t PITCH = PC * 16;
 constexpr int IN_R = 20, IN_C = 36;             // input region (3-pixel halo)
 // packed weights (floats): w1[9][16] b1[16] w2[16][9][16] b2[16] w3[16][9][8] b3[8] w4[8] b4[1]
-constexpr int OFF_W1 = 0, OFF_B1 = 144, OFF_W2 = 160, OFF_B2 = 160 + 2304, OFF_W3 = OFF_B2 + 16,
-              OFF_B3 = OFF_W3 + 1152, OFF_W4 = OFF_B3 + 8, OFF_B4 = OFF_W4 + 8, VIS_WTS = OFF_B4 + 1;
+constexpr int OFF_W2 = 160, OFF_B2 = 160 + 2304, OFF_W3 = OFF_B2 + 16,
+              OFF_B3 = OFF_W3 + 1152, OFF_W4 = OFF_B3 + 8, OFF_B4 = OFF_W4 + 8;
 // shared memory (bytes): planes a1 [hi o0 | hi o1 | lo o0 | lo o1], planes a2, weight tiles, input, small params, barrier
 constexpr uint32_t OFF_A1 = 0, OFF_A2 = 4 * PLANE, OFF_B2T = 8 * PLANE, BT_LAYER = 9 * 1024,      // [tap][2 kc][32 rows: w_hi | w_lo][8]
                    OFF_B3T = OFF_B2T + BT_LAYER, OFF_IN = OFF_B3T + BT_LAYER, OFF_PAR = OFF_IN + IN_R * IN_C * 4,
