@@ -191,10 +191,12 @@ static int launch_fmt_smooth_tc(const float* red, const float* lat, const float*
     MVSF_CUDA_OK(cudaGetDevice(&dev));
     MVSF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     MVSF_CUDA_OK(cudaFuncSetAttribute(fmt_smooth_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
-    MVSF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmt_smooth_tc_kernel<C>, 256, K::SMEM));
+    // resident CTAs per SM: registers (<= 80 x 256 threads -> 3), shared memory, tensor memory (512 columns per SM)
     uint32_t ncols = 32;
     while (ncols < K::TCOLS) ncols <<= 1;
-    if (per_sm > (int)(512 / ncols)) per_sm = 512 / ncols;   // tensor memory: 512 columns per SM
+    per_sm = 3;
+    if (per_sm > (int)(512 / ncols)) per_sm = 512 / ncols;
+    if (per_sm > (int)((220 * 1024) / K::SMEM)) per_sm = (int)((220 * 1024) / K::SMEM);
     if (per_sm < 1) per_sm = 1;
     configured = true;
   }
