@@ -16,7 +16,8 @@ def P(t):
 
 
 @pytest.mark.parametrize("M,N,K,gelu", [(128, 64, 64, 0), (300, 64, 64, 0), (1000, 256, 64, 1), (513, 64, 256, 0),
-                                         (27648, 192, 64, 0), (27648, 64, 256, 1), (130, 16, 128, 0)])
+                                         (27648, 192, 64, 0), (27648, 64, 256, 1), (130, 16, 128, 0),
+                                         (110592, 64, 64, 0), (110592, 256, 64, 1)])   # 6 tiles per persistent CTA
 def test_linear_tc_vs_fp64(M, N, K, gelu):
     from mvsformerplusplus_b200 import _lib
     L = _lib.lib()
