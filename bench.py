@@ -288,8 +288,8 @@ def run_ours(a, wl, rank, world, local_rank):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "ref_views_per_gpu_per_step": B, "parallelism": f"shard{world}",
                            "l2": "inputs_larger_than_l2 (531 MB feature pyramids per depth map)",
-                           "precision": "fp32-class parity mode: tcgen05 GEMMs / attention / 3-D convolutions on fp16 hi+lo split "
-                                        "operands (22-bit mantissa, fp32 accumulate), everything else fp32 SIMT",
+                           "precision": "fp32-class parity mode: tcgen05 GEMMs / attention / 3-D and 2-D convolutions on fp16 hi+lo "
+                                        "split operands (22-bit mantissa, fp32 accumulate), everything else fp32 SIMT",
                            "e2e_pipeline": "pinned host batch -> copy stream -> 2 device slots; upload of batch i+1 overlaps "
                                            "the kernels of batch i; depth+confidence read back every step"},
                 "e2e": {"value": maps * 1000.0 / ms_e2e, "unit": "depth-maps/s", "h2d_bytes_per_step": h2d,

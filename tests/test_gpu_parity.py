@@ -489,7 +489,7 @@ def test_identity_homography_property(dev, L):
 # ----------------------------------------------------------------------------------------------- tensor-core attention
 @pytest.mark.parametrize("N", [200, 1000, 4000, 27648])
 def test_attention_tensor_core_vs_fp64(dev, L, N):
-    """Product attention kernel (mma.sync, 3-term split-fp16) against an fp64 softmax(QK^T*scale)V evaluated with torch
+    """Product attention kernel (tcgen05, fp16 hi|lo split operands) against an fp64 softmax(QK^T*scale)V evaluated with torch
     on the GPU (test-side ground truth, chunked over queries).
     Inputs are deliberately harsher than LayerNorm-ed tokens (std 1.5 -> |score| up to ~14 in log2 units)."""
     g = torch.Generator().manual_seed(N)
