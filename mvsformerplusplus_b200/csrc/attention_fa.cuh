@@ -263,7 +263,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
         for (int e = 0; e < 32; ++e) pmax = fmaxf(pmax, __uint_as_float(sr[c][e]));
       volatile float* xj = xchg + (j & 1) * 512;
       xj[half * 128 + row] = pmax;
-      named_bar_sync(1 + w, 256);
+      if (w == 0) named_bar_sync_c<1>(256); else named_bar_sync_c<2>(256);
       const float mx = fmaxf(m, fmaxf(pmax, xj[(half ^ 1) * 128 + row]));
       const float corr = ex2f(m - mx);
       m = mx;

@@ -47,6 +47,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
 // named barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+// compile-time id: a run-time id makes ptxas reserve all 16 hardware barriers (and profilers that patch the kernel then
+// cannot launch it)
+template <int ID>
+__device__ __forceinline__ void named_bar_sync_c(int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
