@@ -94,19 +94,33 @@ def make_net(seed=7):
 
 # ======================================================================================================
 def cpu_reference_pass(wl, threads, seed=1234):
-    """One pass of the reference's algorithm on the host (oracle port with the reference's own ATen kernels:
-    F.grid_sample + SDPA, fp32).  Returns seconds."""
+    """One pass of the hot path on the host cores, fp32.  Returns (seconds, kind):
+    kind "reference" - the reference's OWN modules (models/FMT.py, models/cost_volume.py, models/module.py ... imported
+                       from oracle/_ref, the build-time copy made by oracle/build_ref.py) through the glue of
+                       DINOv2_mvsformer_model.py:117-179, with this repo's seeded weights loaded by state dict;
+    kind "port"      - the oracle port with the reference's ATen kernels (F.grid_sample + SDPA), when oracle/_ref is absent."""
     import torch
+    from mvsformerplusplus_b200 import synth
     from mvsformerplusplus_b200.config import default_args
-    from oracle import hotpath as O  # bench.py's cpu_baseline leg is one of the three allowed oracle users
-    O.USE_ATEN_KERNELS = True
     torch.set_num_threads(threads)
-    net, sd = make_net()
     feats, proj, dv = make_inputs(wl, seed)
+    from oracle import ref_hotpath as RH  # bench.py's CPU legs are allowed oracle users (checker / baseline only)
+    if RH.reference_root() is not None:
+        R = RH.import_reference()
+        args = default_args()
+        torch.manual_seed(0)
+        model = RH.RefHotPath(R, args).eval()
+        synth.randomize_state_dict(model, seed=7)   # same seeded weights as make_net()
+        t0 = time.perf_counter()
+        RH.reference_hotpath(R, model, args, feats, proj, dv, TMP, capture=False)
+        return time.perf_counter() - t0, "reference"
+    from oracle import hotpath as O
+    O.USE_ATEN_KERNELS = True
+    net, sd = make_net()
     t0 = time.perf_counter()
     with torch.no_grad():
         O.hotpath_forward(feats, proj, dv, sd, default_args(), tmp=TMP)
-    return time.perf_counter() - t0
+    return time.perf_counter() - t0, "port"
 
 
 def cpu_threads():
@@ -119,19 +133,21 @@ def run_reference_arm(a, wl, rank, world):
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
     threads = cpu_threads()
-    times = []
+    times, kind = [], "port"
     for i in range(a.warmup + a.steps):
-        dt = cpu_reference_pass(wl, threads)
+        dt, kind = cpu_reference_pass(wl, threads)
         if i >= a.warmup:
             times.append(dt)
     ms = 1000.0 * sum(times) / len(times)
     val = 1000.0 / ms
-    sample = "1 full depth map (whole workload, fp32, oracle port calling the reference's ATen kernels) per step"
+    what = ("the reference's own modules (oracle/_ref copy of models/), glue of DINOv2_mvsformer_model.py:117-179" if kind == "reference"
+            else "oracle port calling the reference's ATen kernels")
+    sample = f"1 full depth map (whole workload, fp32, {what}) per step"
     line = {"impl": "reference", "metric": "depth-maps/sec (hot path: FMT + 4-stage cascade)", "value": val, "unit": "depth-maps/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "host_threads": threads},
-            "cpu_baseline": {"value": val, "unit": "depth-maps/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "depth-maps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "depth-maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -278,10 +294,12 @@ def run_ours(a, wl, rank, world, local_rank):
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             threads = cpu_threads()
-            dt = cpu_reference_pass(wl, threads)
-            cpu = {"value": 1.0 / dt, "unit": "depth-maps/s", "cores": threads, "kind": "port",
-                   "sample": "1 full depth map of the same workload (cold, fp32, oracle port calling the reference's ATen "
-                             "kernels F.grid_sample + SDPA)"}
+            cpu_reference_pass(wl, threads)             # warm-up pass (allocator, thread pools), like the reference arm
+            dt, kind = cpu_reference_pass(wl, threads)
+            cpu = {"value": 1.0 / dt, "unit": "depth-maps/s", "cores": threads, "kind": kind,
+                   "sample": "1 full depth map of the same workload (second of two passes, fp32; " +
+                             ("the reference's own modules from oracle/_ref)" if kind == "reference" else
+                              "oracle port calling the reference's ATen kernels F.grid_sample + SDPA)")}
         maps = B * world
         line = {"metric": "depth-maps/sec (hot path: FMT + 4-stage cascade)", "value": maps * 1000.0 / ms_step,
                 "unit": "depth-maps/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,

@@ -55,6 +55,10 @@ int mvsf_nhwc_to_nchw(const float* src, float* dst, int N, int C, int HW, mvsf_s
  * homs [(V-1)][12]: rot row-major (9) then trans (3) of  P_src * P_ref^-1.   kinv_ref [9] row-major. */
 int mvsf_compose_geometry(const float* proj, int V, float* homs, float* kinv_ref, mvsf_stream_t stream);
 
+/* ---- W2 prep for the warp seam: models/warping.py:80-82  proj = src_proj @ inverse(ref_proj) on composed 4x4
+ * projections [B][4][4] (fp64 on device) -> homs [B][12] = rot row-major (9) then trans (3). */
+int mvsf_homography_from_proj(const float* src_proj, const float* ref_proj, int B, float* homs, mvsf_stream_t stream);
+
 /* ---- F5: models/module.py:692-704 init_inverse_range.  depth_values [Dn] -> out [D][H][W] */
 int mvsf_init_inverse_range(const float* depth_values, int Dn, float* out, int D, int H, int W, mvsf_stream_t stream);
 /* ---- F6: models/module.py:707-724 schedule_inverse_range (shift=False).
@@ -62,8 +66,13 @@ int mvsf_init_inverse_range(const float* depth_values, int Dn, float* out, int D
 int mvsf_schedule_inverse_range(const float* prev_depth, const float* prev_hypo, int Dp, float split_itv, float* out,
                                 int D, int H, int W, mvsf_stream_t stream);
 /* ---- F7: models/position_encoding.py:138-161 get_position_3d(normalize=True).
- * stats [6] = {width_min,width_max,height_min,height_max,depth_min,depth_max}; when compute_minmax != 0 the
- * first four are computed from this call's positions (stage 1) else reused.  pos [3][D][H][W]. */
+ * stats [6] = {width_min,width_max,height_min,height_max,depth_min,depth_max}.  pos [3][D][H][W].
+ * compute_minmax: 1 = extents from this call's positions + depth range of depth_values, then normalise (B == 1);
+ *                 0 = reuse the extents, refresh the depth range, normalise.
+ * Batched callers (the reference reduces extents and depth_values.min()/max() over the whole batch,
+ * position_encoding.py:152-157, DINOv2_mvsformer_model.py:156):  2 = reset + accumulate this sample's extents,
+ * 3 = accumulate, 4 = finalise (decode extents, depth range over depth_values[0..Dn), Dn = B * numdepth),
+ * 5 = normalise only.  Unused pointers may be NULL in modes 2-5. */
 int mvsf_position3d(const float* kinv_ref, const float* depth, const float* depth_values, int Dn, float* stats,
                     int compute_minmax, float* pos, int D, int H, int W, mvsf_stream_t stream);
 

@@ -16,6 +16,7 @@ SIGNATURES = {
     "mvsf_nchw_to_nhwc": ([P, P, I, I, I, P], I),
     "mvsf_nhwc_to_nchw": ([P, P, I, I, I, P], I),
     "mvsf_compose_geometry": ([P, I, P, P, P], I),
+    "mvsf_homography_from_proj": ([P, P, I, P, P], I),
     "mvsf_init_inverse_range": ([P, I, P, I, I, I, P], I),
     "mvsf_schedule_inverse_range": ([P, P, I, F, P, I, I, I, P], I),
     "mvsf_position3d": ([P, P, P, I, P, I, P, I, I, I, P], I),

@@ -71,6 +71,20 @@ def validate_args(args):
                 raise NotImplementedError(f"Unkown Attention Type {tc.get('attention_type')}")
             if not (tc.get("position_encoding", True) and tc.get("use_pe_proj", True)):
                 raise NotImplementedError("transformer regulariser: pe_proj path only (shipped config)")
+            # options the CUDA path hard-codes (FlashAttnBlock kwargs, models/module.py:536-582): a non-default value
+            # would load with strict=True and silently compute different arithmetic, so reject it at construction
+            if not tc.get("post_norm", True):
+                raise NotImplementedError("transformer regulariser: post_norm=False is not implemented (shipped: post-norm)")
+            if tc.get("qkv_bias", False):
+                raise NotImplementedError("transformer regulariser: qkv_bias=True is not implemented (shipped: no qkv bias)")
+            if not tc.get("proj_bias", True) or not tc.get("ffn_bias", True):
+                raise NotImplementedError("transformer regulariser: proj_bias / ffn_bias must be True (shipped config)")
+            if tuple(tc.get("down_rate", (2, 4, 4))) != (2, 4, 4) or tc.get("mid_channel", 64) != 64 or \
+                    tc.get("num_heads", 4) != 4 or tc.get("mlp_ratio", 4) != 4:
+                raise NotImplementedError("transformer regulariser: only the shipped geometry (down_rate (2,4,4), "
+                                          "mid_channel 64, 4 heads, mlp_ratio 4) is implemented")
+            if stage_list(args["base_ch"], s) != 8 or tc.get("base_channel", 8) != 8:
+                raise NotImplementedError("transformer regulariser: base channel must be 8 (shipped config)")
         elif t != "Normal":
             raise NotImplementedError(f"cost_reg_type {t}")
     return args

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -21,13 +22,31 @@ int fail(int code, const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 
+int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+  return d;
+}
+int device_sm_count(int dev) {
+  static std::atomic<int> cache[64];
+  const int slot = dev & 63;
+  int v = cache[slot].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[slot].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 // Opt-in per-kernel device timers (CUDA events on the launching stream around selected launches): bench.py needs the
 // duration of single kernels that are launched from inside a multi-kernel entry point.
 struct KTimer { std::string name; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev; };
-static bool g_ktimer_on = false;
+static std::atomic<bool> g_ktimer_on{false};
 static std::vector<KTimer> g_ktimers;
-bool ktimer_enabled() { return g_ktimer_on; }
+static std::mutex g_ktimer_mu;   // the timers are process-global; calls may come from several host threads
+bool ktimer_enabled() { return g_ktimer_on.load(std::memory_order_relaxed); }
 cudaEvent_t ktimer_begin(const char* name, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_ktimer_mu);
   KTimer* t = nullptr;
   for (auto& k : g_ktimers)
     if (k.name == name) t = &k;
@@ -87,7 +106,7 @@ long long mvsf_launch_count(int reset) {
 }
 
 int mvsf_ktimer_enable(int on) {
-  mvsf::g_ktimer_on = on != 0;
+  mvsf::g_ktimer_on.store(on != 0);
   return MVSF_OK;
 }
 /* device milliseconds and launches recorded under `name` since the last read (synchronises the device, then resets) */
@@ -95,6 +114,7 @@ int mvsf_ktimer_read(const char* name, double* ms, long long* launches) {
   MVSF_REQUIRE(name && ms && launches, "ktimer_read: null pointer");
   *ms = 0.0;
   *launches = 0;
+  std::lock_guard<std::mutex> lk(mvsf::g_ktimer_mu);
   for (auto& k : mvsf::g_ktimers) {
     if (k.name != name) continue;
     for (auto& pr : k.ev) {

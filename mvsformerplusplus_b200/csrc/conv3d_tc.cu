@@ -650,10 +650,11 @@ static int launch_one(const ConvTcArgs& a, int NS, size_t smem, int OD, int OH, 
                       int num_sms, cudaStream_t s) {
   using G = c3::Geo<MODE, NT>;
   auto kern = conv3d_tc_kernel<MODE, NT, OUT>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int dev = current_device();
+  if (once.need(dev)) {
     MVSF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    once.done(dev);
   }
   c3::Maps maps;
   int rc;
@@ -679,12 +680,7 @@ static int launch_mode(const ConvTcArgs& a, cudaStream_t s) {
   if (MODE == CONV_S1) { OD = a.ID; OH = a.IH; OW = a.IW; cells_h = OH; cells_w = OW; }
   else if (MODE == CONV_S2) { OD = (a.ID - 1) / a.SD + 1; OH = (a.IH - 1) / 2 + 1; OW = (a.IW - 1) / 2 + 1; cells_h = OH; cells_w = OW; }
   else { OD = a.ID * a.SD; OH = a.IH * 2; OW = a.IW * 2; cells_h = a.IH; cells_w = a.IW; }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    MVSF_CUDA_OK(cudaGetDevice(&dev));
-    MVSF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = device_sm_count(current_device());
   const int NPAD = c3::npad(a.COUT);
   const uint32_t b_bytes = c3::slab_bytes(a.COUT);
   const int ncls = MODE == DECONV_S2 ? 4 : 1;
@@ -721,10 +717,11 @@ template <int MODE, int NT>
 static int launch_col_one(const ConvTcArgs& a, int NS, int wres, size_t smem, int OH, int OW, int DC, int num_sms, cudaStream_t s) {
   using G = c3::Geo<MODE, NT>;
   auto kern = conv3d_col_kernel<MODE, NT>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int dev = current_device();
+  if (once.need(dev)) {
     MVSF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    once.done(dev);
   }
   c3::Maps maps;
   int rc;
@@ -748,12 +745,7 @@ template <int MODE>
 static int launch_col(const ConvTcArgs& a, cudaStream_t s) {
   const int D = a.ID;
   const int OH = MODE == CONV_S1 ? a.IH : (a.IH - 1) / 2 + 1, OW = MODE == CONV_S1 ? a.IW : (a.IW - 1) / 2 + 1;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    MVSF_CUDA_OK(cudaGetDevice(&dev));
-    MVSF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = device_sm_count(current_device());
   const int NPAD = c3::npad(a.COUT);
   const int ngroups = a.CIN / 8 / a.KG;
   const size_t slab = (size_t)NPAD * 1728;

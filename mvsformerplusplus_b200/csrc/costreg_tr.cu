@@ -140,10 +140,11 @@ static int run_attention(const float* qkv, float* o, __half* o2, __half* tiled, 
   const int ntiles = cdiv(N, 128);
   qkv_tile_kernel<<<cdiv((long long)ntiles * 128 * 24, 256), 256, 0, s>>>(qkv, tiled, N, ntiles, scale_log2e);
   MVSF_LAUNCH_CHECK("qkv_tile");
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  const int dev = current_device();
+  if (once.need(dev)) {
     MVSF_CUDA_OK(cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa6::SMEM));
-    configured = true;
+    once.done(dev);
   }
   cudaEvent_t kt = ktimer_enabled() ? ktimer_begin("attention_tc", s) : nullptr;
   attention_fa_kernel<<<dim3(cdiv(ntiles, 2), 4), fa6::THREADS, fa6::SMEM, s>>>(tiled, o, o2, N, ntiles);

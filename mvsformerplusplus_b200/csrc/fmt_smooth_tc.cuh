@@ -184,12 +184,11 @@ template <int C>
 static int launch_fmt_smooth_tc(const float* red, const float* lat, const float* wts, float* out, int V, int h, int w,
                                 cudaStream_t s) {
   using K = sm2::Cfg<C>;
-  static bool configured = false;
-  static int num_sms = 148, per_sm = 1;
-  if (!configured) {
-    int dev = 0;
-    MVSF_CUDA_OK(cudaGetDevice(&dev));
-    MVSF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  static DeviceOnce once;
+  static int per_sm = 1;   // a function of the kernel's compile-time footprint only
+  const int dev = current_device();
+  const int num_sms = device_sm_count(dev);
+  if (once.need(dev)) {
     MVSF_CUDA_OK(cudaFuncSetAttribute(fmt_smooth_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
     // resident CTAs per SM: registers (<= 80 x 256 threads -> 3), shared memory, tensor memory (512 columns per SM)
     uint32_t ncols = 32;
@@ -198,7 +197,7 @@ static int launch_fmt_smooth_tc(const float* red, const float* lat, const float*
     if (per_sm > (int)(512 / ncols)) per_sm = 512 / ncols;
     if (per_sm > (int)((220 * 1024) / K::SMEM)) per_sm = (int)((220 * 1024) / K::SMEM);
     if (per_sm < 1) per_sm = 1;
-    configured = true;
+    once.done(dev);
   }
   const int H = 2 * h, W = 2 * w;
   const int tiles_x = cdiv(W, 32), tiles_y = cdiv(H, 16);

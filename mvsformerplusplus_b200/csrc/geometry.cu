@@ -91,6 +91,26 @@ __global__ void compose_geometry_kernel(const float* __restrict__ proj, int V, f
   }
 }
 
+// models/warping.py:80-82 for already composed 4x4 projections (the warp seam's own arguments):
+// hom = rot (9, row-major) | trans (3) of src_proj @ inverse(ref_proj), one thread per batch item
+__global__ void homography_from_proj_kernel(const float* __restrict__ src_proj, const float* __restrict__ ref_proj, int B,
+                                            float* __restrict__ homs) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double Pr[16], Pi[16], Ps[16];
+  for (int i = 0; i < 16; ++i) { Pr[i] = (double)ref_proj[b * 16 + i]; Ps[i] = (double)src_proj[b * 16 + i]; }
+  const bool ok = invert4(Pr, Pi);
+  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+  float* h = homs + (size_t)b * 12;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) {
+      double s = 0.0;
+      for (int k = 0; k < 4; ++k) s += Ps[r * 4 + k] * Pi[k * 4 + c];
+      if (!ok) s = nanv;
+      if (c < 3) h[r * 3 + c] = (float)s; else h[9 + r] = (float)s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // F5: models/module.py:692-704
 // ------------------------------------------------------------------------------------------------
@@ -324,6 +344,13 @@ int mvsf_compose_geometry(const float* proj, int V, float* homs, float* kinv_ref
   return MVSF_OK;
 }
 
+int mvsf_homography_from_proj(const float* src_proj, const float* ref_proj, int B, float* homs, mvsf_stream_t stream) {
+  MVSF_REQUIRE(src_proj && ref_proj && homs && B > 0, "homography_from_proj: bad arguments");
+  homography_from_proj_kernel<<<cdiv(B, 32), 32, 0, (cudaStream_t)stream>>>(src_proj, ref_proj, B, homs);
+  MVSF_LAUNCH_CHECK("homography_from_proj");
+  return MVSF_OK;
+}
+
 int mvsf_init_inverse_range(const float* depth_values, int Dn, float* out, int D, int H, int W, mvsf_stream_t stream) {
   MVSF_REQUIRE(depth_values && out && Dn >= 2 && D >= 2 && H > 0 && W > 0, "init_inverse_range: bad arguments");
   int HW = H * W;
@@ -345,22 +372,36 @@ int mvsf_schedule_inverse_range(const float* prev_depth, const float* prev_hypo,
 
 int mvsf_position3d(const float* kinv_ref, const float* depth, const float* depth_values, int Dn, float* stats,
                     int compute_minmax, float* pos, int D, int H, int W, mvsf_stream_t stream) {
-  MVSF_REQUIRE(kinv_ref && depth && depth_values && stats && pos && Dn >= 1 && D >= 1 && H > 0 && W > 0,
-               "position3d: bad arguments");
+  // compute_minmax: 1 = extents of this sample + depth range, then normalise (B == 1, first stage that uses the PE)
+  //                 0 = reuse the decoded extents in `stats`, refresh the depth range from depth_values, normalise
+  //   batched callers (the reference reduces the extents and depth_values.min()/max() over the whole batch,
+  //   position_encoding.py:152-157, DINOv2_mvsformer_model.py:156): 2 = reset + accumulate extents, 3 = accumulate,
+  //   4 = decode extents + depth range of depth_values[0..Dn) (pass the whole [B,Dn] block), 5 = normalise only
+  const int mode = compute_minmax;
+  MVSF_REQUIRE(mode >= 0 && mode <= 5 && stats && D >= 1 && H > 0 && W > 0, "position3d: bad arguments");
+  MVSF_REQUIRE(mode == 4 || (kinv_ref && depth), "position3d: null kinv / depth");
+  MVSF_REQUIRE((mode != 0 && mode != 1 && mode != 4) || (depth_values && Dn >= 1), "position3d: null depth_values");
+  MVSF_REQUIRE((mode != 0 && mode != 1 && mode != 5) || pos, "position3d: null output");
   cudaStream_t s = (cudaStream_t)stream;
-  if (compute_minmax) {
+  if (mode == 1 || mode == 2) {
     pos3d_init_kernel<<<1, 1, 0, s>>>(reinterpret_cast<unsigned*>(stats));
     MVSF_LAUNCH_CHECK("pos3d_init");
+  }
+  if (mode == 1 || mode == 2 || mode == 3) {
     size_t total = (size_t)D * H * W;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     pos3d_minmax_kernel<<<blocks, 256, 0, s>>>(kinv_ref, depth, reinterpret_cast<unsigned*>(stats), D, H, W);
     MVSF_LAUNCH_CHECK("pos3d_minmax");
   }
-  pos3d_finalize_kernel<<<1, 32, 0, s>>>(stats, depth_values, Dn, compute_minmax);
-  MVSF_LAUNCH_CHECK("pos3d_finalize");
-  pos3d_normalize_kernel<<<cdiv(H * W, 256), 256, 0, s>>>(kinv_ref, depth, stats, pos, D, H, W);
-  MVSF_LAUNCH_CHECK("pos3d_normalize");
+  if (mode == 0 || mode == 1 || mode == 4) {
+    pos3d_finalize_kernel<<<1, 32, 0, s>>>(stats, depth_values, Dn, mode != 0);
+    MVSF_LAUNCH_CHECK("pos3d_finalize");
+  }
+  if (mode == 0 || mode == 1 || mode == 5) {
+    pos3d_normalize_kernel<<<cdiv(H * W, 256), 256, 0, s>>>(kinv_ref, depth, stats, pos, D, H, W);
+    MVSF_LAUNCH_CHECK("pos3d_normalize");
+  }
   return MVSF_OK;
 }
 

@@ -264,12 +264,10 @@ int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
   if (epi == LIN_RES || epi == LIN_RES_LN) MVSF_REQUIRE(a.res && a.gamma, "linear_tc: residual epilogue needs res and gamma");
   const size_t smem = tc_smem_bytes(a.N, a.K);
   MVSF_REQUIRE(smem <= 227 * 1024, "linear_tc: N*K too large for resident weights (%zu bytes of shared memory)", smem);
-  static bool configured = false;
-  static int num_sms = 148;
-  if (!configured) {
-    int dev = 0;
-    MVSF_CUDA_OK(cudaGetDevice(&dev));
-    MVSF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  static DeviceOnce once;
+  const int dev = current_device();
+  const int num_sms = device_sm_count(dev);
+  if (once.need(dev)) {
     const int maxs = 227 * 1024;
     MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
@@ -277,7 +275,7 @@ int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
     MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_RES_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
     MVSF_CUDA_OK(cudaFuncSetAttribute(linear_tc_kernel<LIN_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
-    configured = true;
+    once.done(dev);
   }
   const int ntiles = cdiv(a.M, TC_BM);
   dim3 grid(ntiles < num_sms ? ntiles : num_sms);  // persistent: one CTA per SM, tiles strided by gridDim.x

@@ -208,14 +208,12 @@ using namespace mvsf;
 extern "C" int mvsf_vis_cnn(const float* entropy, const float* wts, float* vis, int N, int H, int W,
                             mvsf_stream_t stream) {
   MVSF_REQUIRE(entropy && wts && vis && N > 0 && N <= 65535 && H > 0 && W > 0, "vis_cnn: bad arguments");
-  static bool configured = false;
-  static int num_sms = 148;
-  if (!configured) {
-    int dev = 0;
-    MVSF_CUDA_OK(cudaGetDevice(&dev));
-    MVSF_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  static DeviceOnce once;
+  const int dev = current_device();
+  const int num_sms = device_sm_count(dev);
+  if (once.need(dev)) {
     MVSF_CUDA_OK(cudaFuncSetAttribute(vis_cnn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vc::SMEM));
-    configured = true;
+    once.done(dev);
   }
   const int tiles_x = cdiv(W, vc::TW), tiles_y = cdiv(H, vc::TH);
   const long long ntiles = (long long)tiles_x * tiles_y * N;

@@ -83,6 +83,34 @@ def pack_unet_tc(kind, flat):
     return out
 
 
+@torch.no_grad()
+def homo_warping_3D_with_mask(src_fea, src_proj, ref_proj, depth_values):
+    """Drop-in for the reference's finest seam, models/warping.py:69-109 (called at cost_volume.py:72):
+    src_fea [B,C,H,W], src_proj / ref_proj [B,4,4] (already composed K@E), depth_values [B,D,H,W] or [B,D]
+    -> (warped_src_fea [B,C,D,H,W] fp32, mask [B,D,H,W] bool; True where the sample falls outside the source image or
+    behind the camera).  The hot path never materialises this volume (the warp is fused with the correlation);
+    this standalone op exists for seam-level parity and for callers of the reference function."""
+    _require_cuda(src_fea, "homo_warping_3D_with_mask(src_fea)")
+    B, C, H, W = src_fea.shape
+    D = depth_values.shape[1]
+    dev = src_fea.device
+    L = _lib.lib()
+    st = _stream()
+    depth_values = _f32c(depth_values.to(dev))
+    if depth_values.dim() == 2:  # warping.py:73-74
+        depth_values = depth_values.view(B, D, 1, 1).expand(B, D, H, W).contiguous()
+    sp, rp = _f32c(src_proj.to(dev)), _f32c(ref_proj.to(dev))
+    homs = torch.empty((B, 12), device=dev, dtype=torch.float32)
+    _lib.check(L.mvsf_homography_from_proj(_ptr(sp), _ptr(rp), B, _ptr(homs), st), "homography_from_proj")
+    src = to_nhwc(src_fea)
+    warped = torch.empty((B, C, D, H, W), device=dev, dtype=torch.float32)
+    mask = torch.empty((B, D, H, W), device=dev, dtype=torch.uint8)
+    for b in range(B):
+        _lib.check(L.mvsf_homo_warp(_ptr(src[b]), _ptr(homs[b]), _ptr(depth_values[b]), _ptr(warped[b]), _ptr(mask[b]),
+                                    C, D, H, W, st), "homo_warp")
+    return warped, mask.bool()
+
+
 class _PackedMixin:
     """Packs the module's parameters for the CUDA library on first use / after load_state_dict."""
 
@@ -116,9 +144,18 @@ class StageNet(_PackedMixin, nn.Module):
         bag = build_stage(args, ndepth, stage_idx)
         self.vis = bag.vis
         self.cost_reg = bag.cost_reg
+        # per-view group correlations spilled between the two cost-volume passes; above this many bytes the stage
+        # recomputes the gather in pass B instead (no spill buffer), so large inputs degrade instead of running out of memory
+        self.corr_spill_budget_bytes = int(args.get("corr_spill_budget_bytes", 8 << 30))
         self._init_packing()
 
     # ---- packing
+    def repack(self):
+        """Drop the packed (BN-folded, fp16-split) weight blobs; they are rebuilt on the next forward.  The cache is
+        invalidated automatically by load_state_dict() and .to()/.cuda(); call this after in-place parameter edits
+        (param.data.copy_, optimiser steps)."""
+        self._packed = None
+
     def _pack(self, device):
         if self._packed is not None and self._packed["device"] == device:
             return self._packed
@@ -165,7 +202,8 @@ class StageNet(_PackedMixin, nn.Module):
         entropy = torch.empty((V - 1, H, W), **f32)
         vis = torch.empty((V - 1, H, W), **f32)
         volume = torch.empty((D, H, W, G), **f32)
-        if G == 8:
+        spill_bytes = 4 * (V - 1) * D * H * W * G
+        if G == 8 and spill_bytes <= self.corr_spill_budget_bytes:
             # pass A also stores the per-view group correlations; the view aggregation then streams them (no second gather)
             corr = torch.empty((V - 1, D, H, W, G), **f32)
             _lib.check(L.mvsf_warp_corr_entropy_store(_ptr(feat_nhwc), _ptr(homs), _ptr(depth_values), _ptr(entropy),
@@ -353,7 +391,8 @@ def cascade_forward(fmt_module, fusions, args, features, proj_matrices, depth_va
     depth_values = _f32c(depth_values.to(dev))
     Dn = depth_values.shape[1]
     prob_maps = torch.empty((B, Hf, Wf), **f32)
-    stats = torch.zeros((B, 8), **f32)
+    stats = torch.zeros(8, **f32)   # x/y extents of the 3-D positions + depth range, shared by the whole batch
+    have_extents = False            # the reference computes them on the first stage that builds the PE and reuses them
     outputs, so = {}, None
     for s in range(len(ndepths)):
         pm = _f32c(proj_matrices[f"stage{s + 1}"].to(dev))
@@ -372,13 +411,23 @@ def cascade_forward(fmt_module, fusions, args, features, proj_matrices, depth_va
                                                          D, H, W, st), "schedule_inverse_range")
         p3d = None
         if args["cost_reg_type"][s] != "Normal" and args.get("use_pe3d", False):
+            # position_encoding.py:138-161: extents (first PE stage only) and depth_values.min()/max() are reductions
+            # over the WHOLE batch (DINOv2_mvsformer_model.py:152-160)
             p3d = torch.empty((B, 3, D, H, W), **f32)
-            kinv = torch.empty(9, **f32)
+            kinvs = torch.empty((B, 9), **f32)
             homs = torch.empty((V - 1) * 12, **f32)
             for b in range(B):
-                _lib.check(L.mvsf_compose_geometry(_ptr(pm[b]), V, _ptr(homs), _ptr(kinv), st), "compose_geometry")
-                _lib.check(L.mvsf_position3d(_ptr(kinv), _ptr(ds[b]), _ptr(depth_values[b]), Dn, _ptr(stats[b]),
-                                             1 if s == 0 else 0, _ptr(p3d[b]), D, H, W, st), "position3d")
+                _lib.check(L.mvsf_compose_geometry(_ptr(pm[b]), V, _ptr(homs), _ptr(kinvs[b]), st), "compose_geometry")
+                if not have_extents:
+                    _lib.check(L.mvsf_position3d(_ptr(kinvs[b]), _ptr(ds[b]), None, 0, _ptr(stats), 2 if b == 0 else 3,
+                                                 None, D, H, W, st), "position3d(extents)")
+            if not have_extents:
+                _lib.check(L.mvsf_position3d(None, None, _ptr(depth_values), B * Dn, _ptr(stats), 4, None, D, H, W, st),
+                           "position3d(finalize)")
+                have_extents = True
+            for b in range(B):
+                _lib.check(L.mvsf_position3d(_ptr(kinvs[b]), _ptr(ds[b]), None, 0, _ptr(stats), 5, _ptr(p3d[b]),
+                                             D, H, W, st), "position3d(normalise)")
         so = fusions[s].forward(f, pm, ds, tmp=tmp[s], position3d=p3d, keep_intermediates=keep_intermediates)
         outputs[f"stage{s + 1}"] = so
         conf = so["photometric_confidence"]

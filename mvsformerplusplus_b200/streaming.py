@@ -13,7 +13,8 @@ class PrefetchingRunner:
         self.net = net
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.slots = [dict(bufs=None, ready=torch.cuda.Event(), free=torch.cuda.Event(), tag=None) for _ in range(slots)]
+        self.slots = [dict(bufs=None, ready=torch.cuda.Event(), free=torch.cuda.Event(), tag=None, batch=None)
+                      for _ in range(slots)]
         self._next = 0
 
     # a batch is (features: dict[str, Tensor], proj_matrices: dict[str, Tensor], depth_values: Tensor), pinned host tensors
@@ -31,13 +32,19 @@ class PrefetchingRunner:
     def _upload(self, slot, batch):
         host = self._flat(batch)
         if slot["bufs"] is None or any(b.shape != h.shape or b.stride() != h.stride() for b, h in zip(slot["bufs"], host)):
+            # (re)allocation comes from the compute stream's allocator pool: the block may have just been freed by kernels
+            # that are still queued on the compute stream, so the copy stream must not write it before they have run
             slot["bufs"] = [torch.empty_strided(h.shape, h.stride(), dtype=h.dtype, device=self.device) for h in host]
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            for b in slot["bufs"]:
+                b.record_stream(self.copy_stream)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(slot["free"])     # the kernels that read this slot have finished
             for b, h in zip(slot["bufs"], host):
                 b.copy_(h, non_blocking=True)
             slot["ready"].record(self.copy_stream)
-        slot["tag"] = id(batch)
+        # identity of the prefetched batch: a strong reference (id() alone can be reused by Python after the batch dies)
+        slot["tag"], slot["batch"] = id(batch), batch
 
     def bytes_per_batch(self, batch):
         return sum(t.numel() * t.element_size() for t in self._flat(batch))
@@ -46,18 +53,18 @@ class PrefetchingRunner:
     def run(self, batch, next_batch=None, tmp=(5.0, 5.0, 5.0, 1.0)):
         """Runs the hot path on `batch` (uploaded now unless a previous call prefetched it) and starts the upload of
         `next_batch` so that it overlaps this call's kernels.  Returns the reference's output dict (device tensors)."""
-        cur = next((s for s in self.slots if s["tag"] == id(batch)), None)
+        cur = next((s for s in self.slots if s["batch"] is batch), None)
         if cur is None:
             cur = self.slots[self._next]
             self._next = (self._next + 1) % len(self.slots)
             self._upload(cur, batch)
         compute = torch.cuda.current_stream(self.device)
         compute.wait_event(cur["ready"])
-        if next_batch is not None and not any(s["tag"] == id(next_batch) for s in self.slots if s is not cur):
+        if next_batch is not None and not any(s["batch"] is next_batch for s in self.slots if s is not cur):
             nxt = next(s for s in self.slots if s is not cur)
             self._upload(nxt, next_batch)
         f, p, d = self._unflat(batch, cur["bufs"])
         out = self.net.forward_features(f, p, d, tmp)
         cur["free"].record(compute)
-        cur["tag"] = None                                  # consumed: the same host batch is uploaded again next time
+        cur["tag"] = cur["batch"] = None                   # consumed: the same host batch is uploaded again next time
         return out

@@ -38,3 +38,15 @@ def max_abs(a, b):
 
 def rel_linf(a, b):
     return float(((a.double() - b.double()).abs() / b.double().abs().clamp_min(1e-12)).max())
+
+
+# ---- parity report shared by the GPU test modules (written to gpurun_out/parity_report.json as tests run)
+REPORT = {}
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rec(name, **kw):
+    REPORT[name] = {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in kw.items()}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)

@@ -1,0 +1,88 @@
+"""Full-size parity: the CUDA hot path against the CPU oracle at BASELINE.json configs[1] (DTU test config: V=5,
+numdepth 192, 1152x1536, 27 648 regulariser tokens) and configs[3] (Tanks&Temples intermediate: V=10, numdepth 256,
+1088x1920 -> 32 640 tokens, odd attention tile count, 9 source views), on the same seeded synthetic inputs bench.py
+times (white-noise feature pyramids, look-at camera ring, seeded weights with randomised BatchNorm statistics).
+
+Two comparisons per config, both at the north-star tolerances (1e-4 absolute on per-pixel probability, 1e-3 relative
+L-inf on depth; models/networks/DINOv2_mvsformer_model.py:117-179):
+  * the free-running cascade (every stage consumes OUR previous stage), final refined depth + averaged confidence
+  * every stage teacher-forced on the ORACLE's stage inputs (FMT features, hypotheses, 3-D positions): per-stage
+    prob_volume / depth / confidence plus the intermediates (entropy, visibility weight, aggregated volume, logits)
+The oracle needs ~10-40 s of host time per config on the GPU box."""
+import os
+
+import pytest
+import torch
+
+from tests.common import TMP, max_abs, rec, rel_linf
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = {
+    "dtu": dict(V=5, H=1152, W=1536, numdepth=192),   # BASELINE.json configs[1]
+    "tt": dict(V=10, H=1088, W=1920, numdepth=256),   # BASELINE.json configs[3] (1080 rows padded to 1088)
+}
+
+
+@pytest.fixture(scope="module", params=list(CONFIGS))
+def fullsize(request):
+    import bench
+    from mvsformerplusplus_b200.config import default_args
+    from oracle import hotpath as O
+    name = request.param
+    wl = CONFIGS[name]
+    dev = torch.device("cuda:0")
+    net, sd = bench.make_net()
+    net = net.to(dev)
+    feats, proj, dv = bench.make_inputs(wl, 1234)
+    out = net.forward_features({k: v.to(dev) for k, v in feats.items()}, {k: v.to(dev) for k, v in proj.items()},
+                               dv.to(dev), TMP, keep_intermediates=True)
+    torch.cuda.synchronize()
+    torch.set_num_threads(bench.cpu_threads())
+    O.USE_ATEN_KERNELS = False
+    with torch.no_grad():
+        ora = O.hotpath_forward(feats, proj, dv, sd, default_args(), tmp=TMP, keep_intermediates=True)
+    return name, wl, net, out, ora, proj, dv, dev
+
+
+def test_full_size_cascade_vs_oracle(fullsize):
+    name, wl, net, out, ora, proj, dv, dev = fullsize
+    e = {}
+    for s in range(1, 5):
+        so, want = out[f"stage{s}"], ora[f"stage{s}"]
+        e[f"s{s}_prob"] = max_abs(so["prob_volume"].cpu(), want["prob_volume"])
+        e[f"s{s}_conf"] = max_abs(so["photometric_confidence"].cpu(), want["photometric_confidence"])
+        e[f"s{s}_depth_rel"] = rel_linf(so["depth"].cpu(), want["depth"])
+        e[f"s{s}_depth_values_rel"] = rel_linf(so["depth_values"].cpu(), want["depth_values"])
+    e["refined_depth_rel"] = rel_linf(out["refined_depth"].cpu(), ora["refined_depth"])
+    e["confidence"] = max_abs(out["photometric_confidence"].cpu(), ora["photometric_confidence"])
+    for k in ("stage1", "stage4"):
+        e[f"fmt_{k}"] = max_abs(out["features"][k].cpu(), ora["features"][k])
+    rec(f"fullsize_{name}_cascade", **e)
+    assert e["refined_depth_rel"] < 1e-3 and e["confidence"] < 1e-4
+    for s in range(1, 5):
+        assert e[f"s{s}_prob"] < 1e-4 and e[f"s{s}_conf"] < 1e-4 and e[f"s{s}_depth_rel"] < 1e-3, (s, e)
+
+
+@pytest.mark.parametrize("s", [1, 2, 3, 4])
+def test_full_size_stage_teacher_forced(fullsize, s):
+    from oracle import hotpath as O
+    name, wl, net, out, ora, proj, dv, dev = fullsize
+    f = ora["features"][f"stage{s}"]
+    ds = ora[f"stage{s}"]["depth_values"]
+    p3d = None
+    if s == 1:
+        B, _, _, H, W = f.shape
+        p3d, *_ = O.get_position_3d(B, H, W, proj["stage1"][:, 0, 1, :3, :3], ds, dv.min(), dv.max(), None, None, None, None)
+    so = net.fusions[s - 1].forward(f.to(dev), proj[f"stage{s}"].to(dev), ds.to(dev), TMP[s - 1],
+                                    position3d=None if p3d is None else p3d.to(dev), keep_intermediates=True)
+    want = ora[f"stage{s}"]
+    e = dict(entropy=max_abs(so["entropy"].cpu(), want["entropy"]), vis=max_abs(so["vis_weight"].cpu(), want["vis_weight"]),
+             volume=max_abs(so["volume_mean"].cpu().permute(0, 4, 1, 2, 3), want["volume_mean"]),
+             logits=max_abs(so["prob_volume_pre"].cpu(), want["prob_volume_pre"]),
+             logit_scale=float(want["prob_volume_pre"].abs().max()),
+             prob=max_abs(so["prob_volume"].cpu(), want["prob_volume"]),
+             conf=max_abs(so["photometric_confidence"].cpu(), want["photometric_confidence"]),
+             depth_rel=rel_linf(so["depth"].cpu(), want["depth"]))
+    rec(f"fullsize_{name}_teacher_forced_s{s}", **e)
+    assert e["prob"] < 1e-4 and e["conf"] < 1e-4 and e["depth_rel"] < 1e-3, e

@@ -11,19 +11,9 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.common import TMP, build_case, load_golden, max_abs, rel_linf
+from tests.common import ROOT, TMP, build_case, load_golden, max_abs, rec, rel_linf
 
 pytestmark = pytest.mark.gpu
-
-REPORT = {}
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-
-
-def rec(name, **kw):
-    REPORT[name] = {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in kw.items()}
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
-        json.dump(REPORT, f, indent=1, sort_keys=True)
 
 
 @pytest.fixture(scope="module")

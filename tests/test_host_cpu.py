@@ -98,3 +98,64 @@ def test_packing_layout_sizes_and_bn_folding():
     wf = flat[:144].view(9, 16).t().reshape(16, 1, 3, 3)
     got = torch.nn.functional.conv2d(x, wf, flat[144:160], padding=1)
     assert float((got - want).abs().max()) < 1e-5
+
+
+def test_validate_args_rejects_hard_coded_transformer_options():
+    for key, val in (("post_norm", False), ("qkv_bias", True), ("mid_channel", 32), ("num_heads", 8), ("down_rate", [2, 2, 2])):
+        bad = default_args()
+        bad["transformer_config"][0][key] = val
+        with pytest.raises(NotImplementedError):
+            validate_args(bad)
+        from mvsformerplusplus_b200.hotpath import HotPathNet
+        with pytest.raises(NotImplementedError):   # surfaces at construction, not at the first forward
+            HotPathNet(bad)
+
+
+def test_reference_arm_reproduces_golden_fixture():
+    """bench.py --impl reference runs the reference's own modules through oracle/ref_hotpath.py (from oracle/_ref, the
+    build-time copy, or /root/reference): it must reproduce the committed reference-executed fixture bit for bit."""
+    from oracle import ref_hotpath as RH
+    if RH.reference_root() is None:
+        pytest.skip("no reference sources (oracle/_ref not built and /root/reference absent)")
+    from tests.common import TMP, build_case, load_golden
+    gold, meta = load_golden("hotpath_v4_64x96")
+    args, params, sd, feats, proj, dv = build_case(meta)
+    R = RH.import_reference()
+    torch.manual_seed(0)
+    model = RH.RefHotPath(R, args).eval()
+    model.load_state_dict(sd, strict=True)
+    out = RH.reference_hotpath(R, model, args, feats, proj, dv, TMP, capture=False)
+    assert torch.equal(out["refined_depth"][0], gold["refined_depth"])
+    assert torch.equal(out["photometric_confidence"][0], gold["photometric_confidence"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference repository only exists in the build container")
+def test_install_on_reference_constructed_model_keeps_the_checkpoint_contract():
+    """test.py:209-220 on the real thing: init_model -> DINOv2MVSNet(arch.args); install() swaps FMT_module / fusions for
+    this package's modules; every state-dict key and value of the model is unchanged, so a reference checkpoint loads with
+    strict=True before or after install()."""
+    import json
+    import sys
+    sys.path.insert(0, "/root/reference")
+    import models.dino.layers.attention as A
+    A.FLASH_AVAILABLE = False
+    from models.networks.DINOv2_mvsformer_model import DINOv2MVSNet
+    from mvsformerplusplus_b200 import hotpath
+    cfg = json.load(open("/root/reference/config/mvsformer++.json"))["arch"]["args"]
+    torch.manual_seed(0)
+    model = DINOv2MVSNet(cfg).eval()
+    synth.randomize_state_dict(model.FMT_module, seed=3)
+    synth.randomize_state_dict(model.fusions, seed=4)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    hotpath.install(model)
+    assert isinstance(model.FMT_module, hotpath.FMT_with_pathway)
+    assert all(isinstance(f, hotpath.StageNet) for f in model.fusions)
+    after = model.state_dict()
+    assert sorted(after.keys()) == sorted(before.keys())
+    for k in before:
+        assert torch.equal(after[k], before[k]), k
+    model.load_state_dict(before, strict=True)   # test.py:220
+    # the installed modules refuse to run on the CPU instead of silently falling back
+    feats = synth.make_features(3, 64, 96)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.FMT_module.forward(feats)
