@@ -24,6 +24,9 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "dtu": dict(name="DTU test config: V=5 views, numdepth=192 (425..931mm), 1152x1536, ndepths [32,16,8,4], "
                      "feature pyramids C=[64,32,16,8] (BASELINE.json configs[1])", V=5, H=1152, W=1536, numdepth=192),
+    "tt": dict(name="Tanks&Temples intermediate: V=10 views, numdepth=256 (425..1101mm), 1088x1920 (1080 rows padded to a "
+                    "multiple of 64 as the reference's loader does), ndepths [32,16,8,4] (BASELINE.json configs[3])",
+               V=10, H=1088, W=1920, numdepth=256, interval=2.65),
     "small": dict(name="plumbing: V=3, numdepth=48, 128x192", V=3, H=128, W=192, numdepth=48),
 }
 TMP = [5.0, 5.0, 5.0, 1.0]
@@ -77,7 +80,7 @@ def make_inputs(wl, seed, jitter=0.0):
     from mvsformerplusplus_b200 import synth
     feats = synth.make_features(wl["V"], wl["H"], wl["W"], seed=seed, smooth=False)
     proj = synth.make_proj_matrices(wl["V"], wl["H"], wl["W"], jitter=jitter)
-    dv = synth.make_depth_values(wl["numdepth"], 425.0, 2.65 * 192 / wl["numdepth"])
+    dv = synth.make_depth_values(wl["numdepth"], 425.0, wl.get("interval", 2.65 * 192 / wl["numdepth"]))
     return feats, proj, dv
 
 

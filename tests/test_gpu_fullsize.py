@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 CONFIGS = {
     "dtu": dict(V=5, H=1152, W=1536, numdepth=192),   # BASELINE.json configs[1]
-    "tt": dict(V=10, H=1088, W=1920, numdepth=256),   # BASELINE.json configs[3] (1080 rows padded to 1088)
+    "tt": dict(V=10, H=1088, W=1920, numdepth=256, interval=2.65),   # BASELINE.json configs[3] (1080 rows padded to 1088)
 }
 
 
@@ -39,7 +39,7 @@ def fullsize(request):
                                dv.to(dev), TMP, keep_intermediates=True)
     torch.cuda.synchronize()
     torch.set_num_threads(bench.cpu_threads())
-    O.USE_ATEN_KERNELS = False
+    O.USE_ATEN_KERNELS = True    # the two heavy ops run the ATen kernels the reference itself calls (F.grid_sample, SDPA)
     with torch.no_grad():
         ora = O.hotpath_forward(feats, proj, dv, sd, default_args(), tmp=TMP, keep_intermediates=True)
     return name, wl, net, out, ora, proj, dv, dev
