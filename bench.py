@@ -323,19 +323,90 @@ def run_ours(a, wl, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_dsweep(a):
+    """BASELINE.json configs[4] / SURVEY.md 8(d) config 5: kernel-level sweep of the fused warp + group-correlation
+    kernels (pass A entropy + pass B aggregation; the vis CNN between them is timed separately) at the full-resolution
+    stage geometry C = G = 8, 1152x1536, V = 5, with D in {48, 96, 192, 384} plane-sweep hypotheses spanning 425..931 mm
+    uniformly in inverse depth.  Prints achieved algorithmic GB/s per D."""
+    import ctypes
+    import torch
+    from mvsformerplusplus_b200 import _lib, packing, synth
+    from mvsformerplusplus_b200.params import build_hotpath_params
+    from mvsformerplusplus_b200.config import default_args
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    L = _lib.lib()
+    V, C, G, H, W = 5, 8, 8, 1152, 1536
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator().manual_seed(1234)
+    feat = torch.randn(V, H, W, C, generator=g).to(dev)
+    pm = synth.make_proj_matrices(V, H, W)["stage4"][0].to(dev)
+    homs, kinv = torch.empty((V - 1) * 12, device=dev), torch.empty(9, device=dev)
+    _lib.check(L.mvsf_compose_geometry(P(pm), V, P(homs), P(kinv), st()), "compose_geometry")
+    torch.manual_seed(0)
+    sd = synth.randomize_state_dict(build_hotpath_params(default_args()).eval(), seed=7)
+    wts = packing.pack_vis(sd, "fusions.3.vis.").to(dev)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+    rows = []
+    for D in (48, 96, 192, 384):
+        k = torch.arange(D, dtype=torch.float32, device=dev) / (D - 1)
+        inv = 1.0 / 931.15 + (1.0 / 425.0 - 1.0 / 931.15) * k
+        depth = (1.0 / inv).view(D, 1, 1).expand(D, H, W).contiguous()
+        ent = torch.empty(V - 1, H, W, device=dev)
+        vis = torch.empty(V - 1, H, W, device=dev)
+        vol = torch.empty(D, H, W, G, device=dev)
+
+        def pass_a():
+            _lib.check(L.mvsf_warp_corr_entropy(P(feat), P(homs), P(depth), P(ent), V, C, G, D, H, W, st()), "warp_corr_entropy")
+
+        def pass_b():
+            _lib.check(L.mvsf_warp_corr_aggregate(P(feat), P(homs), P(depth), P(vis), P(vol), V, C, G, D, H, W, st()), "warp_corr_aggregate")
+
+        pass_a()
+        _lib.check(L.mvsf_vis_cnn(P(ent), P(wts), P(vis), V - 1, H, W, st()), "vis_cnn")
+        pass_b()
+        torch.cuda.synchronize()
+        reps = max(1, a.steps // 3)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ta = tb = 0.0
+        for _ in range(reps):
+            ev[0].record(); pass_a(); ev[1].record(); pass_b(); ev[2].record()
+            torch.cuda.synchronize()
+            ta += ev[0].elapsed_time(ev[1]); tb += ev[1].elapsed_time(ev[2])
+        ta, tb = ta / reps, tb / reps
+        alg = 4 * (V * C * H * W + D * H * W + G * D * H * W)
+        rows.append({"D": D, "pass_a_ms": round(ta, 4), "pass_b_ms": round(tb, 4), "algorithmic_bytes": alg,
+                     "achieved_gbs": alg / 1e9 / ((ta + tb) / 1e3), "frac": alg / 1e9 / ((ta + tb) / 1e3) / peak})
+        del depth, vol
+    best = max(r["achieved_gbs"] for r in rows)
+    line = {"metric": "warp+corr HBM GB/s vs D (C=G=8, 1152x1536, V=5; BASELINE.json configs[4])", "value": best, "unit": "GB/s",
+            "n_gpus": 1, "steps": a.steps, "warmup": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "dsweep: plane-sweep hypotheses uniform in inverse depth over 425..931 mm, two-gather plan "
+                                   "(pass A entropy + pass B aggregation), inputs larger than L2 (283 MB of features)"},
+            "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "achieved": best, "frac": best / peak, "traffic": None},
+            "sweep": rows, "gpu_launches": 2 * len(rows) * max(1, a.steps // 3)}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dtu", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="dtu", choices=sorted(WORKLOADS) + ["dsweep"])
     ap.add_argument("--batch", type=int, default=1, help="reference views per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.workload == "dsweep":
+        if rank == 0 and a.impl == "ours":
+            run_dsweep(a)
+        return
     wl = WORKLOADS[a.workload]
     if a.impl == "reference":
         if a.steps > 3:

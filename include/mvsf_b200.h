@@ -81,6 +81,16 @@ int mvsf_position3d(const float* kinv_ref, const float* depth, const float* dept
 int mvsf_homo_warp(const float* src_nhwc, const float* hom, const float* depth, float* warped, uint8_t* mask, int C,
                    int D, int H, int W, mvsf_stream_t stream);
 
+/* ---- test hook: the cost-volume passes have two organisations computing the same function - L1 gathers from global
+ * memory (warp_corr.cu, any C in 8/16/32/64) and TMA-staged shared-memory windows (warp_tile.cu, C = 8/16, even H).
+ * enable = 1 (default): use the window kernels where they apply; 0: force the L1 organisation everywhere. */
+int mvsf_warp_corr_set_tile_path(int enable);
+
+/* ---- which of the two cost-volume plans the library recommends for a stage shape: 1 = two gathers
+ * (mvsf_warp_corr_entropy, mvsf_vis_cnn, mvsf_warp_corr_aggregate), 0 = spill plan (mvsf_warp_corr_entropy_store,
+ * mvsf_vis_cnn, mvsf_corr_aggregate: needs a [(V-1)][D][H][W][8] fp32 buffer).  Both give the same volume. */
+int mvsf_warp_corr_plan(int C, int G, int D, int H, int W);
+
 /* ---- W2+W3+W4 pass A: warp + group correlation summed over groups + softmax-entropy over D.
  * models/cost_volume.py:72-92.  feat [V][H][W][C] (view 0 = reference), homs [(V-1)][12], depth [D][H][W]
  * -> entropy [(V-1)][H][W].   The (V-1,C,D,H,W) warped volume is never written. */

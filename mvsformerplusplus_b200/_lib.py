@@ -21,6 +21,8 @@ SIGNATURES = {
     "mvsf_schedule_inverse_range": ([P, P, I, F, P, I, I, I, P], I),
     "mvsf_position3d": ([P, P, P, I, P, I, P, I, I, I, P], I),
     "mvsf_homo_warp": ([P, P, P, P, P, I, I, I, I, P], I),
+    "mvsf_warp_corr_set_tile_path": ([I], I),
+    "mvsf_warp_corr_plan": ([I, I, I, I, I], I),
     "mvsf_warp_corr_entropy": ([P, P, P, P, I, I, I, I, I, I, P], I),
     "mvsf_vis_cnn": ([P, P, P, I, I, I, P], I),
     "mvsf_warp_corr_aggregate": ([P, P, P, P, P, I, I, I, I, I, I, P], I),
@@ -56,6 +58,8 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the symbol is not exported
             fn.argtypes = argt
             fn.restype = rest
+        if os.environ.get("MVSF_WARP_TILE", "1") == "0":   # debugging / A-B measurements: force the L1-gather organisation
+            L.mvsf_warp_corr_set_tile_path(0)
         _lib = L
     return _lib
 
@@ -84,7 +88,8 @@ class profile_calls:
         self._orig = {}
         for name in SIGNATURES:
             if name.endswith("_workspace_bytes") or name in ("mvsf_abi_version", "mvsf_launch_count", "mvsf_ktimer_enable",
-                                                             "mvsf_ktimer_read"):
+                                                             "mvsf_ktimer_read", "mvsf_warp_corr_plan",
+                                                             "mvsf_warp_corr_set_tile_path"):
                 continue
             fn = getattr(L, name)
             self._orig[name] = fn

@@ -19,6 +19,13 @@
 
 namespace mvsf {
 
+// warp_tile.cu: TMA-staged shared-memory windows, for C = 8 / 16 (the fine stages)
+bool warp_tile_supported(const float* feat, int C, int G, int D, int H, int W);
+int warp_tile_entropy(const float* feat, const float* homs, const float* depth, float* entropy, int V, int C, int D, int H,
+                      int W, cudaStream_t s);
+int warp_tile_aggregate(const float* feat, const float* homs, const float* depth, const float* vis, float* volume, int V, int C,
+                        int D, int H, int W, cudaStream_t s);
+
 constexpr int kMaxGenericD = 512;
 
 // v2 organisation (r1 ncu: v1 was instruction-issue bound because all C/4 lanes of a pixel recomputed the exact-rounding
@@ -363,10 +370,26 @@ static int launch_aggregate(const float* feat, const float* homs, const float* d
 
 using namespace mvsf;
 
+// test hook: 0 forces the L1-gather organisation (warp_corr.cu) for every shape, 1 (default) lets C = 8 / 16 stages use
+// the TMA-staged window kernels (warp_tile.cu).  Both compute the same function; tests compare them.
+static int g_use_tile = 1;
+
 extern "C" {
+
+int mvsf_warp_corr_set_tile_path(int enable) {
+  g_use_tile = enable != 0;
+  return MVSF_OK;
+}
 
 static int warp_corr_entropy_impl(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
                                   int C, int G, int D, int H, int W, mvsf_stream_t stream);
+
+/* 1: run the cost volume as two gathers (mvsf_warp_corr_entropy + mvsf_warp_corr_aggregate; the window kernels make the
+ * second gather cheaper than spilling and re-reading 4*(V-1)*G*D*H*W bytes); 0: spill plan
+ * (mvsf_warp_corr_entropy_store + mvsf_corr_aggregate) */
+int mvsf_warp_corr_plan(int C, int G, int D, int H, int W) {
+  return (g_use_tile && G == 8 && warp_tile_supported(nullptr, C, G, D, H, W)) ? 1 : 0;
+}
 
 int mvsf_warp_corr_entropy(const float* feat, const float* homs, const float* depth, float* entropy, int V, int C,
                            int G, int D, int H, int W, mvsf_stream_t stream) {
@@ -396,6 +419,12 @@ static int warp_corr_entropy_impl(const float* feat, const float* homs, const fl
   MVSF_REQUIRE(C % G == 0 && (C == 8 || C == 16 || C == 32 || C == 64), "warp_corr_entropy: C must be 8/16/32/64, C %% G == 0");
   MVSF_REQUIRE(D <= kMaxGenericD, "warp_corr_entropy: D <= %d", kMaxGenericD);
   cudaStream_t s = (cudaStream_t)stream;
+  if (!corr && g_use_tile && warp_tile_supported(feat, C, G, D, H, W)) {
+    int rc = warp_tile_entropy(feat, homs, depth, entropy, V, C, D, H, W, s);
+    if (rc) return rc;
+    MVSF_LAUNCH_CHECK("warp_tile_entropy");
+    return MVSF_OK;
+  }
   switch (C) {
     case 8: launch_entropy<8>(feat, homs, depth, entropy, corr, V, G, D, H, W, s); break;
     case 16: launch_entropy<16>(feat, homs, depth, entropy, corr, V, G, D, H, W, s); break;
@@ -413,6 +442,12 @@ int mvsf_warp_corr_aggregate(const float* feat, const float* homs, const float* 
   MVSF_REQUIRE(G <= C, "G must <= C!");
   MVSF_REQUIRE(G == 8 && (C == 8 || C == 16 || C == 32 || C == 64), "warp_corr_aggregate: G must be 8 and C in 8/16/32/64");
   cudaStream_t s = (cudaStream_t)stream;
+  if (g_use_tile && warp_tile_supported(feat, C, G, D, H, W)) {
+    int rc = warp_tile_aggregate(feat, homs, depth, vis, volume, V, C, D, H, W, s);
+    if (rc) return rc;
+    MVSF_LAUNCH_CHECK("warp_tile_aggregate");
+    return MVSF_OK;
+  }
   switch (C) {
     case 8: launch_aggregate<8, 1>(feat, homs, depth, vis, volume, V, D, H, W, s); break;
     case 16: launch_aggregate<16, 2>(feat, homs, depth, vis, volume, V, D, H, W, s); break;

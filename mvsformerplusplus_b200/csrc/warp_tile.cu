@@ -1,0 +1,509 @@
+// W2+W3+W4 for the fine stages (C = 8 / 16 feature channels): homography warp fused with group-wise correlation
+// (models/warping.py:69-109, models/cost_volume.py:72-101) around TMA-staged source windows in shared memory.
+//
+// Why a second organisation next to warp_corr.cu: with 8 or 16 channels one bilinear corner is only 32 / 64 bytes, so a
+// warp-wide global gather touches 16 / 8 different 128-byte lines per instruction and runs at 25-50 % of the L1
+// wavefront rate, and the taps of neighbouring pixels are NOT coherent at stages 2-4 (the hypothesis planes follow the
+// previous stage's per-pixel depth).  Here
+//   * a CTA owns a tile of reference pixels; per (source view, chunk of <= 8 hypotheses) it computes its tap
+//     coordinates, reduces their bounding box, and one thread issues ONE cp.async.bulk.tensor (TMA) box load of the
+//     source footprint: a 5-D view (c, y-parity, x, y/2, view) of the channels-last feature tensor, so the window lands
+//     in shared memory as [y/2][x][y&1][C] and everything outside the image is zero-filled by the TMA unit
+//     (= grid_sample's padding_mode='zeros', no per-corner masking);
+//   * every lane then owns whole taps: the 4 corners x 8 channels of a tap are 8 pieces of 16 bytes that, in this
+//     layout, fall on 8 DIFFERENT 16-byte bank groups whatever the tap position is; lane l reads them in the order
+//     (round i) bank group = i XOR (l mod 8), so the 8 lanes of every LDS.128 phase hit 8 different bank groups:
+//     conflict-free shared-memory gathers at 128 B/clk/SM for arbitrary (incoherent) tap positions.  Which corner a
+//     round delivers depends on the tap's x/y parity; that is folded into per-tap swaps of the two x / y weights and
+//     base addresses (lane-constant predicates), so the 8 rounds themselves are straight-line code;
+//   * taps outside the staged window (depth outliers) fall back to global loads for that lane only.
+// Pass A (entropy) and pass B (view aggregation) both gather (no spill of the per-view correlations: at these stages
+// the spill costs more HBM time than the second gather).
+#include <cuda.h>
+#include <float.h>
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace mvsf {
+namespace wt {
+
+constexpr int TW = 32, TH = 8, THREADS = 256;   // reference-pixel tile: one warp per tile row
+constexpr int DCH = 8;                          // hypotheses per window (register-resident tap coordinates)
+constexpr int kMaxD = 512;
+
+template <int C>
+struct Cfg {
+  static constexpr int LPX = C / 8;                  // lanes per pixel: every lane owns 8 channels of a tap
+  static constexpr int PIX = THREADS / LPX;          // pixels per CTA
+  static constexpr int TROWS = PIX / TW;             // tile rows
+  static constexpr int WX = 64, WY = 16;             // staged window (source texels); WY even
+  static constexpr int POS = 2 * C * 4;              // bytes of one window position [y&1][C]
+  static constexpr int P = WX * POS;                 // pitch of one row pair
+  static constexpr uint32_t BYTES = (WY / 2) * P;    // 32 KB (C = 8), 64 KB (C = 16)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// one lane polls, the warp reconverges; bounded so that a mis-programmed pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t it = 0;
+    while (!mbar_try_wait(bar, parity))
+      if (++it > (1u << 26)) __trap();
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// acc (4 channels) += w * t, as two packed fp32x2 FMAs (FFMA2: one issue slot per two FMAs)
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& t) {
+  const float2 ww = make_float2(w, w);
+  float2 lo = __ffma2_rn(make_float2(t.x, t.y), ww, make_float2(acc.x, acc.y));
+  float2 hi = __ffma2_rn(make_float2(t.z, t.w), ww, make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x))); }
+
+// per-lane constants of the rotated read order
+struct Lane {
+  bool b0, b1, b2;      // bits of (lane & 7) that are XORed into the bank-group index of a round
+  uint32_t base[2];     // window base + 16-byte piece offset for rounds with i0 = 0 / 1
+};
+
+// One tap (4 corners x 8 channels of this lane) from the staged window: sA / sB receive the bilinear sample of the lane's
+// two channel quads (quad A = the one read in rounds with i0 = 0).  (lx, ly) = integer tap position relative to the window
+// origin (both rows / columns inside the window), (fx, fy) = fractional parts.
+// C = 8 : position = [y&1][8 ch] = 64 B; 16-byte bank group of a piece = (x&1)<<2 | (y&1)<<1 | quad.
+// C = 16: position = [y&1][16 ch] = 128 B (one line); bank group = (y&1)<<2 | channel quarter; a lane owns quarters
+//         {2k, 2k+1} (k = lane & 1 is the "b0" group bit here, the x corner is a compile-time round bit).
+template <int C>
+__device__ __forceinline__ void gather_window(const Lane& L, int lx, int ly, float fx, float fy, float4& sA, float4& sB) {
+  using K = Cfg<C>;
+  const float gx = 1.0f - fx, gy = 1.0f - fy;
+  const bool yodd = ly & 1;
+  // byte offsets (window-relative) of the even-parity and odd-parity source row of this tap
+  const uint32_t rE = (uint32_t)((ly + 1) >> 1) * K::P;
+  const uint32_t rO = (uint32_t)(ly >> 1) * K::P + C * 4;
+  const float wE = yodd ? fy : gy, wO = yodd ? gy : fy;   // weight of the even / odd row
+  if (C == 8) {
+    const bool xodd = lx & 1;
+    const uint32_t cE = (uint32_t)((lx + 1) & ~1) * K::POS, cO = (uint32_t)(lx | 1) * K::POS;
+    const float vE = xodd ? fx : gx, vO = xodd ? gx : fx;  // weight of the even / odd column
+    // rounds: i2 selects the x parity (XOR b2), i1 the y parity (XOR b1), i0 the channel quad (XOR b0, folded in base[])
+    const uint32_t X0 = L.b2 ? cO : cE, X1 = L.b2 ? cE : cO;
+    const float wx0 = L.b2 ? vO : vE, wx1 = L.b2 ? vE : vO;
+    const uint32_t R0 = L.b1 ? rO : rE, R1 = L.b1 ? rE : rO;
+    const float wy0 = L.b1 ? wO : wE, wy1 = L.b1 ? wE : wO;
+    const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
+    const float4 a0 = lds128(X0 + R0 + L.base[0]), b0 = lds128(X0 + R0 + L.base[1]);
+    const float4 a1 = lds128(X0 + R1 + L.base[0]), b1 = lds128(X0 + R1 + L.base[1]);
+    const float4 a2 = lds128(X1 + R0 + L.base[0]), b2 = lds128(X1 + R0 + L.base[1]);
+    const float4 a3 = lds128(X1 + R1 + L.base[0]), b3 = lds128(X1 + R1 + L.base[1]);
+    fma4(sA, w00, a0); fma4(sB, w00, b0);
+    fma4(sA, w01, a1); fma4(sB, w01, b1);
+    fma4(sA, w10, a2); fma4(sB, w10, b2);
+    fma4(sA, w11, a3); fma4(sB, w11, b3);
+  } else {
+    // C == 16: x corner = compile-time (both columns are whole lines), y parity XOR b2, low quarter bit XOR b1
+    const uint32_t c0 = (uint32_t)lx * K::POS;
+    const uint32_t R0 = (L.b2 ? rO : rE) + c0, R1 = (L.b2 ? rE : rO) + c0;
+    const float wy0 = L.b2 ? wO : wE, wy1 = L.b2 ? wE : wO;
+    const float w00 = gx * wy0, w01 = gx * wy1, w10 = fx * wy0, w11 = fx * wy1;
+    const float4 a0 = lds128(R0 + L.base[0]), b0 = lds128(R0 + L.base[1]);
+    const float4 a1 = lds128(R1 + L.base[0]), b1 = lds128(R1 + L.base[1]);
+    const float4 a2 = lds128(R0 + L.base[0] + K::POS), b2 = lds128(R0 + L.base[1] + K::POS);
+    const float4 a3 = lds128(R1 + L.base[0] + K::POS), b3 = lds128(R1 + L.base[1] + K::POS);
+    fma4(sA, w00, a0); fma4(sB, w00, b0);
+    fma4(sA, w01, a1); fma4(sB, w01, b1);
+    fma4(sA, w10, a2); fma4(sB, w10, b2);
+    fma4(sA, w11, a3); fma4(sB, w11, b3);
+  }
+}
+
+// same tap through global memory (zero padding by masked weights, as warp_corr.cu): the rare out-of-window taps
+template <int C>
+__device__ __forceinline__ void gather_global(const float* __restrict__ srcA, const float* __restrict__ srcB, float ix, float iy,
+                                              int W, int H, float4& sA, float4& sB) {
+  int4 off;
+  float4 wt;
+  make_tap_fast(ix, iy, W, H, C, off, wt);
+  fma4(sA, wt.x, ldg4(srcA + off.x)); fma4(sB, wt.x, ldg4(srcB + off.x));
+  fma4(sA, wt.y, ldg4(srcA + off.y)); fma4(sB, wt.y, ldg4(srcB + off.y));
+  fma4(sA, wt.z, ldg4(srcA + off.z)); fma4(sB, wt.z, ldg4(srcB + off.z));
+  fma4(sA, wt.w, ldg4(srcA + off.w)); fma4(sB, wt.w, ldg4(srcB + off.w));
+}
+
+struct TapCoord {
+  float fx, fy;
+  int x0, y0;
+  bool inb;   // sample position inside (-1, W) x (-1, H): otherwise every corner is outside the image -> contributes 0
+};
+__device__ __forceinline__ TapCoord split_coord(float ix, float iy, int W, int H) {
+  TapCoord t;
+  t.inb = (ix > -1.0f) && (ix < (float)W) && (iy > -1.0f) && (iy < (float)H);   // false for NaN / Inf
+  const float sx = t.inb ? ix : 0.0f, sy = t.inb ? iy : 0.0f;
+  const float MAGIC = 12582912.0f;   // 1.5 * 2^23: round-down add = floor (|s| < 2^22)
+  const float tx = __fadd_rd(sx, MAGIC), ty = __fadd_rd(sy, MAGIC);
+  t.x0 = __float_as_int(tx) - 0x4B400000;
+  t.y0 = __float_as_int(ty) - 0x4B400000;
+  t.fx = sx - (tx - MAGIC);
+  t.fy = sy - (ty - MAGIC);
+  return t;
+}
+
+struct Shared {
+  unsigned long long bar;
+  int bbox[2][4];   // double-buffered {min x0, max x0, min y0, max y0} of the current window's taps
+};
+
+// Stages one window: reduces the bounding box of the CTA's taps, centres the WX x WY box on it, issues the TMA load and
+// waits for it.  Returns the window origin (ox, oy even) to every thread.  `slot` alternates per call.
+template <int C>
+__device__ __forceinline__ void stage_window(const CUtensorMap* map, Shared& sh, uint32_t win, int slot, uint32_t& phase, int view,
+                                             int mnx, int mxx, int mny, int mxy, int& ox, int& oy) {
+  using K = Cfg<C>;
+  mnx = __reduce_min_sync(0xffffffffu, mnx);
+  mxx = __reduce_max_sync(0xffffffffu, mxx);
+  mny = __reduce_min_sync(0xffffffffu, mny);
+  mxy = __reduce_max_sync(0xffffffffu, mxy);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&sh.bbox[slot][0], mnx);
+    atomicMax(&sh.bbox[slot][1], mxx);
+    atomicMin(&sh.bbox[slot][2], mny);
+    atomicMax(&sh.bbox[slot][3], mxy);
+  }
+  __syncthreads();   // bbox complete; every lane has also finished reading the previous window
+  const int bx0 = sh.bbox[slot][0], bx1 = sh.bbox[slot][1], by0 = sh.bbox[slot][2], by1 = sh.bbox[slot][3];
+  if (bx0 > bx1) { ox = 0; oy = 0; }
+  else {
+    const int slack_x = K::WX - (bx1 + 2 - bx0), slack_y = K::WY - (by1 + 2 - by0);
+    ox = bx0 - (slack_x > 0 ? slack_x / 2 : 0);
+    oy = (by0 - (slack_y > 0 ? slack_y / 2 : 0)) & ~1;
+  }
+  if (threadIdx.x == 0) {
+    sh.bbox[slot ^ 1][0] = INT_MAX; sh.bbox[slot ^ 1][1] = INT_MIN;   // reset the other slot for the next window
+    sh.bbox[slot ^ 1][2] = INT_MAX; sh.bbox[slot ^ 1][3] = INT_MIN;
+    const uint32_t bar = smem_u32(&sh.bar);
+    expect_tx(bar, K::BYTES);
+    tma_load_5d(win, map, 0, 0, ox, oy >> 1, view, bar);
+  }
+  mbar_wait_warp(smem_u32(&sh.bar), phase);
+  phase ^= 1;
+}
+
+// Everything a lane needs to sample source view `view` for its pixel.
+template <int C>
+struct ViewCtx {
+  Hom m;
+  float rx, ry, rz;
+  const float* srcA;
+  const float* srcB;
+};
+
+// One (view, hypothesis chunk [d0, d0 + n)) of this lane's pixel: tap coordinates, window staging, gather.
+// consume(k, sA, sB) receives the bilinear sample of hypothesis d0 + k (quad A / quad B channels of the lane).
+// The bounding box is taken from the first and last hypothesis of the chunk: taps of one pixel lie on its epipolar line
+// and move monotonically with the (monotone) hypotheses, so those two bound the rest; a tap that still falls outside the
+// window (non-monotone caller-supplied hypotheses, depth outliers of neighbours) goes through global memory.
+template <int C, int DCHT, typename F>
+__device__ __forceinline__ void process_chunk(const CUtensorMap* map, Shared& sh, uint32_t win, int& slot, uint32_t& phase,
+                                              const Lane& L, const ViewCtx<C>& vc, int view, const float* __restrict__ depth_p,
+                                              int HW, int d0, int n, bool active, const CoordConst& cc, int W, int H, F&& consume) {
+  using K = Cfg<C>;
+  float ix, iy;
+  warp_coord_fast(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)d0 * HW), cc, ix, iy);
+  TapCoord tF = split_coord(ix, iy, W, H);
+  tF.inb = tF.inb && active;
+  TapCoord tL = tF;
+  if (n > 1) {
+    warp_coord_fast(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)(d0 + n - 1) * HW), cc, ix, iy);
+    tL = split_coord(ix, iy, W, H);
+    tL.inb = tL.inb && active;
+  }
+  int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+  if (tF.inb) { mnx = mxx = tF.x0; mny = mxy = tF.y0; }
+  if (tL.inb) { mnx = min(mnx, tL.x0); mxx = max(mxx, tL.x0); mny = min(mny, tL.y0); mxy = max(mxy, tL.y0); }
+  int ox, oy;
+  stage_window<C>(map, sh, win, slot, phase, view, mnx, mxx, mny, mxy, ox, oy);
+  slot ^= 1;
+#pragma unroll
+  for (int k = 0; k < DCHT; ++k) {
+    if (k < n) {
+      TapCoord t;
+      if (k == 0) t = tF;
+      else if (k == n - 1) t = tL;
+      else {
+        warp_coord_fast(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)(d0 + k) * HW), cc, ix, iy);
+        t = split_coord(ix, iy, W, H);
+        t.inb = t.inb && active;
+      }
+      float4 sA = make_float4(0.f, 0.f, 0.f, 0.f), sB = sA;
+      const int lx = t.x0 - ox, ly = t.y0 - oy;
+      const bool inwin = t.inb && (unsigned)lx <= (unsigned)(K::WX - 2) && (unsigned)ly <= (unsigned)(K::WY - 2);
+      gather_window<C>(L, inwin ? lx : 0, inwin ? ly : 0, t.fx, t.fy, sA, sB);
+      if (!inwin) {
+        sA = make_float4(0.f, 0.f, 0.f, 0.f); sB = sA;
+        if (t.inb) {   // rare: sample through global memory (coordinates recomputed: they are not kept in registers)
+          warp_coord_fast(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)(d0 + k) * HW), cc, ix, iy);
+          gather_global<C>(vc.srcA, vc.srcB, ix, iy, W, H, sA, sB);
+        }
+      }
+      consume(k, sA, sB);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// MODE 0: pass A  -> entropy[v][pixel]      (cost_volume.py:89-92)
+// MODE 1: pass B  -> volume[d][pixel][g]    (cost_volume.py:95-101), G = 8 groups
+// DCHT: hypotheses per window (4 or 8).  GENERIC (pass A only): D > DCHT, similarities parked in a per-thread array.
+// ----------------------------------------------------------------------------------------------------------------------
+template <int C, int MODE, int DCHT, bool GENERIC>
+__global__ void __launch_bounds__(THREADS, 2)
+warp_tile_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ feat, const float* __restrict__ homs,
+                 const float* __restrict__ depth, const float* __restrict__ vis, float* __restrict__ out, int V, int D, int H,
+                 int W, int dch) {
+  using K = Cfg<C>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ Shared sh;
+  const uint32_t win = (smem_u32(smem_raw) + 127u) & ~127u;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int HW = H * W;
+  // pixel of this lane: LPX adjacent lanes share a pixel
+  const int pix_in_cta = tid / K::LPX;
+  const int px = blockIdx.x * TW + (pix_in_cta % TW), py = blockIdx.y * K::TROWS + (pix_in_cta / TW);
+  const bool active = (px < W) && (py < H);
+  const int p = min(py, H - 1) * W + min(px, W - 1);
+  const int sub = tid % K::LPX;           // which 8-channel slice of the pixel
+  Lane L;
+  int chA, chB;                            // first channel of the lane's quad A / quad B
+  if (C == 8) {
+    L.b0 = lane & 1; L.b1 = (lane >> 1) & 1; L.b2 = (lane >> 2) & 1;
+    L.base[0] = win + (L.b0 ? 16 : 0);
+    L.base[1] = win + (L.b0 ? 0 : 16);
+    chA = L.b0 ? 4 : 0; chB = L.b0 ? 0 : 4;
+  } else {
+    // lanes 2j, 2j+1 = the two channel halves of one pixel; bits 1-2 of the lane = tap slot inside an LDS.128 phase
+    L.b0 = false; L.b1 = (lane >> 1) & 1; L.b2 = (lane >> 2) & 1;
+    const int q0 = 2 * sub + (L.b1 ? 1 : 0), q1 = 2 * sub + (L.b1 ? 0 : 1);
+    L.base[0] = win + q0 * 16;
+    L.base[1] = win + q1 * 16;
+    chA = q0 * 4; chB = q1 * 4;
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&sh.bar), 1);
+    fence_barrier_init();
+    sh.bbox[0][0] = INT_MAX; sh.bbox[0][1] = INT_MIN; sh.bbox[0][2] = INT_MAX; sh.bbox[0][3] = INT_MIN;
+    sh.bbox[1][0] = INT_MAX; sh.bbox[1][1] = INT_MIN; sh.bbox[1][2] = INT_MAX; sh.bbox[1][3] = INT_MIN;
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  int slot = 0;
+  const CoordConst cc = make_coord_const(W, H);
+  const float fxp = (float)min(px, W - 1), fyp = (float)min(py, H - 1);
+  const float4 rA = ldg4(feat + (size_t)p * C + chA), rB = ldg4(feat + (size_t)p * C + chB);
+  constexpr float inv_cpg = 8.0f / (float)C;   // G / C with G = 8 groups: mean over the channels of a group
+  const float* __restrict__ depth_p = depth + p;
+
+  auto make_view = [&](int v) {
+    ViewCtx<C> vc;
+    vc.m = load_hom(homs + (size_t)v * 12);
+    vc.rx = __fadd_rn(fmaf(vc.m.r01, fyp, __fmul_rn(vc.m.r00, fxp)), vc.m.r02);
+    vc.ry = __fadd_rn(fmaf(vc.m.r11, fyp, __fmul_rn(vc.m.r10, fxp)), vc.m.r12);
+    vc.rz = __fadd_rn(fmaf(vc.m.r21, fyp, __fmul_rn(vc.m.r20, fxp)), vc.m.r22);
+    vc.srcA = feat + (size_t)(v + 1) * HW * C + chA;
+    vc.srcB = feat + (size_t)(v + 1) * HW * C + chB;
+    return vc;
+  };
+
+  if (MODE == 0) {
+    // ------------------------------------------------------------------ pass A: views outer, hypothesis chunks inner
+    float sims[GENERIC ? kMaxD : DCHT];
+    for (int v = 0; v < V - 1; ++v) {
+      const ViewCtx<C> vc = make_view(v);
+      float mx = -FLT_MAX;
+      for (int d0 = 0; d0 < D; d0 += dch) {
+        const int n = min(dch, D - d0);
+        process_chunk<C, DCHT>(&map, sh, win, slot, phase, L, vc, v + 1, depth_p, HW, d0, n, active, cc, W, H,
+                               [&](int k, const float4& sA, const float4& sB) {
+                                 float s = dot4(rA, sA) + dot4(rB, sB);
+                                 if (K::LPX == 2) s += __shfl_xor_sync(0xffffffffu, s, 1);
+                                 s *= inv_cpg;
+                                 sims[GENERIC ? d0 + k : k] = s;
+                                 mx = fmaxf(mx, s);
+                               });
+        if (!GENERIC) break;
+      }
+      // softmax over D -> entropy (cost_volume.py:90-92): p = exp(s - max) / Z ; H = -sum p * log(p + 1e-7)
+      float Z = 0.f, ent = 0.f;
+      if (GENERIC) {
+        for (int d = 0; d < D; ++d) { sims[d] = expf(sims[d] - mx); Z += sims[d]; }
+        for (int d = 0; d < D; ++d) { const float pr = __fdiv_rn(sims[d], Z); ent -= pr * logf(pr + 1e-7f); }
+      } else {
+#pragma unroll
+        for (int k = 0; k < DCHT; ++k)
+          if (k < D) { sims[k] = expf(sims[k] - mx); Z += sims[k]; }
+#pragma unroll
+        for (int k = 0; k < DCHT; ++k)
+          if (k < D) { const float pr = __fdiv_rn(sims[k], Z); ent -= pr * logf(pr + 1e-7f); }
+      }
+      if (active && sub == 0) out[(size_t)v * HW + p] = ent;
+    }
+  } else {
+    // ------------------------------------------------------------------ pass B: hypothesis chunks outer, views inner
+    float wsum = 0.f;
+    for (int v = 0; v < V - 1; ++v) wsum = __fadd_rn(wsum, __ldg(vis + (size_t)v * HW + p));
+    const float den = __fadd_rn(wsum, 1e-6f);
+    // ref * (1 / channels per group): what every warped channel is multiplied with before the visibility weight
+    const float4 qA = make_float4(rA.x * inv_cpg, rA.y * inv_cpg, rA.z * inv_cpg, rA.w * inv_cpg);
+    const float4 qB = make_float4(rB.x * inv_cpg, rB.y * inv_cpg, rB.z * inv_cpg, rB.w * inv_cpg);
+    for (int d0 = 0; d0 < D; d0 += dch) {
+      const int n = min(dch, D - d0);
+      float4 accA[DCHT], accB[DCHT];
+#pragma unroll
+      for (int k = 0; k < DCHT; ++k) accA[k] = accB[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int v = 0; v < V - 1; ++v) {
+        const ViewCtx<C> vc = make_view(v);
+        const float w = __ldg(vis + (size_t)v * HW + p);
+        process_chunk<C, DCHT>(&map, sh, win, slot, phase, L, vc, v + 1, depth_p, HW, d0, n, active, cc, W, H,
+                               [&](int k, const float4& sA, const float4& sB) {
+                                 // group correlation of this view (cost_volume.py:78-85) times its weight (:97)
+                                 accA[k].x = fmaf(qA.x * sA.x, w, accA[k].x); accA[k].y = fmaf(qA.y * sA.y, w, accA[k].y);
+                                 accA[k].z = fmaf(qA.z * sA.z, w, accA[k].z); accA[k].w = fmaf(qA.w * sA.w, w, accA[k].w);
+                                 accB[k].x = fmaf(qB.x * sB.x, w, accB[k].x); accB[k].y = fmaf(qB.y * sB.y, w, accB[k].y);
+                                 accB[k].z = fmaf(qB.z * sB.z, w, accB[k].z); accB[k].w = fmaf(qB.w * sB.w, w, accB[k].w);
+                               });
+      }
+      if (active) {
+#pragma unroll
+        for (int k = 0; k < DCHT; ++k) {
+          if (k < n) {
+            float* o = out + ((size_t)(d0 + k) * HW + p) * 8;
+            if (C == 8) {   // channels == groups
+              *reinterpret_cast<float4*>(o + chA) = make_float4(__fdiv_rn(accA[k].x, den), __fdiv_rn(accA[k].y, den),
+                                                                __fdiv_rn(accA[k].z, den), __fdiv_rn(accA[k].w, den));
+              *reinterpret_cast<float4*>(o + chB) = make_float4(__fdiv_rn(accB[k].x, den), __fdiv_rn(accB[k].y, den),
+                                                                __fdiv_rn(accB[k].z, den), __fdiv_rn(accB[k].w, den));
+            } else {        // 2 channels per group: a quad is 2 groups
+              *reinterpret_cast<float2*>(o + chA / 2) = make_float2(__fdiv_rn(accA[k].x + accA[k].y, den), __fdiv_rn(accA[k].z + accA[k].w, den));
+              *reinterpret_cast<float2*>(o + chB / 2) = make_float2(__fdiv_rn(accB[k].x + accB[k].y, den), __fdiv_rn(accB[k].z + accB[k].w, den));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 5-D view (c, y&1, x, y/2, view) of the channels-last feature tensor [V][H][W][C] (H even)
+template <int C>
+static int make_window_map(CUtensorMap* m, const float* feat, int V, int H, int W) {
+  using K = Cfg<C>;
+  EncodeTiledFn enc = encode_tiled_fn();
+  MVSF_REQUIRE(enc, "warp_tile: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t row = (cuuint64_t)W * C * 4;
+  const cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)W, (cuuint64_t)(H / 2), (cuuint64_t)V};
+  const cuuint64_t strides[4] = {row, (cuuint64_t)C * 4, 2 * row, (cuuint64_t)H * row};
+  const cuuint32_t box[5] = {(cuuint32_t)C, 2, (cuuint32_t)K::WX, (cuuint32_t)(K::WY / 2), 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(feat), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MVSF_ERR_CUDA, "warp_tile: cuTensorMapEncodeTiled failed (%d) for V=%d H=%d W=%d C=%d", (int)r, V, H, W, C);
+  return MVSF_OK;
+}
+
+template <int C, int MODE, int DCHT, bool GENERIC>
+static int launch(const float* feat, const float* homs, const float* depth, const float* vis, float* out, int V, int D, int H,
+                  int W, int dch, cudaStream_t s) {
+  using K = Cfg<C>;
+  auto kern = warp_tile_kernel<C, MODE, DCHT, GENERIC>;
+  static DeviceOnce once;
+  const int dev = current_device();
+  const size_t smem = K::BYTES + 128;
+  if (once.need(dev)) {
+    MVSF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    once.done(dev);
+  }
+  CUtensorMap map;
+  int rc = make_window_map<C>(&map, feat, V, H, W);
+  if (rc) return rc;
+  dim3 grid(cdiv(W, TW), cdiv(H, K::TROWS));
+  kern<<<grid, THREADS, smem, s>>>(map, feat, homs, depth, vis, out, V, D, H, W, dch);
+  return MVSF_OK;
+}
+
+template <int C>
+static int dispatch(int mode, const float* feat, const float* homs, const float* depth, const float* vis, float* out, int V,
+                    int D, int H, int W, cudaStream_t s) {
+  if (mode == 0) {
+    if (D <= 4) return launch<C, 0, 4, false>(feat, homs, depth, vis, out, V, D, H, W, D, s);
+    if (D <= 8) return launch<C, 0, 8, false>(feat, homs, depth, vis, out, V, D, H, W, D, s);
+    int c = D / 24;   // plane sweeps: the epipolar span of a chunk has to stay inside the window
+    c = c < 2 ? 2 : (c > 8 ? 8 : c);
+    return launch<C, 0, 8, true>(feat, homs, depth, vis, out, V, D, H, W, c, s);
+  }
+  if (D <= 4) return launch<C, 1, 4, false>(feat, homs, depth, vis, out, V, D, H, W, D, s);
+  int c = D <= 8 ? D : D / 24;
+  c = c < 2 ? 2 : (c > 8 ? 8 : c);
+  return launch<C, 1, 8, false>(feat, homs, depth, vis, out, V, D, H, W, c, s);
+}
+
+}  // namespace wt
+
+// Used by warp_corr.cu's entry points.  Returns false when this organisation does not apply (other channel counts, odd H:
+// the y-parity view of the tensor map needs an even number of rows, misaligned pointers).
+bool warp_tile_supported(const float* feat, int C, int G, int D, int H, int W) {
+  return (C == 8 || C == 16) && G == 8 && (H % 2 == 0) && H >= 2 && W >= 1 && D >= 1 && D <= wt::kMaxD &&
+         ((uintptr_t)feat & 15) == 0 && ((long long)W * C * 4) % 16 == 0;
+}
+// pass A: entropy [V-1][H][W]
+int warp_tile_entropy(const float* feat, const float* homs, const float* depth, float* entropy, int V, int C, int D, int H,
+                      int W, cudaStream_t s) {
+  return C == 8 ? wt::dispatch<8>(0, feat, homs, depth, nullptr, entropy, V, D, H, W, s)
+                : wt::dispatch<16>(0, feat, homs, depth, nullptr, entropy, V, D, H, W, s);
+}
+// pass B: volume [D][H][W][8]
+int warp_tile_aggregate(const float* feat, const float* homs, const float* depth, const float* vis, float* volume, int V, int C,
+                        int D, int H, int W, cudaStream_t s) {
+  return C == 8 ? wt::dispatch<8>(1, feat, homs, depth, vis, volume, V, D, H, W, s)
+                : wt::dispatch<16>(1, feat, homs, depth, vis, volume, V, D, H, W, s);
+}
+
+}  // namespace mvsf

@@ -203,7 +203,8 @@ class StageNet(_PackedMixin, nn.Module):
         vis = torch.empty((V - 1, H, W), **f32)
         volume = torch.empty((D, H, W, G), **f32)
         spill_bytes = 4 * (V - 1) * D * H * W * G
-        if G == 8 and spill_bytes <= self.corr_spill_budget_bytes:
+        two_gathers = L.mvsf_warp_corr_plan(C, G, D, H, W) == 1   # fine stages: TMA-staged window kernels, no spill
+        if G == 8 and not two_gathers and spill_bytes <= self.corr_spill_budget_bytes:
             # pass A also stores the per-view group correlations; the view aggregation then streams them (no second gather)
             corr = torch.empty((V - 1, D, H, W, G), **f32)
             _lib.check(L.mvsf_warp_corr_entropy_store(_ptr(feat_nhwc), _ptr(homs), _ptr(depth_values), _ptr(entropy),

@@ -149,16 +149,23 @@ def _rand_vis_sd(seed):
     return synth.randomize_state_dict(params, seed=seed)
 
 
-COST_CASES = [  # C, D, H, W, V, theta_step
-    (8, 4, 37, 53, 3, 0.1), (16, 8, 24, 40, 3, 0.1), (32, 16, 16, 24, 4, 0.12), (64, 32, 12, 16, 5, 0.1),
-    (8, 4, 31, 45, 3, 0.6),   # wide baseline: many taps leave the image (zero padding per corner)
-    (8, 48, 10, 14, 3, 0.1),  # generic-D path (D-sweep configuration)
-    (64, 8, 9, 11, 2, 0.1),
+COST_CASES = [  # C, D, H, W, V, theta_step, depth jitter
+    (8, 4, 37, 53, 3, 0.1, 0.02), (16, 8, 24, 40, 3, 0.1, 0.02), (32, 16, 16, 24, 4, 0.12, 0.02), (64, 32, 12, 16, 5, 0.1, 0.02),
+    (8, 4, 31, 45, 3, 0.6, 0.02),   # wide baseline: many taps leave the image (zero padding per corner)
+    (8, 48, 10, 14, 3, 0.1, 0.02),  # generic-D path (D-sweep configuration)
+    (64, 8, 9, 11, 2, 0.1, 0.02),
+    # shapes served by the TMA-staged window kernels (C = 8 / 16, even H): several tiles, ragged right / bottom edges,
+    # taps leaving the image, depth outliers that leave the staged window (global fallback), D = 4 / 8 / chunked D
+    (8, 4, 64, 96, 3, 0.1, 0.02), (8, 4, 30, 44, 5, 0.6, 0.02), (8, 4, 48, 80, 3, 0.15, 0.4), (8, 8, 16, 40, 3, 0.1, 0.02),
+    (8, 7, 18, 34, 2, 0.1, 0.02), (16, 8, 32, 48, 4, 0.1, 0.02), (16, 8, 28, 68, 3, 0.5, 0.3), (16, 4, 12, 20, 3, 0.1, 0.02),
+    (16, 24, 10, 36, 3, 0.1, 0.02), (8, 96, 12, 20, 3, 0.1, 0.0),
 ]
 
 
-@pytest.mark.parametrize("C,D,H,W,V,th", COST_CASES)
-def test_cost_volume_kernels(dev, L, C, D, H, W, V, th):
+@pytest.mark.parametrize("C,D,H,W,V,th,jit", COST_CASES)
+def test_cost_volume_kernels(dev, L, C, D, H, W, V, th, jit):
+    """Pass A (entropy), vis CNN, pass B (aggregation) against the oracle, through every organisation the library has:
+    L1 gathers with recompute, L1 gathers with the correlation spill, and (where they apply) the window kernels."""
     from mvsformerplusplus_b200 import packing, synth
     from oracle import hotpath as O
     sd = _rand_vis_sd(5)
@@ -167,7 +174,7 @@ def test_cost_volume_kernels(dev, L, C, D, H, W, V, th):
     sc = {8: 1, 16: 2, 32: 4, 64: 8}[C]
     pm = synth.make_proj_matrices(V, H * sc, W * sc, theta_step=th)[f"stage{ {1: 4, 2: 3, 4: 2, 8: 1}[sc] }"]
     dv = synth.make_depth_values(192)
-    dvals = O.init_inverse_range(dv, D, H, W) * (1.0 + 0.02 * torch.rand(1, D, H, W, generator=g))
+    dvals = O.init_inverse_range(dv, D, H, W) * (1.0 + jit * torch.rand(1, D, H, W, generator=g))
     want = O.cost_volume(feats, pm, dvals, sd, "fusions.3.", 8)
     homs = torch.empty((V - 1) * 12, device=dev)
     kinv = torch.empty(9, device=dev)
@@ -175,22 +182,40 @@ def test_cost_volume_kernels(dev, L, C, D, H, W, V, th):
     ck(L.mvsf_compose_geometry(P(pmd), V, P(homs), P(kinv), S()), "compose_geometry")
     f = feats[0].permute(0, 2, 3, 1).contiguous().to(dev)
     dd = dvals[0].contiguous().to(dev)
-    ent = torch.empty(V - 1, H, W, device=dev)
-    ck(L.mvsf_warp_corr_entropy(P(f), P(homs), P(dd), P(ent), V, C, 8, D, H, W, S()), "warp_corr_entropy")
     wts = packing.pack_vis(sd, "fusions.3.vis.").to(dev)
-    vis = torch.empty(V - 1, H, W, device=dev)
-    ck(L.mvsf_vis_cnn(P(ent), P(wts), P(vis), V - 1, H, W, S()), "vis_cnn")
-    vol = torch.empty(D, H, W, 8, device=dev)
-    ck(L.mvsf_warp_corr_aggregate(P(f), P(homs), P(dd), P(vis), P(vol), V, C, 8, D, H, W, S()), "warp_corr_aggregate")
-    # the path hotpath.py uses: pass A stores the per-view group correlations, the aggregation streams them
-    ent_s = torch.empty(V - 1, H, W, device=dev)
-    corr = torch.empty(V - 1, D, H, W, 8, device=dev)
-    vol_s = torch.empty(D, H, W, 8, device=dev)
-    ck(L.mvsf_warp_corr_entropy_store(P(f), P(homs), P(dd), P(ent_s), P(corr), V, C, 8, D, H, W, S()), "warp_corr_entropy_store")
-    ck(L.mvsf_corr_aggregate(P(corr), P(vis), P(vol_s), V, 8, D, H, W, S()), "corr_aggregate")
+    vol_scale = max(1.0, float(want["volume_mean"].abs().max()))
+
+    def run_two_gathers():
+        ent = torch.empty(V - 1, H, W, device=dev)
+        ck(L.mvsf_warp_corr_entropy(P(f), P(homs), P(dd), P(ent), V, C, 8, D, H, W, S()), "warp_corr_entropy")
+        vis = torch.empty(V - 1, H, W, device=dev)
+        ck(L.mvsf_vis_cnn(P(ent), P(wts), P(vis), V - 1, H, W, S()), "vis_cnn")
+        vol = torch.empty(D, H, W, 8, device=dev)
+        ck(L.mvsf_warp_corr_aggregate(P(f), P(homs), P(dd), P(vis), P(vol), V, C, 8, D, H, W, S()), "warp_corr_aggregate")
+        return ent, vis, vol
+
+    ck(L.mvsf_warp_corr_set_tile_path(0), "set_tile_path")
+    try:
+        ent, vis, vol = run_two_gathers()
+        # spill plan: pass A stores the per-view group correlations, the aggregation streams them
+        ent_s = torch.empty(V - 1, H, W, device=dev)
+        corr = torch.empty(V - 1, D, H, W, 8, device=dev)
+        vol_s = torch.empty(D, H, W, 8, device=dev)
+        ck(L.mvsf_warp_corr_entropy_store(P(f), P(homs), P(dd), P(ent_s), P(corr), V, C, 8, D, H, W, S()), "warp_corr_entropy_store")
+        ck(L.mvsf_corr_aggregate(P(corr), P(vis), P(vol_s), V, 8, D, H, W, S()), "corr_aggregate")
+    finally:
+        ck(L.mvsf_warp_corr_set_tile_path(1), "set_tile_path")
     assert torch.equal(ent_s, ent)
     e_paths = max_abs(vol_s.cpu(), vol.cpu())
-    assert e_paths <= 2e-6 * max(1.0, float(vol.abs().max())), e_paths   # identical up to the pair sum of 8-channel groups
+    assert e_paths <= 2e-6 * vol_scale, e_paths   # identical up to the pair sum of 8-channel groups
+    tiled = L.mvsf_warp_corr_plan(C, 8, D, H, W) == 1
+    assert tiled == (C in (8, 16) and H % 2 == 0)
+    e_tile = {}
+    if tiled:   # the organisation hotpath.py uses for these shapes
+        ent_t, vis_t, vol_t = run_two_gathers()
+        e_tile = dict(tile_vs_l1_entropy=max_abs(ent_t.cpu(), ent.cpu()), tile_vs_l1_volume=max_abs(vol_t.cpu(), vol_s.cpu()))
+        assert e_tile["tile_vs_l1_entropy"] < 2e-5 and e_tile["tile_vs_l1_volume"] < 1e-5 * vol_scale, e_tile
+        ent, vis, vol_s = ent_t, vis_t, vol_t
     vol = vol_s
     e_ent = max_abs(ent.cpu(), want["entropy"][0])
     e_vis = max_abs(vis.cpu(), want["vis_weight"][0])
@@ -200,8 +225,8 @@ def test_cost_volume_kernels(dev, L, C, D, H, W, V, th):
     ent_o = want["entropy"][0].contiguous().to(dev)
     ck(L.mvsf_vis_cnn(P(ent_o), P(wts), P(vis2), V - 1, H, W, S()), "vis_cnn")
     e_vis2 = max_abs(vis2.cpu(), want["vis_weight"][0])
-    rec(f"cost_volume_C{C}_D{D}_{H}x{W}_V{V}_th{th}", entropy=e_ent, vis=e_vis, vis_isolated=e_vis2, volume=e_vol,
-        vol_scale=float(want["volume_mean"].abs().max()))
+    rec(f"cost_volume_C{C}_D{D}_{H}x{W}_V{V}_th{th}_j{jit}", entropy=e_ent, vis=e_vis, vis_isolated=e_vis2, volume=e_vol,
+        vol_scale=float(want["volume_mean"].abs().max()), tiled=int(tiled), **e_tile)
     assert e_ent < 5e-4 and e_vis < 5e-4 and e_vis2 < 2e-5 and e_vol < 1e-3
 
 

@@ -35,3 +35,6 @@ if a.breakdown:
     tot = sum(v["ms"] for v in summ.values()) / 3
     print(json.dumps({k: {"ms_per_map": round(v["ms"] / 3, 4), "calls_per_map": v["calls"] // 3} for k, v in sorted(summ.items())}, indent=1))
     print("total ms per depth map (sum of bracketed calls):", round(tot, 3))
+    torch.cuda.synchronize()
+    per_call = [(n, round(s.elapsed_time(e), 4)) for n, s, e in prof.records[-len(prof.records) // 3:]]
+    print("per call, last forward:", json.dumps([c for c in per_call if "warp_corr" in c[0] or "corr_aggregate" in c[0] or "vis_cnn" in c[0]]))
