@@ -36,6 +36,7 @@ SIGNATURES = {
     "mvsf_costreg_tr_workspace_bytes": ([I, I, I, I, ctypes.POINTER(Z)], I),
     "mvsf_costreg_tr_forward": ([P, P, P, P, Z, P, P, Z, I, I, I, I, I, F, P], I),
     "mvsf_split_weights_f16": ([P, P, Z, P], I),
+    "mvsf_attention_set_precision": ([I], I),
     "mvsf_attention_forward": ([P, P, P, Z, I, F, P], I),
     "mvsf_linear_tc_forward": ([P, P, P, P, P, Z, I, I, I, I, P], I),
     "mvsf_softargmax": ([P, P, F, P, P, P, I, I, I, P], I),
@@ -58,6 +59,8 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the symbol is not exported
             fn.argtypes = argt
             fn.restype = rest
+        if os.environ.get("MVSF_ATTENTION_PLO", "0") == "1":   # A-B measurements: round-1 three-product attention
+            L.mvsf_attention_set_precision(1)
         if os.environ.get("MVSF_WARP_TILE", "1") == "0":   # debugging / A-B measurements: force the L1-gather organisation
             L.mvsf_warp_corr_set_tile_path(0)
         _lib = L
@@ -89,7 +92,7 @@ class profile_calls:
         for name in SIGNATURES:
             if name.endswith("_workspace_bytes") or name in ("mvsf_abi_version", "mvsf_launch_count", "mvsf_ktimer_enable",
                                                              "mvsf_ktimer_read", "mvsf_warp_corr_plan",
-                                                             "mvsf_warp_corr_set_tile_path"):
+                                                             "mvsf_warp_corr_set_tile_path", "mvsf_attention_set_precision"):
                 continue
             fn = getattr(L, name)
             self._orig[name] = fn

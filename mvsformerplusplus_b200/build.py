@@ -11,7 +11,7 @@ LIB = os.path.join(HERE, "libmvsf_b200.so")
 STAMP = os.path.join(HERE, ".libmvsf_b200.stamp")
 SOURCES = ["api.cu", "geometry.cu", "warp_corr.cu", "warp_tile.cu", "vis_cnn.cu", "costreg_unet.cu", "costreg_tr.cu", "fmt.cu", "linear_tc.cu", "conv3d_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "--extended-lambda"] + os.environ.get("MVSF_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

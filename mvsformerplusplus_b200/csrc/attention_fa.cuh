@@ -105,6 +105,11 @@ __global__ void qkv_tile_kernel(const float* __restrict__ qkv, __half* __restric
   }
 }
 
+// PLO = true : P = P_hi + P_lo (22 mantissa bits), three partial products P_hi V_lo + P_hi V_hi + P_lo V_hi  (round-1 kernel)
+// PLO = false: P = P_hi only (fp16, 11 bits; the SAME rounded P feeds the numerator and the normaliser, so the rounding is an
+//              unbiased 2^-12 relative perturbation of the softmax weights): half the P*V MMAs, no P_lo shared-memory
+//              traffic, no lo-split arithmetic in the softmax threads.  Measured against fp64 in tests/test_gpu_parity.py.
+template <bool PLO>
 __global__ void __launch_bounds__(fa6::THREADS, 1)
 attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, __half* __restrict__ out2, int N, int ntiles) {
   using namespace fa6;
@@ -182,7 +187,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         mma_ts(el, tO, tP + i * 8, vv + i * (2 * LBO_V >> 4), idesc_o2, i > 0 ? 1u : 0u);
-        mma_ss(el, tO + 16, p_lo[w] + i * (2 * LBO_P >> 4), vv + i * (2 * LBO_V >> 4) + (256 >> 4), idesc_o, 1u);
+        if (PLO) mma_ss(el, tO + 16, p_lo[w] + i * (2 * LBO_P >> 4), vv + i * (2 * LBO_V >> 4) + (256 >> 4), idesc_o, 1u);
       }
       commit_e(el, bar_of + 8 * w);
     };
@@ -284,18 +289,22 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
             const float p0 = ex2f(__uint_as_float(sr[c16][c8 * 8 + 2 * e]) - mb);
             const float p1 = ex2f(__uint_as_float(sr[c16][c8 * 8 + 2 * e + 1]) - mb);
             const __half2 hh = __floats2half2_rn(p0, p1);
-            const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
             pw[c8 * 4 + e] = *reinterpret_cast<const uint32_t*>(&hh);
-            pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
+            if (PLO) {
+              const float2 hf = __half22float2(hh);
+              const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+              pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
           }
-          const uint32_t dst = prow + (half * 8 + c16 * 4 + c8) * LBO_P;
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+          if (PLO) {
+            const uint32_t dst = prow + (half * 8 + c16 * 4 + c8) * LBO_P;
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+          }
         }
         tmem_st16(tP + c16 * 16, pw);
       }
       tmem_st_wait();
-      fence_proxy_async();
+      if (PLO) fence_proxy_async();
       tc_fence_before_sync();
       mbar_arrive(bar_pf + 8 * w);
     }

@@ -25,6 +25,10 @@
 
 #include "common.cuh"
 
+#ifndef MVSF_WT_PASSB_BLOCKS
+#define MVSF_WT_PASSB_BLOCKS 3   // resident CTAs per SM of the C = 8, D <= 4 aggregation kernel (3 costs ~20 spilled registers)
+#endif
+
 namespace mvsf {
 namespace wt {
 
@@ -232,12 +236,12 @@ __device__ __forceinline__ void process_chunk(const CUtensorMap* map, Shared& sh
                                               int HW, int d0, int n, bool active, const CoordConst& cc, int W, int H, F&& consume) {
   using K = Cfg<C>;
   float ix, iy;
-  warp_coord_fast(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)d0 * HW), cc, ix, iy);
+  warp_coord_lean(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)d0 * HW), cc, ix, iy);
   TapCoord tF = split_coord(ix, iy, W, H);
   tF.inb = tF.inb && active;
   TapCoord tL = tF;
   if (n > 1) {
-    warp_coord_fast(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)(d0 + n - 1) * HW), cc, ix, iy);
+    warp_coord_lean(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)(d0 + n - 1) * HW), cc, ix, iy);
     tL = split_coord(ix, iy, W, H);
     tL.inb = tL.inb && active;
   }
@@ -254,7 +258,7 @@ __device__ __forceinline__ void process_chunk(const CUtensorMap* map, Shared& sh
       if (k == 0) t = tF;
       else if (k == n - 1) t = tL;
       else {
-        warp_coord_fast(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)(d0 + k) * HW), cc, ix, iy);
+        warp_coord_lean(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)(d0 + k) * HW), cc, ix, iy);
         t = split_coord(ix, iy, W, H);
         t.inb = t.inb && active;
       }
@@ -265,7 +269,7 @@ __device__ __forceinline__ void process_chunk(const CUtensorMap* map, Shared& sh
       if (!inwin) {
         sA = make_float4(0.f, 0.f, 0.f, 0.f); sB = sA;
         if (t.inb) {   // rare: sample through global memory (coordinates recomputed: they are not kept in registers)
-          warp_coord_fast(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)(d0 + k) * HW), cc, ix, iy);
+          warp_coord_lean(vc.rx, vc.ry, vc.rz, vc.m, __ldg(depth_p + (size_t)(d0 + k) * HW), cc, ix, iy);
           gather_global<C>(vc.srcA, vc.srcB, ix, iy, W, H, sA, sB);
         }
       }
@@ -280,7 +284,7 @@ __device__ __forceinline__ void process_chunk(const CUtensorMap* map, Shared& sh
 // DCHT: hypotheses per window (4 or 8).  GENERIC (pass A only): D > DCHT, similarities parked in a per-thread array.
 // ----------------------------------------------------------------------------------------------------------------------
 template <int C, int MODE, int DCHT, bool GENERIC>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, (C == 8 && (MODE == 0 || (DCHT == 4 && MVSF_WT_PASSB_BLOCKS == 3))) ? 3 : 2)
 warp_tile_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ feat, const float* __restrict__ homs,
                  const float* __restrict__ depth, const float* __restrict__ vis, float* __restrict__ out, int V, int D, int H,
                  int W, int dch) {
@@ -490,7 +494,7 @@ static int dispatch(int mode, const float* feat, const float* homs, const float*
 // Used by warp_corr.cu's entry points.  Returns false when this organisation does not apply (other channel counts, odd H:
 // the y-parity view of the tensor map needs an even number of rows, misaligned pointers).
 bool warp_tile_supported(const float* feat, int C, int G, int D, int H, int W) {
-  return (C == 8 || C == 16) && G == 8 && (H % 2 == 0) && H >= 2 && W >= 1 && D >= 1 && D <= wt::kMaxD &&
+  return (C == 8 || C == 16) && G == 8 && (H % 2 == 0) && H >= 2 && W >= 2 && D >= 1 && D <= wt::kMaxD &&
          ((uintptr_t)feat & 15) == 0 && ((long long)W * C * 4) % 16 == 0;
 }
 // pass A: entropy [V-1][H][W]
