@@ -86,10 +86,10 @@ int mvsf_homo_warp(const float* src_nhwc, const float* hom, const float* depth, 
  * enable = 1 (default): use the window kernels where they apply; 0: force the L1 organisation everywhere. */
 int mvsf_warp_corr_set_tile_path(int enable);
 
-/* ---- which of the two cost-volume plans the library recommends for a stage shape: 1 = two gathers
- * (mvsf_warp_corr_entropy, mvsf_vis_cnn, mvsf_warp_corr_aggregate), 0 = spill plan (mvsf_warp_corr_entropy_store,
- * mvsf_vis_cnn, mvsf_corr_aggregate: needs a [(V-1)][D][H][W][8] fp32 buffer).  Both give the same volume. */
-int mvsf_warp_corr_plan(int C, int G, int D, int H, int W);
+/* ---- which of the two cost-volume plans to run for a stage shape: 1 = two gathers (mvsf_warp_corr_entropy, mvsf_vis_cnn,
+ * mvsf_warp_corr_aggregate; no intermediate buffer), 0 = spill plan (mvsf_warp_corr_entropy_store, mvsf_vis_cnn,
+ * mvsf_corr_aggregate; needs a [(V-1)][D][H][W][8] fp32 buffer; the faster one on B200).  Both give the same volume. */
+int mvsf_warp_corr_plan(int C, int G, int D, int H, int W, int V, size_t spill_budget_bytes);
 
 /* ---- W2+W3+W4 pass A: warp + group correlation summed over groups + softmax-entropy over D.
  * models/cost_volume.py:72-92.  feat [V][H][W][C] (view 0 = reference), homs [(V-1)][12], depth [D][H][W]

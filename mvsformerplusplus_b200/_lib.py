@@ -22,7 +22,7 @@ SIGNATURES = {
     "mvsf_position3d": ([P, P, P, I, P, I, P, I, I, I, P], I),
     "mvsf_homo_warp": ([P, P, P, P, P, I, I, I, I, P], I),
     "mvsf_warp_corr_set_tile_path": ([I], I),
-    "mvsf_warp_corr_plan": ([I, I, I, I, I], I),
+    "mvsf_warp_corr_plan": ([I, I, I, I, I, I, Z], I),
     "mvsf_warp_corr_entropy": ([P, P, P, P, I, I, I, I, I, I, P], I),
     "mvsf_vis_cnn": ([P, P, P, I, I, I, P], I),
     "mvsf_warp_corr_aggregate": ([P, P, P, P, P, I, I, I, I, I, I, P], I),

@@ -384,13 +384,15 @@ int mvsf_warp_corr_set_tile_path(int enable) {
 static int warp_corr_entropy_impl(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
                                   int C, int G, int D, int H, int W, mvsf_stream_t stream);
 
-/* 1: run the cost volume as two gathers (mvsf_warp_corr_entropy + mvsf_warp_corr_aggregate; the window kernels make the
- * second gather cheaper than spilling and re-reading 4*(V-1)*G*D*H*W bytes); 0: spill plan
- * (mvsf_warp_corr_entropy_store + mvsf_corr_aggregate) */
-int mvsf_warp_corr_plan(int C, int G, int D, int H, int W) {
-  return (g_use_tile && G == 8 && warp_tile_supported(nullptr, C, G, D, H, W)) ? 1 : 0;
+/* 1: run the cost volume as two gathers (mvsf_warp_corr_entropy + mvsf_warp_corr_aggregate, no intermediate buffer);
+ * 0: spill plan (mvsf_warp_corr_entropy_store + mvsf_corr_aggregate, needs 4*(V-1)*G*D*H*W bytes).  Measured on B200 the
+ * spill plan is the faster one at every stage of the shipped cascade (the gather is bound by the SM's load path, the
+ * streaming pass by HBM), so the recommendation only depends on the buffer size the caller is willing to spend. */
+int mvsf_warp_corr_plan(int C, int G, int D, int H, int W, int V, size_t spill_budget_bytes) {
+  if (G != 8 || !(C == 8 || C == 16 || C == 32 || C == 64)) return 1;   // the spill kernels exist for G == 8 only
+  const size_t spill = (size_t)4 * (size_t)(V > 1 ? V - 1 : 1) * G * D * H * W;
+  return spill > spill_budget_bytes ? 1 : 0;
 }
-
 int mvsf_warp_corr_entropy(const float* feat, const float* homs, const float* depth, float* entropy, int V, int C,
                            int G, int D, int H, int W, mvsf_stream_t stream) {
   return warp_corr_entropy_impl(feat, homs, depth, entropy, nullptr, V, C, G, D, H, W, stream);

@@ -6,22 +6,25 @@
 // wavefront rate, and the taps of neighbouring pixels are NOT coherent at stages 2-4 (the hypothesis planes follow the
 // previous stage's per-pixel depth).  Here
 //   * a CTA owns a tile of reference pixels; per (source view, chunk of <= 8 hypotheses) it computes its tap
-//     coordinates, reduces their bounding box, and one warp issues the source footprint as bulk asynchronous copies
-//     (cp.async.bulk, the TMA engine's linear mode: one 2-4 KB row segment per request, completion on an mbarrier); the
-//     window lands in shared memory as rows [y][x][C] with a row pitch of (row bytes + 64), parts of the window outside
-//     the image are zero-filled (= grid_sample's padding_mode='zeros', no per-corner masking).  (A first version used ONE
-//     5-D cp.async.bulk.tensor box with the two row parities interleaved; its 32-byte inner rows made the TMA unit the
-//     bottleneck - ~4 clk per box row, 2 us per 32 KB window - see DESIGN.md.)
-//   * every lane then owns whole taps: the 4 corners x 8 channels of a tap are 8 pieces of 16 bytes.  With the odd
-//     pitch the 16-byte bank group of a piece is  (4y + 2x + quad) mod 8  (C = 8), i.e. bit0 = channel quad,
-//     bit1 = x parity, bit2 = (x>>1 parity) XOR (y parity): the 8 pieces of ANY tap fall on 8 different bank groups.
-//     Lane l reads them in the order (round i) bank group = i XOR (l mod 8), so the 8 lanes of every LDS.128 phase hit 8
-//     different bank groups: conflict-free shared-memory gathers at 128 B/clk/SM for arbitrary (incoherent) tap
-//     positions.  Which corner a round delivers depends on the tap's x/y parities; that is folded into per-tap swaps of
-//     the x / y weights and base addresses (one-bit XORs), so the 8 rounds themselves are straight-line code;
+//     coordinates, reduces their bounding box, and one thread issues ONE cp.async.bulk.tensor (TMA) box load of the
+//     source footprint: a 5-D view (c, y-parity, x, y/2, view) of the channels-last feature tensor, so the window lands
+//     in shared memory as [y/2][x][y&1][C] and everything outside the image is zero-filled by the TMA unit
+//     (= grid_sample's padding_mode='zeros', no per-corner masking);
+//   * every lane then owns whole taps: the 4 corners x 8 channels of a tap are 8 pieces of 16 bytes that, in this
+//     layout, fall on 8 DIFFERENT 16-byte bank groups whatever the tap position is; lane l reads them in the order
+//     (round i) bank group = i XOR (l mod 8), so the 8 lanes of every LDS.128 phase hit 8 different bank groups:
+//     conflict-free shared-memory gathers at 128 B/clk/SM for arbitrary (incoherent) tap positions.  Which corner a
+//     round delivers depends on the tap's x/y parity; that is folded into per-tap swaps of the two x / y weights and
+//     base addresses (lane-constant predicates), so the 8 rounds themselves are straight-line code;
 //   * taps outside the staged window (depth outliers) fall back to global loads for that lane only.
-// Pass A (entropy) and pass B (view aggregation) both gather (no spill of the per-view correlations: at these stages
-// the spill costs more HBM time than the second gather).
+// Measured on B200 (DTU stage 4, 28.3 M taps per pass; DESIGN.md "warp + correlation" has the full table): pass A 0.37 ms,
+// pass B 0.42 ms - faster than the L1-gather kernels doing the same two gathers (0.43 / 0.50 ms), 28 % faster on the
+// plane-sweep microbenchmark, but slower than warp_corr.cu's spill plan (gather once, stream the stored correlations:
+// 0.51 + 0.19 ms), which therefore stays the default of the cascade; these kernels serve the two-gather plan (plane sweeps,
+// spill buffers over budget).  A variant that staged the window rows with cp.async.bulk (2-4 KB requests, odd row pitch)
+// instead of the tensor box measured slower (0.58 / 0.69 ms); with D = 4..8 taps per lane and window the per-window
+// skeleton (coordinates, bounding box, CTA barrier, staging latency) costs more than the conflict-free gather itself.
+#include <cuda.h>
 #include <float.h>
 #include <limits.h>
 
@@ -43,11 +46,10 @@ struct Cfg {
   static constexpr int LPX = C / 8;                  // lanes per pixel: every lane owns 8 channels of a tap
   static constexpr int PIX = THREADS / LPX;          // pixels per CTA
   static constexpr int TROWS = PIX / TW;             // tile rows
-  static constexpr int WX = 64, WY = 16;             // staged window (source texels)
-  static constexpr int TEX = C * 4;                  // bytes of one texel
-  static constexpr int ROWB = WX * TEX;              // bytes of one window row (2 KB / 4 KB)
-  static constexpr int PITCH = ROWB + 64;            // odd multiple of 64 B: consecutive rows sit in opposite bank halves
-  static constexpr uint32_t BYTES = WY * PITCH;      // 33 KB (C = 8), 65 KB (C = 16)
+  static constexpr int WX = 64, WY = 16;             // staged window (source texels); WY even
+  static constexpr int POS = 2 * C * 4;              // bytes of one window position [y&1][C]
+  static constexpr int P = WX * POS;                 // pitch of one row pair
+  static constexpr uint32_t BYTES = (WY / 2) * P;    // 32 KB (C = 8), 64 KB (C = 16)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,9 +75,10 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   }
   __syncwarp();
 }
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -100,47 +103,46 @@ struct Lane {
 // One tap (4 corners x 8 channels of this lane) from the staged window: sA / sB receive the bilinear sample of the lane's
 // two channel quads (quad A = the one read in rounds with i0 = 0).  (lx, ly) = integer tap position relative to the window
 // origin (both rows / columns inside the window), (fx, fy) = fractional parts.
-// C = 8 : bank group of piece (x, y, quad) = (4y + 2x + quad) mod 8: bit0 = quad, bit1 = x&1, bit2 = ((x>>1)&1) ^ (y&1).
-//         Round (i2,i1,i0) of lane (b2,b1,b0) reads group (i2^b2, i1^b1, i0^b0):
-//           dx = i1 ^ b1 ^ xodd,  dy = i2 ^ b2 ^ ((lx>>1)&1) ^ yodd ^ (dx & xodd),  quad = i0 ^ b0 (folded into base[]).
-// C = 16: bank group of piece (x, y, quarter) = (4y + 4x + quarter) mod 8: bits 0-1 = quarter, bit2 = (x&1) ^ (y&1).  A lane
-//         owns quarters {2k, 2k+1} (k = lane & 1).  Round (ia,ib,ic): dx = ic, dy = ia ^ ic ^ b2 ^ xodd ^ yodd, low quarter
-//         bit = ib ^ b1 (folded into base[]).
+// C = 8 : position = [y&1][8 ch] = 64 B; 16-byte bank group of a piece = (x&1)<<2 | (y&1)<<1 | quad.
+// C = 16: position = [y&1][16 ch] = 128 B (one line); bank group = (y&1)<<2 | channel quarter; a lane owns quarters
+//         {2k, 2k+1} (k = lane & 1 is the "b0" group bit here, the x corner is a compile-time round bit).
 template <int C>
 __device__ __forceinline__ void gather_window(const Lane& L, int lx, int ly, float fx, float fy, float4& sA, float4& sB) {
   using K = Cfg<C>;
   const float gx = 1.0f - fx, gy = 1.0f - fy;
-  const bool xodd = lx & 1, yodd = ly & 1;
-  const uint32_t Y0 = (uint32_t)ly * K::PITCH + (uint32_t)lx * K::TEX, Y1 = Y0 + K::PITCH;   // tap origin in row ly / ly + 1
+  const bool yodd = ly & 1;
+  // byte offsets (window-relative) of the even-parity and odd-parity source row of this tap
+  const uint32_t rE = (uint32_t)((ly + 1) >> 1) * K::P;
+  const uint32_t rO = (uint32_t)(ly >> 1) * K::P + C * 4;
+  const float wE = yodd ? fy : gy, wO = yodd ? gy : fy;   // weight of the even / odd row
   if (C == 8) {
-    const bool a = (lx >> 1) & 1;
-    const bool b = L.b1 != xodd;                               // dx of the rounds with i1 = 0
-    const bool e0 = ((L.b2 != a) != yodd) != (b && xodd);      // dy of round (i2 = 0, i1 = 0)
-    const bool e1 = ((L.b2 != a) != yodd) != (!b && xodd);     // dy of round (i2 = 0, i1 = 1)
-    const uint32_t X0 = b ? K::TEX : 0, X1 = b ? 0 : K::TEX;
-    const float wx0 = b ? fx : gx, wx1 = b ? gx : fx;
-    const uint32_t R00 = (e0 ? Y1 : Y0) + X0, R10 = (e0 ? Y0 : Y1) + X0;   // R[i2][i1]
-    const uint32_t R01 = (e1 ? Y1 : Y0) + X1, R11 = (e1 ? Y0 : Y1) + X1;
-    const float w00 = wx0 * (e0 ? fy : gy), w10 = wx0 * (e0 ? gy : fy);
-    const float w01 = wx1 * (e1 ? fy : gy), w11 = wx1 * (e1 ? gy : fy);
-    const float4 a0 = lds128(R00 + L.base[0]), b0 = lds128(R00 + L.base[1]);
-    const float4 a1 = lds128(R01 + L.base[0]), b1 = lds128(R01 + L.base[1]);
-    const float4 a2 = lds128(R10 + L.base[0]), b2 = lds128(R10 + L.base[1]);
-    const float4 a3 = lds128(R11 + L.base[0]), b3 = lds128(R11 + L.base[1]);
+    const bool xodd = lx & 1;
+    const uint32_t cE = (uint32_t)((lx + 1) & ~1) * K::POS, cO = (uint32_t)(lx | 1) * K::POS;
+    const float vE = xodd ? fx : gx, vO = xodd ? gx : fx;  // weight of the even / odd column
+    // rounds: i2 selects the x parity (XOR b2), i1 the y parity (XOR b1), i0 the channel quad (XOR b0, folded in base[])
+    const uint32_t X0 = L.b2 ? cO : cE, X1 = L.b2 ? cE : cO;
+    const float wx0 = L.b2 ? vO : vE, wx1 = L.b2 ? vE : vO;
+    const uint32_t R0 = L.b1 ? rO : rE, R1 = L.b1 ? rE : rO;
+    const float wy0 = L.b1 ? wO : wE, wy1 = L.b1 ? wE : wO;
+    const float w00 = wx0 * wy0, w01 = wx0 * wy1, w10 = wx1 * wy0, w11 = wx1 * wy1;
+    const float4 a0 = lds128(X0 + R0 + L.base[0]), b0 = lds128(X0 + R0 + L.base[1]);
+    const float4 a1 = lds128(X0 + R1 + L.base[0]), b1 = lds128(X0 + R1 + L.base[1]);
+    const float4 a2 = lds128(X1 + R0 + L.base[0]), b2 = lds128(X1 + R0 + L.base[1]);
+    const float4 a3 = lds128(X1 + R1 + L.base[0]), b3 = lds128(X1 + R1 + L.base[1]);
     fma4(sA, w00, a0); fma4(sB, w00, b0);
     fma4(sA, w01, a1); fma4(sB, w01, b1);
     fma4(sA, w10, a2); fma4(sB, w10, b2);
     fma4(sA, w11, a3); fma4(sB, w11, b3);
   } else {
-    const bool e = (L.b2 != xodd) != yodd;                     // dy of the rounds with ia ^ ic = 0
-    const uint32_t U0 = e ? Y1 : Y0, U1 = e ? Y0 : Y1;         // row of rounds with ia ^ ic = 0 / 1
-    const float v0 = e ? fy : gy, v1 = e ? gy : fy;
-    // (ia, ic): (0,0) -> U0, dx 0 | (0,1) -> U1, dx 1 | (1,0) -> U1, dx 0 | (1,1) -> U0, dx 1
-    const float w00 = gx * v0, w01 = fx * v1, w10 = gx * v1, w11 = fx * v0;
-    const float4 a0 = lds128(U0 + L.base[0]), b0 = lds128(U0 + L.base[1]);
-    const float4 a1 = lds128(U1 + L.base[0] + K::TEX), b1 = lds128(U1 + L.base[1] + K::TEX);
-    const float4 a2 = lds128(U1 + L.base[0]), b2 = lds128(U1 + L.base[1]);
-    const float4 a3 = lds128(U0 + L.base[0] + K::TEX), b3 = lds128(U0 + L.base[1] + K::TEX);
+    // C == 16: x corner = compile-time (both columns are whole lines), y parity XOR b2, low quarter bit XOR b1
+    const uint32_t c0 = (uint32_t)lx * K::POS;
+    const uint32_t R0 = (L.b2 ? rO : rE) + c0, R1 = (L.b2 ? rE : rO) + c0;
+    const float wy0 = L.b2 ? wO : wE, wy1 = L.b2 ? wE : wO;
+    const float w00 = gx * wy0, w01 = gx * wy1, w10 = fx * wy0, w11 = fx * wy1;
+    const float4 a0 = lds128(R0 + L.base[0]), b0 = lds128(R0 + L.base[1]);
+    const float4 a1 = lds128(R1 + L.base[0]), b1 = lds128(R1 + L.base[1]);
+    const float4 a2 = lds128(R0 + L.base[0] + K::POS), b2 = lds128(R0 + L.base[1] + K::POS);
+    const float4 a3 = lds128(R1 + L.base[0] + K::POS), b3 = lds128(R1 + L.base[1] + K::POS);
     fma4(sA, w00, a0); fma4(sB, w00, b0);
     fma4(sA, w01, a1); fma4(sB, w01, b1);
     fma4(sA, w10, a2); fma4(sB, w10, b2);
@@ -184,12 +186,11 @@ struct Shared {
   int bbox[2][4];   // double-buffered {min x0, max x0, min y0, max y0} of the current window's taps
 };
 
-// Stages one window: reduces the bounding box of the CTA's taps, centres the WX x WY window on it, issues its rows as bulk
-// asynchronous copies (warp 0: one row per lane), zero-fills whatever lies outside the image and waits for the data.
-// Returns the window origin to every thread.  `slot` alternates per call.  src = feature map of the view, [H][W][C].
+// Stages one window: reduces the bounding box of the CTA's taps, centres the WX x WY box on it, issues the TMA load and
+// waits for it.  Returns the window origin (ox, oy even) to every thread.  `slot` alternates per call.
 template <int C>
-__device__ __forceinline__ void stage_window(const float* __restrict__ src, Shared& sh, uint32_t win, int slot, uint32_t& phase,
-                                             int H, int W, int mnx, int mxx, int mny, int mxy, int& ox, int& oy) {
+__device__ __forceinline__ void stage_window(const CUtensorMap* map, Shared& sh, uint32_t win, int slot, uint32_t& phase, int view,
+                                             int mnx, int mxx, int mny, int mxy, int& ox, int& oy) {
   using K = Cfg<C>;
   mnx = __reduce_min_sync(0xffffffffu, mnx);
   mxx = __reduce_max_sync(0xffffffffu, mxx);
@@ -207,37 +208,16 @@ __device__ __forceinline__ void stage_window(const float* __restrict__ src, Shar
   else {
     const int slack_x = K::WX - (bx1 + 2 - bx0), slack_y = K::WY - (by1 + 2 - by0);
     ox = bx0 - (slack_x > 0 ? slack_x / 2 : 0);
-    oy = by0 - (slack_y > 0 ? slack_y / 2 : 0);
+    oy = (by0 - (slack_y > 0 ? slack_y / 2 : 0)) & ~1;
   }
-  // the part of the window that lies inside the image (columns [x_lo, x_hi), rows [y_lo, y_hi))
-  const int x_lo = max(ox, 0), x_hi = min(ox + K::WX, W), y_lo = max(oy, 0), y_hi = min(oy + K::WY, H);
-  const bool any = x_hi > x_lo && y_hi > y_lo;
-  const uint32_t bar = smem_u32(&sh.bar);
-  if (threadIdx.x < 32) {
-    const int r = threadIdx.x;          // window row
-    if (r == 0) {
-      sh.bbox[slot ^ 1][0] = INT_MAX; sh.bbox[slot ^ 1][1] = INT_MIN;   // reset the other slot for the next window
-      sh.bbox[slot ^ 1][2] = INT_MAX; sh.bbox[slot ^ 1][3] = INT_MIN;
-      const uint32_t total = any ? (uint32_t)(y_hi - y_lo) * (uint32_t)(x_hi - x_lo) * K::TEX : 0u;
-      expect_tx(bar, total);
-    }
-    __syncwarp();
-    const int y = oy + r;
-    if (any && r < K::WY && y >= y_lo && y < y_hi)
-      bulk_load(win + (uint32_t)r * K::PITCH + (uint32_t)(x_lo - ox) * K::TEX, src + ((size_t)y * W + x_lo) * C,
-                (uint32_t)(x_hi - x_lo) * K::TEX, bar);
+  if (threadIdx.x == 0) {
+    sh.bbox[slot ^ 1][0] = INT_MAX; sh.bbox[slot ^ 1][1] = INT_MIN;   // reset the other slot for the next window
+    sh.bbox[slot ^ 1][2] = INT_MAX; sh.bbox[slot ^ 1][3] = INT_MIN;
+    const uint32_t bar = smem_u32(&sh.bar);
+    expect_tx(bar, K::BYTES);
+    tma_load_5d(win, map, 0, 0, ox, oy >> 1, view, bar);
   }
-  if (!(any && x_lo == ox && x_hi == ox + K::WX && y_lo == oy && y_hi == oy + K::WY)) {
-    // border window (CTA-uniform, rare): zero everything the copies do not write (disjoint from what they write)
-    for (int i = threadIdx.x; i < K::WY * (K::ROWB / 16); i += THREADS) {
-      const int r = i / (K::ROWB / 16), u = i % (K::ROWB / 16);
-      const int x = ox + (u * 16) / K::TEX, y = oy + r;
-      if (!any || y < y_lo || y >= y_hi || x < x_lo || x >= x_hi)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(win + (uint32_t)r * K::PITCH + (uint32_t)u * 16), "r"(0) : "memory");
-    }
-    __syncthreads();
-  }
-  mbar_wait_warp(bar, phase);
+  mbar_wait_warp(smem_u32(&sh.bar), phase);
   phase ^= 1;
 }
 
@@ -246,8 +226,7 @@ template <int C>
 struct ViewCtx {
   Hom m;
   float rx, ry, rz;
-  const float* src;    // feature map of the source view [H][W][C]
-  const float* srcA;   // + first channel of the lane's quad A / quad B (global fallback)
+  const float* srcA;
   const float* srcB;
 };
 
@@ -257,8 +236,8 @@ struct ViewCtx {
 // and move monotonically with the (monotone) hypotheses, so those two bound the rest; a tap that still falls outside the
 // window (non-monotone caller-supplied hypotheses, depth outliers of neighbours) goes through global memory.
 template <int C, int DCHT, typename F>
-__device__ __forceinline__ void process_chunk(Shared& sh, uint32_t win, int& slot, uint32_t& phase,
-                                              const Lane& L, const ViewCtx<C>& vc, const float* __restrict__ depth_p,
+__device__ __forceinline__ void process_chunk(const CUtensorMap* map, Shared& sh, uint32_t win, int& slot, uint32_t& phase,
+                                              const Lane& L, const ViewCtx<C>& vc, int view, const float* __restrict__ depth_p,
                                               int HW, int d0, int n, bool active, const CoordConst& cc, int W, int H, F&& consume) {
   using K = Cfg<C>;
   float ix, iy;
@@ -275,7 +254,7 @@ __device__ __forceinline__ void process_chunk(Shared& sh, uint32_t win, int& slo
   if (tF.inb) { mnx = mxx = tF.x0; mny = mxy = tF.y0; }
   if (tL.inb) { mnx = min(mnx, tL.x0); mxx = max(mxx, tL.x0); mny = min(mny, tL.y0); mxy = max(mxy, tL.y0); }
   int ox, oy;
-  stage_window<C>(vc.src, sh, win, slot, phase, H, W, mnx, mxx, mny, mxy, ox, oy);
+  stage_window<C>(map, sh, win, slot, phase, view, mnx, mxx, mny, mxy, ox, oy);
   slot ^= 1;
 #pragma unroll
   for (int k = 0; k < DCHT; ++k) {
@@ -311,7 +290,7 @@ __device__ __forceinline__ void process_chunk(Shared& sh, uint32_t win, int& slo
 // ----------------------------------------------------------------------------------------------------------------------
 template <int C, int MODE, int DCHT, bool GENERIC>
 __global__ void __launch_bounds__(THREADS, (C == 8 && (MODE == 0 || (DCHT == 4 && MVSF_WT_PASSB_BLOCKS == 3))) ? 3 : 2)
-warp_tile_kernel(const float* __restrict__ feat, const float* __restrict__ homs,
+warp_tile_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ feat, const float* __restrict__ homs,
                  const float* __restrict__ depth, const float* __restrict__ vis, float* __restrict__ out, int V, int D, int H,
                  int W, int dch) {
   using K = Cfg<C>;
@@ -362,9 +341,8 @@ warp_tile_kernel(const float* __restrict__ feat, const float* __restrict__ homs,
     vc.rx = __fadd_rn(fmaf(vc.m.r01, fyp, __fmul_rn(vc.m.r00, fxp)), vc.m.r02);
     vc.ry = __fadd_rn(fmaf(vc.m.r11, fyp, __fmul_rn(vc.m.r10, fxp)), vc.m.r12);
     vc.rz = __fadd_rn(fmaf(vc.m.r21, fyp, __fmul_rn(vc.m.r20, fxp)), vc.m.r22);
-    vc.src = feat + (size_t)(v + 1) * HW * C;
-    vc.srcA = vc.src + chA;
-    vc.srcB = vc.src + chB;
+    vc.srcA = feat + (size_t)(v + 1) * HW * C + chA;
+    vc.srcB = feat + (size_t)(v + 1) * HW * C + chB;
     return vc;
   };
 
@@ -376,7 +354,7 @@ warp_tile_kernel(const float* __restrict__ feat, const float* __restrict__ homs,
       float mx = -FLT_MAX;
       for (int d0 = 0; d0 < D; d0 += dch) {
         const int n = min(dch, D - d0);
-        process_chunk<C, DCHT>(sh, win, slot, phase, L, vc, depth_p, HW, d0, n, active, cc, W, H,
+        process_chunk<C, DCHT>(&map, sh, win, slot, phase, L, vc, v + 1, depth_p, HW, d0, n, active, cc, W, H,
                                [&](int k, const float4& sA, const float4& sB) {
                                  float s = dot4(rA, sA) + dot4(rB, sB);
                                  if (K::LPX == 2) s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -417,7 +395,7 @@ warp_tile_kernel(const float* __restrict__ feat, const float* __restrict__ homs,
       for (int v = 0; v < V - 1; ++v) {
         const ViewCtx<C> vc = make_view(v);
         const float w = __ldg(vis + (size_t)v * HW + p);
-        process_chunk<C, DCHT>(sh, win, slot, phase, L, vc, depth_p, HW, d0, n, active, cc, W, H,
+        process_chunk<C, DCHT>(&map, sh, win, slot, phase, L, vc, v + 1, depth_p, HW, d0, n, active, cc, W, H,
                                [&](int k, const float4& sA, const float4& sB) {
                                  // group correlation of this view (cost_volume.py:78-85) times its weight (:97)
                                  accA[k].x = fmaf(qA.x * sA.x, w, accA[k].x); accA[k].y = fmaf(qA.y * sA.y, w, accA[k].y);
@@ -447,6 +425,39 @@ warp_tile_kernel(const float* __restrict__ feat, const float* __restrict__ homs,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 5-D view (c, y&1, x, y/2, view) of the channels-last feature tensor [V][H][W][C] (H even)
+template <int C>
+static int make_window_map(CUtensorMap* m, const float* feat, int V, int H, int W) {
+  using K = Cfg<C>;
+  EncodeTiledFn enc = encode_tiled_fn();
+  MVSF_REQUIRE(enc, "warp_tile: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t row = (cuuint64_t)W * C * 4;
+  const cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)W, (cuuint64_t)(H / 2), (cuuint64_t)V};
+  const cuuint64_t strides[4] = {row, (cuuint64_t)C * 4, 2 * row, (cuuint64_t)H * row};
+  const cuuint32_t box[5] = {(cuuint32_t)C, 2, (cuuint32_t)K::WX, (cuuint32_t)(K::WY / 2), 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(feat), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MVSF_ERR_CUDA, "warp_tile: cuTensorMapEncodeTiled failed (%d) for V=%d H=%d W=%d C=%d", (int)r, V, H, W, C);
+  return MVSF_OK;
+}
+
 template <int C, int MODE, int DCHT, bool GENERIC>
 static int launch(const float* feat, const float* homs, const float* depth, const float* vis, float* out, int V, int D, int H,
                   int W, int dch, cudaStream_t s) {
@@ -459,8 +470,11 @@ static int launch(const float* feat, const float* homs, const float* depth, cons
     MVSF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     once.done(dev);
   }
+  CUtensorMap map;
+  int rc = make_window_map<C>(&map, feat, V, H, W);
+  if (rc) return rc;
   dim3 grid(cdiv(W, TW), cdiv(H, K::TROWS));
-  kern<<<grid, THREADS, smem, s>>>(feat, homs, depth, vis, out, V, D, H, W, dch);
+  kern<<<grid, THREADS, smem, s>>>(map, feat, homs, depth, vis, out, V, D, H, W, dch);
   return MVSF_OK;
 }
 
@@ -482,10 +496,11 @@ static int dispatch(int mode, const float* feat, const float* homs, const float*
 
 }  // namespace wt
 
-// Used by warp_corr.cu's entry points.  Returns false when this organisation does not apply (other channel counts,
-// misaligned pointers: the bulk copies need 16-byte aligned row segments).
+// Used by warp_corr.cu's entry points.  Returns false when this organisation does not apply (other channel counts, odd H:
+// the y-parity view of the tensor map needs an even number of rows, misaligned pointers).
 bool warp_tile_supported(const float* feat, int C, int G, int D, int H, int W) {
-  return (C == 8 || C == 16) && G == 8 && H >= 2 && W >= 2 && D >= 1 && D <= wt::kMaxD && ((uintptr_t)feat & 15) == 0;
+  return (C == 8 || C == 16) && G == 8 && (H % 2 == 0) && H >= 2 && W >= 2 && D >= 1 && D <= wt::kMaxD &&
+         ((uintptr_t)feat & 15) == 0 && ((long long)W * C * 4) % 16 == 0;
 }
 // pass A: entropy [V-1][H][W]
 int warp_tile_entropy(const float* feat, const float* homs, const float* depth, float* entropy, int V, int C, int D, int H,

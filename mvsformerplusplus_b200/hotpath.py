@@ -202,9 +202,10 @@ class StageNet(_PackedMixin, nn.Module):
         entropy = torch.empty((V - 1, H, W), **f32)
         vis = torch.empty((V - 1, H, W), **f32)
         volume = torch.empty((D, H, W, G), **f32)
-        spill_bytes = 4 * (V - 1) * D * H * W * G
-        two_gathers = L.mvsf_warp_corr_plan(C, G, D, H, W) == 1   # fine stages: TMA-staged window kernels, no spill
-        if G == 8 and not two_gathers and spill_bytes <= self.corr_spill_budget_bytes:
+        # spill plan (pass A stores the per-view group correlations, the aggregation streams them) unless the buffer would
+        # exceed the budget: then both passes gather (TMA-staged window kernels at C = 8 / 16), no intermediate buffer
+        two_gathers = L.mvsf_warp_corr_plan(C, G, D, H, W, V, ctypes.c_size_t(self.corr_spill_budget_bytes)) == 1
+        if not two_gathers:
             # pass A also stores the per-view group correlations; the view aggregation then streams them (no second gather)
             corr = torch.empty((V - 1, D, H, W, G), **f32)
             _lib.check(L.mvsf_warp_corr_entropy_store(_ptr(feat_nhwc), _ptr(homs), _ptr(depth_values), _ptr(entropy),

@@ -171,3 +171,29 @@ def test_homo_warping_seam_python_signature():
     w3, _ = homo_warping_3D_with_mask(g["src"].to(dev), g["src_proj"].to(dev), g["ref_proj"].to(dev),
                                       dv2.view(B, D, 1, 1).expand(B, D, H, W).to(dev))
     assert torch.equal(w2, w3)
+
+
+def test_stage_without_spill_buffer_matches_spill_plan():
+    """corr_spill_budget_bytes = 0 makes StageNet run the cost volume as two gathers (window kernels at C = 8 / 16, the
+    L1-gather kernels at C = 32 / 64) instead of spilling the per-view correlations: same outputs, no [(V-1),D,H,W,8] buffer."""
+    from mvsformerplusplus_b200 import hotpath, synth
+    from mvsformerplusplus_b200.config import default_args
+    dev = torch.device("cuda:0")
+    V, H, W = 4, 96, 128
+    feats = {k: v.to(dev) for k, v in synth.make_features(V, H, W, seed=2).items()}
+    proj = {k: v.to(dev) for k, v in synth.make_proj_matrices(V, H, W, theta_step=0.12).items()}
+    dv = synth.make_depth_values(48, 425.0, 2.65 * 4).to(dev)
+    outs = []
+    for budget in (None, 0):
+        args = default_args()
+        if budget is not None:
+            args["corr_spill_budget_bytes"] = budget
+        torch.manual_seed(0)
+        net = hotpath.HotPathNet(args).eval()
+        synth.randomize_state_dict(net, seed=29)
+        outs.append(net.to(dev).forward_features(feats, proj, dv, TMP))
+    e = dict(depth_rel=rel_linf(outs[1]["refined_depth"].cpu(), outs[0]["refined_depth"].cpu()),
+             prob4=max_abs(outs[1]["stage4"]["prob_volume"].cpu(), outs[0]["stage4"]["prob_volume"].cpu()),
+             prob1=max_abs(outs[1]["stage1"]["prob_volume"].cpu(), outs[0]["stage1"]["prob_volume"].cpu()))
+    rec("two_gather_plan_vs_spill_plan", **e)
+    assert e["depth_rel"] < 1e-4 and e["prob4"] < 5e-5 and e["prob1"] < 5e-5

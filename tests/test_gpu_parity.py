@@ -154,7 +154,7 @@ COST_CASES = [  # C, D, H, W, V, theta_step, depth jitter
     (8, 4, 31, 45, 3, 0.6, 0.02),   # wide baseline: many taps leave the image (zero padding per corner)
     (8, 48, 10, 14, 3, 0.1, 0.02),  # generic-D path (D-sweep configuration)
     (64, 8, 9, 11, 2, 0.1, 0.02),
-    # more shapes for the TMA-staged window kernels (every C = 8 / 16 case uses them): several tiles, ragged right / bottom edges,
+    # shapes served by the TMA-staged window kernels (C = 8 / 16, even H): several tiles, ragged right / bottom edges,
     # taps leaving the image, depth outliers that leave the staged window (global fallback), D = 4 / 8 / chunked D
     (8, 4, 64, 96, 3, 0.1, 0.02), (8, 4, 30, 44, 5, 0.6, 0.02), (8, 4, 48, 80, 3, 0.15, 0.4), (8, 8, 16, 40, 3, 0.1, 0.02),
     (8, 7, 18, 34, 2, 0.1, 0.02), (16, 8, 32, 48, 4, 0.1, 0.02), (16, 8, 28, 68, 3, 0.5, 0.3), (16, 4, 12, 20, 3, 0.1, 0.02),
@@ -208,8 +208,9 @@ def test_cost_volume_kernels(dev, L, C, D, H, W, V, th, jit):
     assert torch.equal(ent_s, ent)
     e_paths = max_abs(vol_s.cpu(), vol.cpu())
     assert e_paths <= 2e-6 * vol_scale, e_paths   # identical up to the pair sum of 8-channel groups
-    tiled = L.mvsf_warp_corr_plan(C, 8, D, H, W) == 1
-    assert tiled == (C in (8, 16))
+    assert L.mvsf_warp_corr_plan(C, 8, D, H, W, V, ctypes.c_size_t(1 << 40)) == 0      # room for the spill buffer: spill plan
+    assert L.mvsf_warp_corr_plan(C, 8, D, H, W, V, ctypes.c_size_t(1024)) == 1         # no room: two gathers
+    tiled = C in (8, 16) and H % 2 == 0    # shapes the window kernels serve
     e_tile = {}
     if tiled:   # the organisation hotpath.py uses for these shapes
         ent_t, vis_t, vol_t = run_two_gathers()
