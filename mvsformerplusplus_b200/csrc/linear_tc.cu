@@ -58,10 +58,20 @@ __device__ __forceinline__ void store_split16(__half* c2row, int N, int col, con
 // The weight tiles of all K-blocks stay resident in shared memory for the CTA's lifetime; accumulators are double
 // buffered in TMEM (2 x N columns) so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 // mbarriers: empty[s] (MMAs that read stage s finished -> refill), acc_full[b] / acc_empty[b] (accumulator hand-over).
-constexpr int TC_NPROD = 128, TC_NEPI = 256;  // two epilogue warpgroups: even / odd tiles (= the two TMEM buffers)
+// Two epilogue groups: even / odd tiles (= the two TMEM buffers).  Element-wise epilogues (bias / GELU / ELU+1 / residual)
+// use 8 warps per group - two warps per TMEM lane quarter, each taking half of the N columns: those epilogues are bound by
+// instruction issue (erf, fp16 hi|lo split: ~30 instructions per element), and 16 epilogue warps keep all four schedulers
+// busy; the LayerNorm epilogues need a whole row per thread (and ~130-170 registers), they keep 4 warps per group.
+constexpr int TC_NPROD = 128;
+template <int EPI> struct TcCfg {
+  static constexpr bool LN = (EPI == LIN_RES_LN || EPI == LIN_LN);
+  static constexpr int WPG = LN ? 4 : 8;          // epilogue warps per group
+  static constexpr int NEPI = 2 * WPG * 32;
+  static constexpr int THREADS = TC_NPROD + NEPI;
+};
 
 template <int EPI>
-__device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t tacc, int m0, int warp4, int lane) {
+__device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t tacc, int m0, int warp4, int lane, int c_begin, int c_end) {
   const int N = a.N;
   const int row = warp4 * 32 + lane;
   const int m = m0 + row;
@@ -109,7 +119,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t ta
       }
     }
   } else {
-    for (int c = 0; c < N / 16; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       float v[16];
       tmem_ld16(trow + c * 16, v);
 #pragma unroll
@@ -136,8 +146,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t ta
 constexpr int TC_RING = 3;
 
 template <int EPI>
-__global__ void __launch_bounds__(TC_NPROD + TC_NEPI, 1)
+__global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1)
 linear_tc_kernel(TcLinArgs a) {
+  constexpr int WPG = TcCfg<EPI>::WPG, NTHREADS = TcCfg<EPI>::THREADS;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = a.N, K = a.K;
@@ -155,14 +166,14 @@ linear_tc_kernel(TcLinArgs a) {
   if (tid == 0) {
     for (int i = 0; i < TC_RING; ++i) mbar_init(bar_empty + 8 * i, 1);
     mbar_init(bar_accf + 0, 1); mbar_init(bar_accf + 8, 1);
-    mbar_init(bar_acce + 0, 128); mbar_init(bar_acce + 8, 128);
+    mbar_init(bar_acce + 0, WPG * 32); mbar_init(bar_acce + 8, WPG * 32);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), ncols);
   // resident weights: all K-blocks, hi and lo
   for (int kb = 0; kb < nkb; ++kb) {
-    fill_tile<TC_NPROD + TC_NEPI>(sB + (2 * kb) * b_bytes, a.Bh + kb * TC_BK, a.ldb, N, N, tid);
-    fill_tile<TC_NPROD + TC_NEPI>(sB + (2 * kb + 1) * b_bytes, a.Bl + kb * TC_BK, a.ldb, N, N, tid);
+    fill_tile<NTHREADS>(sB + (2 * kb) * b_bytes, a.Bh + kb * TC_BK, a.ldb, N, N, tid);
+    fill_tile<NTHREADS>(sB + (2 * kb + 1) * b_bytes, a.Bl + kb * TC_BK, a.ldb, N, N, tid);
   }
   cp_async_commit_group();
   cp_async_wait_group<0>();
@@ -232,14 +243,19 @@ linear_tc_kernel(TcLinArgs a) {
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int warp4 = warp & 3;         // the TMEM lane quarter this warp may access
-    const int grp = (warp - 4) >> 2;    // epilogue warpgroup 0 drains buffer 0 (even tiles), group 1 buffer 1 (odd tiles)
+    const int ew = warp - 4;
+    const int grp = ew / WPG;           // epilogue group 0 drains buffer 0 (even tiles), group 1 buffer 1 (odd tiles)
+    const int part = (ew % WPG) >> 2;   // which share of the columns (element-wise epilogues: 2 warps per lane quarter)
+    const int nchunks = N / 16;
+    const int c_begin = (WPG == 8) ? (part ? (nchunks + 1) / 2 : 0) : 0;
+    const int c_end = (WPG == 8) ? (part ? nchunks : (nchunks + 1) / 2) : nchunks;
     int tile_it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
       const int buf = tile_it & 1;
       if (buf != grp) continue;
       mbar_wait(bar_accf + 8 * buf, (uint32_t)((tile_it >> 1) & 1));
       tc_fence_after_sync();
-      tc_epilogue_tile<EPI>(a, tmem_base + (uint32_t)(buf * N), tile * TC_BM, warp4, lane);
+      tc_epilogue_tile<EPI>(a, tmem_base + (uint32_t)(buf * N), tile * TC_BM, warp4, lane, c_begin, c_end);
       tc_fence_before_sync();
       mbar_arrive(bar_acce + 8 * buf);
     }
@@ -279,14 +295,13 @@ int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
   }
   const int ntiles = cdiv(a.M, TC_BM);
   dim3 grid(ntiles < num_sms ? ntiles : num_sms);  // persistent: one CTA per SM, tiles strided by gridDim.x
-  constexpr int TC_THREADS2 = TC_NPROD + TC_NEPI;
   switch (epi) {
-    case LIN_BIAS: linear_tc_kernel<LIN_BIAS><<<grid, TC_THREADS2, smem, s>>>(a); break;
-    case LIN_GELU: linear_tc_kernel<LIN_GELU><<<grid, TC_THREADS2, smem, s>>>(a); break;
-    case LIN_ELU1: linear_tc_kernel<LIN_ELU1><<<grid, TC_THREADS2, smem, s>>>(a); break;
-    case LIN_RES: linear_tc_kernel<LIN_RES><<<grid, TC_THREADS2, smem, s>>>(a); break;
-    case LIN_RES_LN: linear_tc_kernel<LIN_RES_LN><<<grid, TC_THREADS2, smem, s>>>(a); break;
-    case LIN_LN: linear_tc_kernel<LIN_LN><<<grid, TC_THREADS2, smem, s>>>(a); break;
+    case LIN_BIAS: linear_tc_kernel<LIN_BIAS><<<grid, TcCfg<LIN_BIAS>::THREADS, smem, s>>>(a); break;
+    case LIN_GELU: linear_tc_kernel<LIN_GELU><<<grid, TcCfg<LIN_GELU>::THREADS, smem, s>>>(a); break;
+    case LIN_ELU1: linear_tc_kernel<LIN_ELU1><<<grid, TcCfg<LIN_ELU1>::THREADS, smem, s>>>(a); break;
+    case LIN_RES: linear_tc_kernel<LIN_RES><<<grid, TcCfg<LIN_RES>::THREADS, smem, s>>>(a); break;
+    case LIN_RES_LN: linear_tc_kernel<LIN_RES_LN><<<grid, TcCfg<LIN_RES_LN>::THREADS, smem, s>>>(a); break;
+    case LIN_LN: linear_tc_kernel<LIN_LN><<<grid, TcCfg<LIN_LN>::THREADS, smem, s>>>(a); break;
     default: return fail(MVSF_ERR_INVALID, "linear_tc: unknown epilogue %d", epi);
   }
   MVSF_LAUNCH_CHECK("linear_tc");
