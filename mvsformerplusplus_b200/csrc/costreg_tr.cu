@@ -151,10 +151,11 @@ static int run_attention(const float* qkv, float* o, __half* o2, __half* tiled, 
     once.done(dev);
   }
   cudaEvent_t kt = ktimer_enabled() ? ktimer_begin("attention_tc", s) : nullptr;
+  const dim3 grid(cdiv(ntiles, 2), 4);
   if (g_attention_plo)
-    attention_fa_kernel<true><<<dim3(cdiv(ntiles, 2), 4), fa6::THREADS, fa6::SMEM, s>>>(tiled, o, o2, N, ntiles);
+    attention_fa_kernel<true><<<grid, fa6::THREADS, fa6::SMEM, s>>>(tiled, o, o2, N, ntiles);
   else
-    attention_fa_kernel<false><<<dim3(cdiv(ntiles, 2), 4), fa6::THREADS, fa6::SMEM, s>>>(tiled, o, o2, N, ntiles);
+    attention_fa_kernel<false><<<grid, fa6::THREADS, fa6::SMEM, s>>>(tiled, o, o2, N, ntiles);
   if (kt) ktimer_end(kt, s);
   MVSF_LAUNCH_CHECK("attention_tc");
   return MVSF_OK;
@@ -253,7 +254,7 @@ int mvsf_costreg_tr_forward(float* volume, const float* pos, const float* wts, c
 
 /* Softmax attention alone (attention.py:141-170): qkv [N][3][4][16] fp32 -> out [N][64].  workspace >= N*768 bytes. */
 int mvsf_attention_set_precision(int p_lo) {
-  g_attention_plo = p_lo != 0;
+  g_attention_plo = p_lo != 0;   // 0: fp16 P (default) | 1: fp16 hi+lo P (round 1)
   return MVSF_OK;
 }
 

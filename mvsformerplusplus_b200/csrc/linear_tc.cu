@@ -83,14 +83,16 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t ta
   if (EPI == LIN_RES_LN || EPI == LIN_LN) {  // N == 64: the whole row lives in this thread's registers
     float x[64];
     float s = 0.f;
+    uint32_t raw[4][16];                 // the whole accumulator row in flight, one wait
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld16_nowait(trow + c * 16, raw[c]);
+    tmem_ld_wait();
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      float v[16];
-      tmem_ld16(trow + c * 16, v);
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int col = c * 16 + e;
-        float t = v[e] + (a.bias ? __ldg(a.bias + col) : 0.f);
+        float t = __uint_as_float(raw[c][e]) + (a.bias ? __ldg(a.bias + col) : 0.f);
         if (EPI == LIN_RES_LN) t = (mvalid ? resrow[col] : 0.f) + __ldg(a.gamma + col) * t;
         x[col] = t;
         s += t;
@@ -119,13 +121,15 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t ta
       }
     }
   } else {
-    for (int c = c_begin; c < c_end; ++c) {
+    // software pipeline over the 16-column chunks: the tensor-memory load of chunk c+1 is in flight while chunk c is
+    // processed (a tcgen05.ld + wait costs a few hundred cycles; issued back to back they dominated the epilogue).
+    // Two named register buffers, chunks handled in pairs (a dynamically indexed buffer would live in local memory).
+    auto process = [&](int c, const uint32_t (&raw)[16]) {
       float v[16];
-      tmem_ld16(trow + c * 16, v);
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int col = c * 16 + e;
-        float t = v[e] + (a.bias ? __ldg(a.bias + col) : 0.f);
+        float t = __uint_as_float(raw[e]) + (a.bias ? __ldg(a.bias + col) : 0.f);
         if (EPI == LIN_GELU) t = gelu_erf(t);
         if (EPI == LIN_ELU1) t = (col < a.elu_cols) ? ((t > 0.f ? t : expm1f(t)) + 1.0f) : t;
         if (EPI == LIN_RES) t = (mvalid ? resrow[col] : 0.f) + __ldg(a.gamma + col) * t;
@@ -138,6 +142,18 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t ta
             *reinterpret_cast<float4*>(crow + c * 16 + e * 4) = make_float4(v[e * 4], v[e * 4 + 1], v[e * 4 + 2], v[e * 4 + 3]);
         }
         if (c2row) store_split16(c2row, N, c * 16, v);
+      }
+    };
+    uint32_t rawA[16], rawB[16];
+    if (c_begin < c_end) tmem_ld16_nowait(trow + c_begin * 16, rawA);
+    for (int c = c_begin; c < c_end; c += 2) {
+      tmem_ld_wait();
+      if (c + 1 < c_end) tmem_ld16_nowait(trow + (c + 1) * 16, rawB);
+      process(c, rawA);
+      if (c + 1 < c_end) {
+        tmem_ld_wait();
+        if (c + 2 < c_end) tmem_ld16_nowait(trow + (c + 2) * 16, rawA);
+        process(c + 1, rawB);
       }
     }
   }
