@@ -292,17 +292,19 @@ def run_ours(a, wl, rank, world, local_rank):
         tf_which = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel runs inside a long step)"
                     if peaks else "fallback (B200_PROFILING.md)")
         achieved_tf = att_flops / 1e12 / (att_launch_ms / 1e3) if att_launch_ms > 0 else 0.0
-        traffic = None   # dram bytes per launch of the same kernel from the committed ncu capture (profiles/)
-        tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        traffic = traffic_wc = None   # dram bytes of the same kernels from the committed ncu capture (profiles/)
+        tpath = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
         if os.path.exists(tpath) and wl is WORKLOADS["dtu"]:
-            traffic = json.load(open(tpath)).get("attention_fa_kernel", {}).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("attention_fa_kernel", {}).get("dram_bytes_per_launch")
+            traffic_wc = tj.get("warp_corr_entropy_store + corr_aggregate (8 launches / depth map)", {}).get("dram_bytes_per_depth_map")
         line_extra["roofline"] = {"bound": "tensor", "kernel": "attention_fa_kernel (stage-1 transformer regulariser, 1 launch / layer)",
                                   "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
                                   "traffic": traffic, "peak_source": tf_which, "algorithmic_flops_per_launch": att_flops,
                                   "launch_ms": att_launch_ms, "launches_per_depth_map": att_n // reps,
                                   "share_of_step": att_ms / reps / ms_step if ms_step > 0 else None,
-                                  "note": "fp32-class accuracy costs 3 fp16 products per GEMM and the kernel is bound by the "
-                                          "softmax (3.06e9 exp2 + hi/lo splits per launch), not by the tensor pipe"}
+                                  "note": "bound by the XU pipe (ncu: 81.7 % busy): 3.06e9 exp2 per launch at 16 / clk / SM = 0.66 ms; "
+                                          "Q/K/V are fp16 hi+lo (3 products for the scores), the probabilities fp16"}
         # the fused warp + group-correlation kernels are the HBM-roofline kernels of the path (8 launches / depth map)
         t_wc = sum(per_map.get(k, 0.0) for k in ("mvsf_warp_corr_entropy", "mvsf_warp_corr_aggregate",
                                                   "mvsf_warp_corr_entropy_store", "mvsf_corr_aggregate"))
@@ -314,11 +316,12 @@ def run_ours(a, wl, rank, world, local_rank):
         achieved = sum(alg) / 1e9 / (t_wc / 1e3) if t_wc > 0 else 0.0
         line_extra["roofline_hbm"] = {"bound": "hbm", "kernel": "warp_corr_entropy_store + corr_aggregate (8 launches / depth map)",
                                       "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                      "traffic": None, "peak_source": which, "algorithmic_bytes_per_depth_map": sum(alg),
+                                      "traffic": traffic_wc, "peak_source": which, "algorithmic_bytes_per_depth_map": sum(alg),
                                       "kernel_ms_per_depth_map": t_wc,
-                                      "note": "algorithmic bytes = features + hypotheses + volume; the per-view group "
-                                              "correlations spilled between the two passes (1.7 GB each way) are "
-                                              "implementation traffic and not counted"}
+                                      "note": "algorithmic bytes = features + hypotheses + volume; traffic = measured DRAM bytes of the 8 "
+                                              "launches (profiles/r2_ncu_traffic.json): the per-view group correlations spilled between "
+                                              "the two passes are implementation traffic.  The 4-corner fp32 gather is bound by the SM "
+                                              "load path (3.6 GB per stage and pass at 128 B/clk/SM): ceiling ~0.22 of the HBM roofline"}
         line_extra["kernel_ms_per_depth_map"] = {k.replace("mvsf_", ""): round(v, 4) for k, v in sorted(per_map.items())}
 
     if rank == 0:
@@ -337,8 +340,9 @@ def run_ours(a, wl, rank, world, local_rank):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["name"], "ref_views_per_gpu_per_step": B, "parallelism": f"shard{world}",
                            "l2": "inputs_larger_than_l2 (531 MB feature pyramids per depth map)",
-                           "precision": "fp32-class parity mode: tcgen05 GEMMs / attention / 3-D and 2-D convolutions on fp16 hi+lo "
-                                        "split operands (22-bit mantissa, fp32 accumulate), everything else fp32 SIMT",
+                           "precision": "fp32-class parity mode: tcgen05 GEMMs / attention scores / 3-D and 2-D convolutions on fp16 hi+lo "
+                                        "split operands (22-bit mantissa, fp32 accumulate), attention probabilities fp16, "
+                                        "everything else fp32 SIMT",
                            "e2e_pipeline": "pinned host batch (allocated on the GPU's NUMA node) -> copy stream -> 3 device slots; "
                                            "upload of batch i+1 overlaps the kernels of batch i; depth+confidence read back every step",
                            "numa_binding": numa},

@@ -90,12 +90,18 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t ta
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int col = c * 16 + e;
-        float t = __uint_as_float(raw[c][e]) + (a.bias ? __ldg(a.bias + col) : 0.f);
-        if (EPI == LIN_RES_LN) t = (mvalid ? resrow[col] : 0.f) + __ldg(a.gamma + col) * t;
-        x[col] = t;
-        s += t;
+      for (int q = 0; q < 4; ++q) {   // 128-bit loads of bias / gamma / this row's residual
+        const int col = c * 16 + q * 4;
+        const float4 b4 = a.bias ? ldg4(a.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float t[4] = {__uint_as_float(raw[c][q * 4]) + b4.x, __uint_as_float(raw[c][q * 4 + 1]) + b4.y,
+                      __uint_as_float(raw[c][q * 4 + 2]) + b4.z, __uint_as_float(raw[c][q * 4 + 3]) + b4.w};
+        if (EPI == LIN_RES_LN) {
+          const float4 g4 = ldg4(a.gamma + col);
+          const float4 r4 = mvalid ? *reinterpret_cast<const float4*>(resrow + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          t[0] = r4.x + g4.x * t[0]; t[1] = r4.y + g4.y * t[1]; t[2] = r4.z + g4.z * t[2]; t[3] = r4.w + g4.w * t[3];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { x[col + j] = t[j]; s += t[j]; }
       }
     }
     const float mean = s * (1.0f / 64.0f);
@@ -125,14 +131,25 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t ta
     // processed (a tcgen05.ld + wait costs a few hundred cycles; issued back to back they dominated the epilogue).
     // Two named register buffers, chunks handled in pairs (a dynamically indexed buffer would live in local memory).
     auto process = [&](int c, const uint32_t (&raw)[16]) {
-      float v[16];
+      float v[16], bs[16], rs[16], gm[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // 128-bit loads of the per-column vectors and of this row's residual
+        const float4 b4 = a.bias ? ldg4(a.bias + c * 16 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bs[q * 4] = b4.x; bs[q * 4 + 1] = b4.y; bs[q * 4 + 2] = b4.z; bs[q * 4 + 3] = b4.w;
+        if (EPI == LIN_RES) {
+          const float4 g4 = ldg4(a.gamma + c * 16 + q * 4);
+          gm[q * 4] = g4.x; gm[q * 4 + 1] = g4.y; gm[q * 4 + 2] = g4.z; gm[q * 4 + 3] = g4.w;
+          const float4 r4 = mvalid ? *reinterpret_cast<const float4*>(resrow + c * 16 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          rs[q * 4] = r4.x; rs[q * 4 + 1] = r4.y; rs[q * 4 + 2] = r4.z; rs[q * 4 + 3] = r4.w;
+        }
+      }
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int col = c * 16 + e;
-        float t = __uint_as_float(raw[e]) + (a.bias ? __ldg(a.bias + col) : 0.f);
+        float t = __uint_as_float(raw[e]) + bs[e];
         if (EPI == LIN_GELU) t = gelu_erf(t);
         if (EPI == LIN_ELU1) t = (col < a.elu_cols) ? ((t > 0.f ? t : expm1f(t)) + 1.0f) : t;
-        if (EPI == LIN_RES) t = (mvalid ? resrow[col] : 0.f) + __ldg(a.gamma + col) * t;
+        if (EPI == LIN_RES) t = rs[e] + gm[e] * t;
         v[e] = t;
       }
       if (mvalid) {
@@ -159,7 +176,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t ta
   }
 }
 
-constexpr int TC_RING = 3;
+constexpr int TC_RING = 4;   // A-tile stages; two fills stay in flight behind the block whose MMAs are being issued
 
 template <int EPI>
 __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1)
@@ -205,20 +222,20 @@ linear_tc_kernel(TcLinArgs a) {
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers + MMA issue (thread 0)
-    // global block counter g enumerates (tile, kb) pairs of this CTA; the MMAs of block g-1 are issued after the
-    // fill of block g has been launched (one block of prefetch skew, two cp.async groups in flight).
-    int g = 0;
-    int pend_tile_it = -1, pend_kb = 0, pend_stage = 0;  // block whose MMAs are still to be issued
-    auto issue_pending = [&]() {
-      if (pend_tile_it < 0) return;
+    // Blocks g = 0, 1, ... enumerate the (tile, kb) pairs of this CTA in order; block g uses ring stage g % TC_RING.  The
+    // copies of blocks g, g-1 are still in flight while the MMAs of block g-2 are issued (two cp.async groups of prefetch:
+    // with one group the L2 / HBM latency of every 32 KB block was exposed - ncu: long-scoreboard stalls 25 per issue,
+    // issue slots 11 % busy on the K = 256 layers).
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nblk = my_tiles * nkb;
+    auto issue_block = [&](int gb) {   // MMAs of block gb (its copies have landed and are visible to the async proxy)
       if (tid == 0) {
-        const int buf = pend_tile_it & 1;
-        if (pend_kb == 0) {  // first block of a tile: the epilogue must have drained this accumulator buffer
-          mbar_wait(bar_acce + 8 * buf, (uint32_t)(((pend_tile_it >> 1) & 1) ^ 1));
-        }
+        const int t_it = gb / nkb, kb = gb - t_it * nkb, st = gb % TC_RING;
+        const int buf = t_it & 1;
+        if (kb == 0) mbar_wait(bar_acce + 8 * buf, (uint32_t)(((t_it >> 1) & 1) ^ 1));   // epilogue drained this accumulator
         tc_fence_after_sync();
-        const uint32_t sa = sA + pend_stage * 2 * a_bytes;
-        const uint32_t sb = sB + pend_kb * 2 * b_bytes;
+        const uint32_t sa = sA + st * 2 * a_bytes;
+        const uint32_t sb = sB + kb * 2 * b_bytes;
         const uint32_t tacc = tmem_base + (uint32_t)(buf * N);
 #pragma unroll
         for (int i = 0; i < TC_BK / 16; ++i) {
@@ -226,17 +243,17 @@ linear_tc_kernel(TcLinArgs a) {
           const uint64_t al = make_desc(sa + a_bytes + 2 * i * lbo_a, lbo_a, 128);
           const uint64_t bh = make_desc(sb + 2 * i * lbo_b, lbo_b, 128);
           const uint64_t bl = make_desc(sb + b_bytes + 2 * i * lbo_b, lbo_b, 128);
-          mma_f16_ss(tacc, al, bh, idesc, (pend_kb > 0 || i > 0) ? 1u : 0u);
+          mma_f16_ss(tacc, al, bh, idesc, (kb > 0 || i > 0) ? 1u : 0u);
           mma_f16_ss(tacc, ah, bl, idesc, 1u);
           mma_f16_ss(tacc, ah, bh, idesc, 1u);
         }
-        commit(bar_empty + 8 * pend_stage);
-        if (pend_kb == nkb - 1) commit(bar_accf + 8 * buf);
+        commit(bar_empty + 8 * st);
+        if (kb == nkb - 1) commit(bar_accf + 8 * buf);
       }
     };
-    int tile_it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
-      const int m0 = tile * TC_BM;
+    int g = 0;
+    for (int t_it = 0; t_it < my_tiles; ++t_it) {
+      const int m0 = ((int)blockIdx.x + t_it * (int)gridDim.x) * TC_BM;
       const int valid_rows = min(TC_BM, a.M - m0);
       for (int kb = 0; kb < nkb; ++kb, ++g) {
         const int st = g % TC_RING;
@@ -245,17 +262,26 @@ linear_tc_kernel(TcLinArgs a) {
         fill_tile<TC_NPROD>(s0, a.Ah + (size_t)m0 * a.lda + kb * TC_BK, a.lda, TC_BM, valid_rows, tid);
         fill_tile<TC_NPROD>(s0 + a_bytes, a.Al + (size_t)m0 * a.lda + kb * TC_BK, a.lda, TC_BM, valid_rows, tid);
         cp_async_commit_group();
-        cp_async_wait_group<1>();       // the previous block's copies (of this thread) have landed
-        fence_proxy_async();
-        named_bar_sync(1, TC_NPROD);    // ... and everybody else's
-        issue_pending();
-        pend_tile_it = tile_it; pend_kb = kb; pend_stage = st;
+        if (g >= 2) {
+          cp_async_wait_group<2>();       // block g-2's copies (of this thread) have landed
+          fence_proxy_async();
+          named_bar_sync(1, TC_NPROD);    // ... and everybody else's
+          issue_block(g - 2);
+        }
       }
     }
-    cp_async_wait_group<0>();
-    fence_proxy_async();
-    named_bar_sync(1, TC_NPROD);
-    issue_pending();
+    if (nblk >= 2) {
+      cp_async_wait_group<1>();
+      fence_proxy_async();
+      named_bar_sync(1, TC_NPROD);
+      issue_block(nblk - 2);
+    }
+    if (nblk >= 1) {
+      cp_async_wait_group<0>();
+      fence_proxy_async();
+      named_bar_sync(1, TC_NPROD);
+      issue_block(nblk - 1);
+    }
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int warp4 = warp & 3;         // the TMEM lane quarter this warp may access
@@ -293,7 +319,10 @@ int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
   if (a.C) MVSF_REQUIRE((a.ldc % 4) == 0 && ((uintptr_t)a.C & 15) == 0, "linear_tc: C must be 16-byte aligned");
   if (a.C2) MVSF_REQUIRE((a.ldc2 % 8) == 0 && ((uintptr_t)a.C2 & 15) == 0, "linear_tc: C2 must be 16-byte aligned");
   if (epi == LIN_RES_LN || epi == LIN_LN) MVSF_REQUIRE(a.N == 64 && a.ln_w && a.ln_b, "linear_tc: LayerNorm epilogue needs N == 64");
-  if (epi == LIN_RES || epi == LIN_RES_LN) MVSF_REQUIRE(a.res && a.gamma, "linear_tc: residual epilogue needs res and gamma");
+  if (epi == LIN_RES || epi == LIN_RES_LN)
+    MVSF_REQUIRE(a.res && a.gamma && ((uintptr_t)a.res & 15) == 0 && ((uintptr_t)a.gamma & 15) == 0 && (a.ldres % 4) == 0,
+                 "linear_tc: residual epilogue needs 16-byte aligned res and gamma");
+  if (a.bias) MVSF_REQUIRE(((uintptr_t)a.bias & 15) == 0, "linear_tc: bias must be 16-byte aligned");
   const size_t smem = tc_smem_bytes(a.N, a.K);
   MVSF_REQUIRE(smem <= 227 * 1024, "linear_tc: N*K too large for resident weights (%zu bytes of shared memory)", smem);
   static DeviceOnce once;
