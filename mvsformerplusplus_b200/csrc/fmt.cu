@@ -168,12 +168,17 @@ struct FmtWs {
 
 // one CrossBlock over `M` tokens (nviews views of L tokens each) stored at x (in place).
 // self attention: kv_src == nullptr ; cross attention: kvc = precomputed K/V summary of the reference view.
+// LayerNorms are fused into the epilogue of the GEMM that produces their input: proj emits x (residual stream) and
+// split(norm2(x)), FFN2 emits x and split(norm1 of the NEXT block) when `next_bw` is given; `ln1_ready` says the previous
+// block already left split(norm1(x)) in ws.xn2.
 static int run_block(float* x, int nviews, int L, const float* bw, size_t boff, const float* kvc, const FmtWs& ws,
-                     cudaStream_t s) {
+                     cudaStream_t s, bool ln1_ready = false, const float* next_bw = nullptr) {
   const int M = nviews * L;
   int rc;
-  layernorm64_split_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, bw + B_N1W, bw + B_N1B, ws.xn2, M, 1e-5f);
-  MVSF_LAUNCH_CHECK("fmt_ln1");
+  if (!ln1_ready) {
+    layernorm64_split_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, bw + B_N1W, bw + B_N1B, ws.xn2, M, 1e-5f);
+    MVSF_LAUNCH_CHECK("fmt_ln1");
+  }
   const float* kvsum;
   size_t kv_stride;
   int ldq;
@@ -207,18 +212,23 @@ static int run_block(float* x, int nviews, int L, const float* bw, size_t boff, 
   }
   TcLinArgs p{};
   p.Ah = ws.att2; p.Al = ws.att2 + 64; p.lda = 128; p.Bh = ws.wh + boff + B_PW; p.Bl = ws.wl + boff + B_PW; p.ldb = 64;
-  p.M = M; p.N = 64; p.K = 64; p.bias = bw + B_PB; p.res = x; p.ldres = 64; p.gamma = bw + B_G1; p.C = x; p.ldc = 64;
-  if ((rc = launch_linear_tc(p, LIN_RES, s))) return rc;
-  layernorm64_split_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, bw + B_N2W, bw + B_N2B, ws.xn2, M, 1e-5f);
-  MVSF_LAUNCH_CHECK("fmt_ln2");
+  p.M = M; p.N = 64; p.K = 64; p.bias = bw + B_PB; p.res = x; p.ldres = 64; p.gamma = bw + B_G1;
+  p.Cpre = x; p.ldcpre = 64; p.ln_w = bw + B_N2W; p.ln_b = bw + B_N2B; p.ln_eps = 1e-5f; p.C2 = ws.xn2; p.ldc2 = 128;
+  if ((rc = launch_linear_tc(p, LIN_RES_LN, s))) return rc;   // x += gamma1 * proj(...), xn2 = split(norm2(x))
   TcLinArgs f1{};
   f1.Ah = ws.xn2; f1.Al = ws.xn2 + 64; f1.lda = 128; f1.Bh = ws.wh + boff + B_F1W; f1.Bl = ws.wl + boff + B_F1W; f1.ldb = 64;
   f1.M = M; f1.N = 256; f1.K = 64; f1.bias = bw + B_F1B; f1.C2 = ws.hid2; f1.ldc2 = 512;
   if ((rc = launch_linear_tc(f1, LIN_GELU, s))) return rc;
   TcLinArgs f2{};
   f2.Ah = ws.hid2; f2.Al = ws.hid2 + 256; f2.lda = 512; f2.Bh = ws.wh + boff + B_F2W; f2.Bl = ws.wl + boff + B_F2W; f2.ldb = 256;
-  f2.M = M; f2.N = 64; f2.K = 256; f2.bias = bw + B_F2B; f2.res = x; f2.ldres = 64; f2.gamma = bw + B_G2; f2.C = x; f2.ldc = 64;
-  if ((rc = launch_linear_tc(f2, LIN_RES, s))) return rc;
+  f2.M = M; f2.N = 64; f2.K = 256; f2.bias = bw + B_F2B; f2.res = x; f2.ldres = 64; f2.gamma = bw + B_G2;
+  if (next_bw) {   // x += gamma2 * ffn(...), xn2 = split(norm1_next(x))
+    f2.Cpre = x; f2.ldcpre = 64; f2.ln_w = next_bw + B_N1W; f2.ln_b = next_bw + B_N1B; f2.ln_eps = 1e-5f; f2.C2 = ws.xn2; f2.ldc2 = 128;
+    if ((rc = launch_linear_tc(f2, LIN_RES_LN, s))) return rc;
+  } else {
+    f2.C = x; f2.ldc = 64;
+    if ((rc = launch_linear_tc(f2, LIN_RES, s))) return rc;
+  }
   return MVSF_OK;
 }
 
@@ -334,17 +344,17 @@ int mvsf_fmt_forward(const float* f1, const float* f2, const float* f3, const fl
 
   const float* b0 = wts; const float* b1 = wts + B_SIZE; const float* b2 = wts + 2 * B_SIZE; const float* b3 = wts + 3 * B_SIZE;
   // reference view: the two self layers (FMT.py:96-107); keep the output of the first one for cross layer 1
-  if ((rc = run_block(o1, 1, L, b0, 0, nullptr, ws, s))) return rc;
+  if ((rc = run_block(o1, 1, L, b0, 0, nullptr, ws, s, false, b2))) return rc;
   MVSF_CUDA_OK(cudaMemcpyAsync(ws.ref0, o1, (size_t)L * 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  if ((rc = run_block(o1, 1, L, b2, 2 * (size_t)B_SIZE, nullptr, ws, s))) return rc;
+  if ((rc = run_block(o1, 1, L, b2, 2 * (size_t)B_SIZE, nullptr, ws, s, true, nullptr))) return rc;
   if ((rc = run_cross_kv(ws.ref0, L, b1, (size_t)B_SIZE, ws.kvc, ws, s))) return rc;
   if ((rc = run_cross_kv(o1, L, b3, 3 * (size_t)B_SIZE, ws.kvc + KVSZ, ws, s))) return rc;
   // source views as one batch: self, cross(ref_list[0]), self, cross(ref_list[1])   (FMT.py:119-135)
   float* xs = o1 + (size_t)L * 64;
-  if ((rc = run_block(xs, V - 1, L, b0, 0, nullptr, ws, s))) return rc;
-  if ((rc = run_block(xs, V - 1, L, b1, (size_t)B_SIZE, ws.kvc, ws, s))) return rc;
-  if ((rc = run_block(xs, V - 1, L, b2, 2 * (size_t)B_SIZE, nullptr, ws, s))) return rc;
-  if ((rc = run_block(xs, V - 1, L, b3, 3 * (size_t)B_SIZE, ws.kvc + KVSZ, ws, s))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b0, 0, nullptr, ws, s, false, b1))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b1, (size_t)B_SIZE, ws.kvc, ws, s, true, b2))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b2, 2 * (size_t)B_SIZE, nullptr, ws, s, true, b3))) return rc;
+  if ((rc = run_block(xs, V - 1, L, b3, 3 * (size_t)B_SIZE, ws.kvc + KVSZ, ws, s, true, nullptr))) return rc;
 
   // top-down pathway (FMT.py:195-197), all views batched
   float* red = base;                  // <= 128 VL floats

@@ -104,6 +104,11 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t ta
         for (int j = 0; j < 4; ++j) { x[col + j] = t[j]; s += t[j]; }
       }
     }
+    if (a.Cpre && mvalid) {
+      float* prow = a.Cpre + (size_t)m * a.ldcpre;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) *reinterpret_cast<float4*>(prow + e * 4) = make_float4(x[e * 4], x[e * 4 + 1], x[e * 4 + 2], x[e * 4 + 3]);
+    }
     const float mean = s * (1.0f / 64.0f);
     float q = 0.f;
 #pragma unroll
@@ -147,7 +152,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcLinArgs& a, uint32_t ta
       for (int e = 0; e < 16; ++e) {
         const int col = c * 16 + e;
         float t = __uint_as_float(raw[e]) + bs[e];
-        if (EPI == LIN_GELU) t = gelu_erf(t);
+        if (EPI == LIN_GELU) t = gelu_erf_lean(t);
         if (EPI == LIN_ELU1) t = (col < a.elu_cols) ? ((t > 0.f ? t : expm1f(t)) + 1.0f) : t;
         if (EPI == LIN_RES) t = rs[e] + gm[e] * t;
         v[e] = t;
@@ -323,6 +328,8 @@ int launch_linear_tc(const TcLinArgs& a, int epi, cudaStream_t s) {
     MVSF_REQUIRE(a.res && a.gamma && ((uintptr_t)a.res & 15) == 0 && ((uintptr_t)a.gamma & 15) == 0 && (a.ldres % 4) == 0,
                  "linear_tc: residual epilogue needs 16-byte aligned res and gamma");
   if (a.bias) MVSF_REQUIRE(((uintptr_t)a.bias & 15) == 0, "linear_tc: bias must be 16-byte aligned");
+  if (a.Cpre) MVSF_REQUIRE((epi == LIN_RES_LN || epi == LIN_LN) && (a.ldcpre % 4) == 0 && ((uintptr_t)a.Cpre & 15) == 0,
+                           "linear_tc: Cpre needs a LayerNorm epilogue and 16-byte alignment");
   const size_t smem = tc_smem_bytes(a.N, a.K);
   MVSF_REQUIRE(smem <= 227 * 1024, "linear_tc: N*K too large for resident weights (%zu bytes of shared memory)", smem);
   static DeviceOnce once;

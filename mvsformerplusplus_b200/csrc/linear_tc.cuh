@@ -16,6 +16,8 @@ struct TcLinArgs {
   const float* ln_w; const float* ln_b; float ln_eps;
   int elu_cols;
   float* C; int ldc;            // fp32 result (may be nullptr when only the split result is needed)
+  float* Cpre; int ldcpre;      // LayerNorm epilogues only, optional: the value BEFORE the LayerNorm (the residual stream of a
+                                // pre-norm block: x_new = res + gamma * (acc + bias)), may alias `res`
   __half* C2; int ldc2;         // optional fp16 hi|lo split of the result: row m = [hi(0..N) | lo(0..N)]
 };
 
