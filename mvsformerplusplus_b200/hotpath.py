@@ -117,6 +117,12 @@ class _PackedMixin:
     def _invalidate(self, *a, **k):
         self._packed = None
 
+    def repack(self):
+        """Drop the packed (BN-folded, fp16-split) weight blobs; they are rebuilt on the next forward.  The cache is
+        invalidated automatically by load_state_dict() and .to()/.cuda(); call this after in-place parameter edits
+        (param.data.copy_, optimiser steps)."""
+        self._packed = None
+
     def _init_packing(self):
         self._packed = None
         self.register_load_state_dict_post_hook(lambda m, k: m._invalidate())
@@ -150,12 +156,6 @@ class StageNet(_PackedMixin, nn.Module):
         self._init_packing()
 
     # ---- packing
-    def repack(self):
-        """Drop the packed (BN-folded, fp16-split) weight blobs; they are rebuilt on the next forward.  The cache is
-        invalidated automatically by load_state_dict() and .to()/.cuda(); call this after in-place parameter edits
-        (param.data.copy_, optimiser steps)."""
-        self._packed = None
-
     def _pack(self, device):
         if self._packed is not None and self._packed["device"] == device:
             return self._packed
