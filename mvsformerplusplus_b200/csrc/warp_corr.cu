@@ -25,6 +25,9 @@ int warp_tile_entropy(const float* feat, const float* homs, const float* depth, 
                       int W, cudaStream_t s);
 int warp_tile_aggregate(const float* feat, const float* homs, const float* depth, const float* vis, float* volume, int V, int C,
                         int D, int H, int W, cudaStream_t s);
+bool warp_stream_store_supported(const float* feat, const float* corr, int C, int G, int D, int H, int W);
+int warp_stream_entropy_store(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
+                              int C, int D, int H, int W, cudaStream_t s);
 
 constexpr int kMaxGenericD = 512;
 
@@ -421,6 +424,13 @@ static int warp_corr_entropy_impl(const float* feat, const float* homs, const fl
   MVSF_REQUIRE(C % G == 0 && (C == 8 || C == 16 || C == 32 || C == 64), "warp_corr_entropy: C must be 8/16/32/64, C %% G == 0");
   MVSF_REQUIRE(D <= kMaxGenericD, "warp_corr_entropy: D <= %d", kMaxGenericD);
   cudaStream_t s = (cudaStream_t)stream;
+  if (corr && g_use_tile && warp_stream_store_supported(feat, corr, C, G, D, H, W)) {
+    // fine stages of the cascade (C = 8, D = 4 and C = 16, D = 8): persistent TMA producer / consumer pipeline
+    int rc = warp_stream_entropy_store(feat, homs, depth, entropy, corr, V, C, D, H, W, s);
+    if (rc) return rc;
+    MVSF_LAUNCH_CHECK("warp_stream_entropy_store");
+    return MVSF_OK;
+  }
   if (!corr && g_use_tile && warp_tile_supported(feat, C, G, D, H, W)) {
     int rc = warp_tile_entropy(feat, homs, depth, entropy, V, C, D, H, W, s);
     if (rc) return rc;

@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -425,6 +426,193 @@ warp_tile_kernel(const __grid_constant__ CUtensorMap map, const float* __restric
   }
 }
 
+// ======================================================================================================================
+// Pass A of the SPILL plan for the fine stages, as a persistent producer / consumer pipeline (the cascade's default path):
+//   out: entropy[v][pixel]  and  corr[v][d][pixel][8]   (then vis CNN, then corr_aggregate streams corr).
+// One producer warp runs ahead of eight consumer warps through a ring of NBUF window buffers:
+//   producer, per (tile, view): wait empty[buf] -> predict the window origin from 32 sample pixels of the tile (first and last
+//             hypothesis: the taps of a pixel lie between them on its epipolar line) -> origin to shared memory ->
+//             expect_tx + ONE cp.async.bulk.tensor box -> full[buf]
+//   consumers, per (tile, view): wait full[buf] -> D taps per lane from the window (conflict-free rotated LDS.128; taps
+//             outside the window through global memory) -> similarity, per-view entropy, correlation store -> arrive empty[buf]
+// No CTA-wide barrier, no bounding-box reduction and no staging latency on the consumers' path (the first window kernels
+// above pay all three per (view, chunk) and measured 0.37 ms at DTU stage 4; the L1-gather pass A 0.51 ms).
+// ======================================================================================================================
+template <int C>
+struct PsCfg {
+  static constexpr int NCONS = 256 * Cfg<C>::LPX;   // consumer threads: an 8 x 32 pixel tile, LPX lanes per pixel
+  static constexpr int THREADS = NCONS + 32;        // + the producer warp
+  static constexpr int TROWS = 8;
+};
+
+template <int NBUF>
+struct PsShared {
+  unsigned long long full[NBUF], empty[NBUF];
+  int origin[NBUF][2];
+};
+
+template <int C, int D, int NBUF>
+__global__ void __launch_bounds__(PsCfg<C>::THREADS, (C == 8) ? 2 : 1)
+warp_stream_entropy_store_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ feat,
+                                 const float* __restrict__ homs, const float* __restrict__ depth, float* __restrict__ entropy,
+                                 float* __restrict__ corr, int V, int H, int W, int tiles_x, int ntiles, int dbg) {
+  using K = Cfg<C>;
+  using P = PsCfg<C>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ PsShared<NBUF> sh;
+  const uint32_t win0 = (smem_u32(smem_raw) + 127u) & ~127u;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int HW = H * W;
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) { mbar_init(smem_u32(&sh.full[b]), 1); mbar_init(smem_u32(&sh.empty[b]), P::NCONS / 32); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const CoordConst cc = make_coord_const(W, H);
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == P::NCONS / 32) {
+    // ------------------------------------------------------------------------------------------------ producer warp
+    // sample pixel of this lane inside a tile: 4 rows x 8 columns spread over the 8 x 32 tile
+    const int sr = (lane >> 3) * 2 + 1, sc = (lane & 7) * 4 + 1;
+    int j = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int px = min((tile % tiles_x) * TW + sc, W - 1), py = min((tile / tiles_x) * P::TROWS + sr, H - 1);
+      const int p = py * W + px;
+      const float d_first = __ldg(depth + p), d_last = __ldg(depth + (size_t)(D - 1) * HW + p);
+      const float fxp = (float)px, fyp = (float)py;
+      for (int v = 0; v < V - 1; ++v, ++j) {
+        const int buf = j % NBUF;
+        const Hom m = load_hom(homs + (size_t)v * 12);
+        const float rx = __fadd_rn(fmaf(m.r01, fyp, __fmul_rn(m.r00, fxp)), m.r02);
+        const float ry = __fadd_rn(fmaf(m.r11, fyp, __fmul_rn(m.r10, fxp)), m.r12);
+        const float rz = __fadd_rn(fmaf(m.r21, fyp, __fmul_rn(m.r20, fxp)), m.r22);
+        int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float ix, iy;
+          warp_coord_lean(rx, ry, rz, m, e ? d_last : d_first, cc, ix, iy);
+          const TapCoord tc = split_coord(ix, iy, W, H);
+          if (tc.inb) { mnx = min(mnx, tc.x0); mxx = max(mxx, tc.x0); mny = min(mny, tc.y0); mxy = max(mxy, tc.y0); }
+        }
+        mnx = __reduce_min_sync(0xffffffffu, mnx);
+        mxx = __reduce_max_sync(0xffffffffu, mxx);
+        mny = __reduce_min_sync(0xffffffffu, mny);
+        mxy = __reduce_max_sync(0xffffffffu, mxy);
+        int ox = 0, oy = 0;
+        if (mnx <= mxx) {
+          const int slack_x = K::WX - (mxx + 2 - mnx), slack_y = K::WY - (mxy + 2 - mny);
+          ox = mnx - (slack_x > 0 ? slack_x / 2 : 0);
+          oy = (mny - (slack_y > 0 ? slack_y / 2 : 0)) & ~1;
+        }
+        mbar_wait_warp(smem_u32(&sh.empty[buf]), (uint32_t)(((j / NBUF) & 1) ^ 1));   // consumers released this buffer
+        if (lane == 0) {
+          sh.origin[buf][0] = ox;
+          sh.origin[buf][1] = oy;
+          const uint32_t bar = smem_u32(&sh.full[buf]);
+          if (dbg & 1) {   // measurement only: no staging, the buffer is declared full at once
+            asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+          } else {
+            expect_tx(bar, K::BYTES);
+            tma_load_5d(win0 + (uint32_t)buf * K::BYTES, &map, 0, 0, ox, oy >> 1, v + 1, bar);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------------------------------------- consumer warps
+  const int pix_in_cta = tid / K::LPX, sub = tid % K::LPX;
+  Lane L;
+  int chA, chB;
+  uint32_t base0, base1;
+  if (C == 8) {
+    L.b0 = lane & 1; L.b1 = (lane >> 1) & 1; L.b2 = (lane >> 2) & 1;
+    base0 = (L.b0 ? 16 : 0);
+    base1 = (L.b0 ? 0 : 16);
+    chA = L.b0 ? 4 : 0; chB = L.b0 ? 0 : 4;
+  } else {
+    L.b0 = false; L.b1 = (lane >> 1) & 1; L.b2 = (lane >> 2) & 1;
+    const int q0 = 2 * sub + (L.b1 ? 1 : 0), q1 = 2 * sub + (L.b1 ? 0 : 1);
+    base0 = q0 * 16;
+    base1 = q1 * 16;
+    chA = q0 * 4; chB = q1 * 4;
+  }
+  constexpr float inv_cpg = 8.0f / (float)C;
+  int j = 0;
+  for (int t = 0; t < my_tiles; ++t) {
+    const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+    const int px = (tile % tiles_x) * TW + (pix_in_cta % TW), py = (tile / tiles_x) * P::TROWS + (pix_in_cta / TW);
+    const bool active = (px < W) && (py < H);
+    const int p = min(py, H - 1) * W + min(px, W - 1);
+    const float fxp = (float)min(px, W - 1), fyp = (float)min(py, H - 1);
+    const float4 rA = ldg4(feat + (size_t)p * C + chA), rB = ldg4(feat + (size_t)p * C + chB);
+    float dv[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) dv[k] = __ldg(depth + (size_t)k * HW + p);
+    for (int v = 0; v < V - 1; ++v, ++j) {
+      const int buf = j % NBUF;
+      const Hom m = load_hom(homs + (size_t)v * 12);
+      const float rx = __fadd_rn(fmaf(m.r01, fyp, __fmul_rn(m.r00, fxp)), m.r02);
+      const float ry = __fadd_rn(fmaf(m.r11, fyp, __fmul_rn(m.r10, fxp)), m.r12);
+      const float rz = __fadd_rn(fmaf(m.r21, fyp, __fmul_rn(m.r20, fxp)), m.r22);
+      const float* __restrict__ srcA = feat + (size_t)(v + 1) * HW * C + chA;
+      const float* __restrict__ srcB = feat + (size_t)(v + 1) * HW * C + chB;
+      mbar_wait_warp(smem_u32(&sh.full[buf]), (uint32_t)((j / NBUF) & 1));
+      const int ox = sh.origin[buf][0], oy = sh.origin[buf][1];
+      L.base[0] = win0 + (uint32_t)buf * K::BYTES + base0;
+      L.base[1] = win0 + (uint32_t)buf * K::BYTES + base1;
+      float sims[D];
+      float mx = -FLT_MAX;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        float ix, iy;
+        warp_coord_lean(rx, ry, rz, m, dv[k], cc, ix, iy);
+        TapCoord tc = split_coord(ix, iy, W, H);
+        tc.inb = tc.inb && active;
+        float4 sA = make_float4(0.f, 0.f, 0.f, 0.f), sB = sA;
+        const int lx = tc.x0 - ox, ly = tc.y0 - oy;
+        const bool inwin = tc.inb && (unsigned)lx <= (unsigned)(K::WX - 2) && (unsigned)ly <= (unsigned)(K::WY - 2);
+        if (!(dbg & 2)) gather_window<C>(L, inwin ? lx : 0, inwin ? ly : 0, tc.fx, tc.fy, sA, sB);
+        if (!inwin) {
+          sA = make_float4(0.f, 0.f, 0.f, 0.f); sB = sA;
+          if (tc.inb && !(dbg & 4)) gather_global<C>(srcA, srcB, ix, iy, W, H, sA, sB);
+        }
+        // per-view group correlations exactly as the aggregation pass consumes them (cost_volume.py:78-85)
+        if (active && !(dbg & 8)) {
+          float* cp = corr + (((size_t)v * D + k) * HW + p) * 8;
+          if (C == 8) {
+            *reinterpret_cast<float4*>(cp + chA) = make_float4(rA.x * sA.x, rA.y * sA.y, rA.z * sA.z, rA.w * sA.w);
+            *reinterpret_cast<float4*>(cp + chB) = make_float4(rB.x * sB.x, rB.y * sB.y, rB.z * sB.z, rB.w * sB.w);
+          } else {
+            *reinterpret_cast<float2*>(cp + chA / 2) = make_float2(fmaf(rA.y, sA.y, rA.x * sA.x) * inv_cpg, fmaf(rA.w, sA.w, rA.z * sA.z) * inv_cpg);
+            *reinterpret_cast<float2*>(cp + chB / 2) = make_float2(fmaf(rB.y, sB.y, rB.x * sB.x) * inv_cpg, fmaf(rB.w, sB.w, rB.z * sB.z) * inv_cpg);
+          }
+        }
+        float s = dot4(rA, sA) + dot4(rB, sB);
+        if (K::LPX == 2) s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s *= inv_cpg;
+        sims[k] = s;
+        mx = fmaxf(mx, s);
+      }
+      __syncwarp();
+      if (lane == 0) {   // this warp is done with the window
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(&sh.empty[buf])) : "memory");
+      }
+      // softmax over D -> entropy (cost_volume.py:90-92)
+      float Z = 0.f, ent = 0.f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) { sims[k] = expf(sims[k] - mx); Z += sims[k]; }
+#pragma unroll
+      for (int k = 0; k < D; ++k) { const float pr = __fdiv_rn(sims[k], Z); ent -= pr * logf(pr + 1e-7f); }
+      if (active && sub == 0) entropy[(size_t)v * HW + p] = ent;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -494,6 +682,29 @@ static int dispatch(int mode, const float* feat, const float* homs, const float*
   return launch<C, 1, 8, false>(feat, homs, depth, vis, out, V, D, H, W, c, s);
 }
 
+template <int C, int D, int NBUF>
+static int launch_stream_store(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
+                               int H, int W, cudaStream_t s) {
+  using K = Cfg<C>;
+  auto kern = warp_stream_entropy_store_kernel<C, D, NBUF>;
+  static DeviceOnce once;
+  const int dev = current_device();
+  const size_t smem = (size_t)NBUF * K::BYTES + 128;
+  if (once.need(dev)) {
+    MVSF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    once.done(dev);
+  }
+  CUtensorMap map;
+  int rc = make_window_map<C>(&map, feat, V, H, W);
+  if (rc) return rc;
+  const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, PsCfg<C>::TROWS), ntiles = tiles_x * tiles_y;
+  const int per_sm = (C == 8) ? 2 : 1;
+  const int cap = device_sm_count(dev) * per_sm;
+  static const int dbg = getenv("MVSF_WT_DEBUG") ? atoi(getenv("MVSF_WT_DEBUG")) : 0;   // measurement knobs (1: no staging, 2: no
+  kern<<<ntiles < cap ? ntiles : cap, PsCfg<C>::THREADS, smem, s>>>(map, feat, homs, depth, entropy, corr, V, H, W, tiles_x, ntiles, dbg);   // window gather, 4: no fallback, 8: no store)
+  return MVSF_OK;
+}
+
 }  // namespace wt
 
 // Used by warp_corr.cu's entry points.  Returns false when this organisation does not apply (other channel counts, odd H:
@@ -513,6 +724,16 @@ int warp_tile_aggregate(const float* feat, const float* homs, const float* depth
                         int D, int H, int W, cudaStream_t s) {
   return C == 8 ? wt::dispatch<8>(1, feat, homs, depth, vis, volume, V, D, H, W, s)
                 : wt::dispatch<16>(1, feat, homs, depth, vis, volume, V, D, H, W, s);
+}
+
+// pass A of the spill plan (entropy + per-view group correlations) for the shapes the pipeline kernel is built for
+bool warp_stream_store_supported(const float* feat, const float* corr, int C, int G, int D, int H, int W) {
+  return warp_tile_supported(feat, C, G, D, H, W) && ((C == 8 && D == 4) || (C == 16 && D == 8)) && ((uintptr_t)corr & 15) == 0;
+}
+int warp_stream_entropy_store(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
+                              int C, int D, int H, int W, cudaStream_t s) {
+  if (C == 8) return wt::launch_stream_store<8, 4, 3>(feat, homs, depth, entropy, corr, V, H, W, s);
+  return wt::launch_stream_store<16, 8, 3>(feat, homs, depth, entropy, corr, V, H, W, s);
 }
 
 }  // namespace mvsf

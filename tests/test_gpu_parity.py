@@ -212,11 +212,23 @@ def test_cost_volume_kernels(dev, L, C, D, H, W, V, th, jit):
     assert L.mvsf_warp_corr_plan(C, 8, D, H, W, V, ctypes.c_size_t(1024)) == 1         # no room: two gathers
     tiled = C in (8, 16) and H % 2 == 0    # shapes the window kernels serve
     e_tile = {}
-    if tiled:   # the organisation hotpath.py uses for these shapes
+    if tiled:   # window kernels: the two-gather plan ...
         ent_t, vis_t, vol_t = run_two_gathers()
         e_tile = dict(tile_vs_l1_entropy=max_abs(ent_t.cpu(), ent.cpu()), tile_vs_l1_volume=max_abs(vol_t.cpu(), vol_s.cpu()))
         assert e_tile["tile_vs_l1_entropy"] < 2e-5 and e_tile["tile_vs_l1_volume"] < 1e-5 * vol_scale, e_tile
-        ent, vis, vol_s = ent_t, vis_t, vol_t
+        # ... and the spill plan as hotpath.py runs it (C = 8, D = 4 / C = 16, D = 8: the persistent TMA pipeline kernel)
+        ent_p = torch.empty(V - 1, H, W, device=dev)
+        corr_p = torch.full((V - 1, D, H, W, 8), float("nan"), device=dev)
+        vol_p = torch.empty(D, H, W, 8, device=dev)
+        ck(L.mvsf_warp_corr_entropy_store(P(f), P(homs), P(dd), P(ent_p), P(corr_p), V, C, 8, D, H, W, S()), "warp_corr_entropy_store")
+        vis_p = torch.empty(V - 1, H, W, device=dev)
+        ck(L.mvsf_vis_cnn(P(ent_p), P(wts), P(vis_p), V - 1, H, W, S()), "vis_cnn")
+        ck(L.mvsf_corr_aggregate(P(corr_p), P(vis_p), P(vol_p), V, 8, D, H, W, S()), "corr_aggregate")
+        e_tile.update(pipe_vs_l1_entropy=max_abs(ent_p.cpu(), ent.cpu()), pipe_vs_l1_corr=max_abs(corr_p.cpu(), corr.cpu()),
+                      pipe_vs_l1_volume=max_abs(vol_p.cpu(), vol_s.cpu()))
+        assert bool(torch.isfinite(corr_p).all())
+        assert e_tile["pipe_vs_l1_entropy"] < 2e-5 and e_tile["pipe_vs_l1_corr"] < 1e-5 * vol_scale * 8 and e_tile["pipe_vs_l1_volume"] < 1e-5 * vol_scale, e_tile
+        ent, vis, vol_s = ent_p, vis_p, vol_p
     vol = vol_s
     e_ent = max_abs(ent.cpu(), want["entropy"][0])
     e_vis = max_abs(vis.cpu(), want["vis_weight"][0])
