@@ -96,6 +96,10 @@ int mvsf_warp_corr_plan(int C, int G, int D, int H, int W, int V, size_t spill_b
  * -> entropy [(V-1)][H][W].   The (V-1,C,D,H,W) warped volume is never written. */
 int mvsf_warp_corr_entropy(const float* feat, const float* homs, const float* depth, float* entropy, int V, int C,
                            int G, int D, int H, int W, mvsf_stream_t stream);
+/* ---- precision of the layer-2/3 activations inside the visibility CNN: 1 (default) = fp16 hi + lo (fp32-class),
+ * 0 = fp16 (half the tensor-core instructions; measured against the oracle in tests/test_gpu_parity.py). */
+int mvsf_vis_cnn_set_precision(int x_lo);
+
 /* ---- W4 visibility CNN: models/cost_volume.py:37,93.  entropy [N][H][W] -> vis [N][H][W].
  * wts: packed, BN folded: w1[9][16] b1[16] w2[16 ic][9][16 oc] b2[16] w3[16 ic][9][8 oc] b3[8] w4[8] b4[1] (=3649 floats) */
 int mvsf_vis_cnn(const float* entropy, const float* wts, float* vis, int N, int H, int W, mvsf_stream_t stream);

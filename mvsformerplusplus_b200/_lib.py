@@ -24,6 +24,7 @@ SIGNATURES = {
     "mvsf_warp_corr_set_tile_path": ([I], I),
     "mvsf_warp_corr_plan": ([I, I, I, I, I, I, Z], I),
     "mvsf_warp_corr_entropy": ([P, P, P, P, I, I, I, I, I, I, P], I),
+    "mvsf_vis_cnn_set_precision": ([I], I),
     "mvsf_vis_cnn": ([P, P, P, I, I, I, P], I),
     "mvsf_warp_corr_aggregate": ([P, P, P, P, P, I, I, I, I, I, I, P], I),
     "mvsf_warp_corr_entropy_store": ([P, P, P, P, P, I, I, I, I, I, I, P], I),
@@ -61,6 +62,8 @@ def lib():
             fn.restype = rest
         if os.environ.get("MVSF_ATTENTION_PLO", "0") == "1":   # A-B measurements: round-1 three-product attention
             L.mvsf_attention_set_precision(1)
+        if os.environ.get("MVSF_VIS_XLO") in ("0", "1"):   # A-B measurements of the vis-CNN activation precision
+            L.mvsf_vis_cnn_set_precision(int(os.environ["MVSF_VIS_XLO"]))
         if os.environ.get("MVSF_WARP_TILE", "1") == "0":   # debugging / A-B measurements: force the L1-gather organisation
             L.mvsf_warp_corr_set_tile_path(0)
         _lib = L
@@ -92,7 +95,8 @@ class profile_calls:
         for name in SIGNATURES:
             if name.endswith("_workspace_bytes") or name in ("mvsf_abi_version", "mvsf_launch_count", "mvsf_ktimer_enable",
                                                              "mvsf_ktimer_read", "mvsf_warp_corr_plan",
-                                                             "mvsf_warp_corr_set_tile_path", "mvsf_attention_set_precision"):
+                                                             "mvsf_warp_corr_set_tile_path", "mvsf_attention_set_precision",
+                                                             "mvsf_vis_cnn_set_precision"):
                 continue
             fn = getattr(L, name)
             self._orig[name] = fn

@@ -31,6 +31,13 @@
 
 #include "common.cuh"
 
+#ifndef MVSF_PS_BLOCKS8
+#define MVSF_PS_BLOCKS8 2        // resident CTAs per SM of the C = 8 pipeline kernel (ring of MVSF_PS_NBUF8 windows of 32 KB each);
+                                 // measured at DTU stage 4: 2 CTAs x 3 windows 0.367 ms, 3 CTAs x 2 windows 0.444 ms
+#endif
+#ifndef MVSF_PS_NBUF8
+#define MVSF_PS_NBUF8 3
+#endif
 #ifndef MVSF_WT_PASSB_BLOCKS
 #define MVSF_WT_PASSB_BLOCKS 3   // resident CTAs per SM of the C = 8, D <= 4 aggregation kernel (3 costs ~20 spilled registers)
 #endif
@@ -452,7 +459,7 @@ struct PsShared {
 };
 
 template <int C, int D, int NBUF>
-__global__ void __launch_bounds__(PsCfg<C>::THREADS, (C == 8) ? 2 : 1)
+__global__ void __launch_bounds__(PsCfg<C>::THREADS, (C == 8) ? MVSF_PS_BLOCKS8 : 1)
 warp_stream_entropy_store_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ feat,
                                  const float* __restrict__ homs, const float* __restrict__ depth, float* __restrict__ entropy,
                                  float* __restrict__ corr, int V, int H, int W, int tiles_x, int ntiles, int dbg) {
@@ -602,12 +609,14 @@ warp_stream_entropy_store_kernel(const __grid_constant__ CUtensorMap map, const 
       if (lane == 0) {   // this warp is done with the window
         asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(&sh.empty[buf])) : "memory");
       }
-      // softmax over D -> entropy (cost_volume.py:90-92)
+      // softmax over D -> entropy (cost_volume.py:90-92).  Intrinsic exp / log (ex2 / lg2 based, ~1e-6 relative here: the
+      // arguments are <= 0 resp. in (1e-7, 1]); the entropy feeds a CNN whose output is compared at 5e-4.
       float Z = 0.f, ent = 0.f;
 #pragma unroll
-      for (int k = 0; k < D; ++k) { sims[k] = expf(sims[k] - mx); Z += sims[k]; }
+      for (int k = 0; k < D; ++k) { sims[k] = __expf(sims[k] - mx); Z += sims[k]; }
+      const float rZ = __fdiv_rn(1.0f, Z);
 #pragma unroll
-      for (int k = 0; k < D; ++k) { const float pr = __fdiv_rn(sims[k], Z); ent -= pr * logf(pr + 1e-7f); }
+      for (int k = 0; k < D; ++k) { const float pr = sims[k] * rZ; ent -= pr * __logf(pr + 1e-7f); }
       if (active && sub == 0) entropy[(size_t)v * HW + p] = ent;
     }
   }
@@ -698,7 +707,7 @@ static int launch_stream_store(const float* feat, const float* homs, const float
   int rc = make_window_map<C>(&map, feat, V, H, W);
   if (rc) return rc;
   const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, PsCfg<C>::TROWS), ntiles = tiles_x * tiles_y;
-  const int per_sm = (C == 8) ? 2 : 1;
+  const int per_sm = (C == 8) ? MVSF_PS_BLOCKS8 : 1;
   const int cap = device_sm_count(dev) * per_sm;
   static const int dbg = getenv("MVSF_WT_DEBUG") ? atoi(getenv("MVSF_WT_DEBUG")) : 0;   // measurement knobs (1: no staging, 2: no
   kern<<<ntiles < cap ? ntiles : cap, PsCfg<C>::THREADS, smem, s>>>(map, feat, homs, depth, entropy, corr, V, H, W, tiles_x, ntiles, dbg);   // window gather, 4: no fallback, 8: no store)
@@ -732,7 +741,7 @@ bool warp_stream_store_supported(const float* feat, const float* corr, int C, in
 }
 int warp_stream_entropy_store(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
                               int C, int D, int H, int W, cudaStream_t s) {
-  if (C == 8) return wt::launch_stream_store<8, 4, 3>(feat, homs, depth, entropy, corr, V, H, W, s);
+  if (C == 8) return wt::launch_stream_store<8, 4, MVSF_PS_NBUF8>(feat, homs, depth, entropy, corr, V, H, W, s);
   return wt::launch_stream_store<16, 8, 3>(feat, homs, depth, entropy, corr, V, H, W, s);
 }
 
