@@ -54,6 +54,34 @@ __device__ __forceinline__ void mma_ts(uint32_t el, uint32_t d, uint32_t ta, uin
       : "memory");
 }
 __device__ __forceinline__ void commit_e(uint32_t el, uint32_t bar) { commit_el(el, bar); }
+
+// 2^x for a pair of scores on the FMA pipe (packed fp32x2 instructions): round-to-nearest split x = n + f, f in [-0.5, 0.5],
+// degree-4 minimax polynomial (relative error 2.7e-6, a hundredth of the fp16 rounding P gets next), n added into the
+// exponent field.  x <= 14 by construction (running max); the clamp keeps n + 127 >= 1.
+// EXPERIMENT, off by default (MVSF_ATT_POLY_PAIRS = 0): the XU (MUFU.EX2, 16 lanes / clk / SM) is 80 % busy in this kernel,
+// so moving a share of the exponentials to the FMA pipe should pay - it does not.  Measured per launch at 27 648 tokens
+// (same accuracy, 2.5e-4 vs fp64): 0 of 4 pairs 0.940 ms, 1 of 4 0.995 ms, 2 of 4 1.079 ms, 3 of 4 1.27 ms.  The 11 extra issue
+// slots per pair (2 FMNMX + 7 packed FADD2 / FFMA2 + 2 IMAD) cost more than the 16 XU cycles they free: with 4.5 warps per
+// scheduler the softmax warps are bound by issue + dependency latency around the exponentials, not by the XU alone.
+#ifndef MVSF_ATT_FOLD_LATE
+#define MVSF_ATT_FOLD_LATE 1   // fold O(j-1) after the exponentials of tile j (0.956 -> 0.940 ms): see the softmax loop
+#endif
+#ifndef MVSF_ATT_POLY_PAIRS
+#define MVSF_ATT_POLY_PAIRS 0   // of every 4 score pairs, how many go through the polynomial
+#endif
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), neg1 = make_float2(-1.0f, -1.0f);
+  const float2 r = __fadd2_rn(x, magic);                          // low mantissa bits = n (two's complement)
+  const float2 f = __fadd2_rn(x, __ffma2_rn(r, neg1, magic));     // x - n
+  float2 p = __ffma2_rn(make_float2(0.009570101276040077f, 0.009570101276040077f), f, make_float2(0.05591785907745361f, 0.05591785907745361f));
+  p = __ffma2_rn(p, f, make_float2(0.240247443318367f, 0.240247443318367f));
+  p = __ffma2_rn(p, f, make_float2(0.6931217908859253f, 0.6931217908859253f));
+  p = __ffma2_rn(p, f, make_float2(0.9999992847442627f, 0.9999992847442627f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23)));
+}
 }  // namespace fa6
 
 // tiled layout: planes Qh, Ql, Kh, Kl of 4 heads x ntiles x 2048 halves (tile = [2 k-chunks][128 rows][8]) and one V plane
@@ -274,26 +302,37 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       const float mx = fmaxf(m, fmaxf(pmax, xj[(half ^ 1) * 128 + row]));
       const float corr = ex2f(m - mx);
       m = mx;
-      if (j > 0) fold(j - 1);                  // also guarantees that P_w(j-1) has been consumed
-      corr_prev = corr;
+      // PLO: P_lo(j) goes to shared memory inside the loop below, so P_w(j-1) must have been consumed before it starts
+      constexpr bool FOLD_LATE = MVSF_ATT_FOLD_LATE && !PLO;
+      if (!FOLD_LATE) {
+        if (j > 0) fold(j - 1);                // also guarantees that P_w(j-1) has been consumed
+        corr_prev = corr;
+      }
       // P is stored as fp16 hi + lo: scale it by 2^14 (largest element 16384 < 65504) so that probabilities down to 4e-12
       // survive - without the bias every p < 3e-8 underflows to zero, a SYSTEMATIC loss of up to N * 3e-8 in the
       // normaliser for peaked rows.  The factor cancels in O / l.
       const float mb = m - 14.0f;
       const float2 nmb2 = make_float2(-mb, -mb);
+      uint32_t pw2[2][16];
 #pragma unroll
       for (int c16 = 0; c16 < 2; ++c16) {      // 32 keys: one tcgen05.st of 16 packed columns, four P_lo chunks of 8 keys
-        uint32_t pw[16];
+        uint32_t (&pw)[16] = pw2[c16];
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           uint32_t pl[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            // (a degree-4 polynomial exp2 on the FMA pipe for 3 of every 8 elements was measured: 0.98 -> 1.14 ms per launch,
-            //  the softmax warps are short of issue slots, not only of MUFU throughput)
             // one packed fp32x2 add for the two score offsets (FADD2: half the issue slots of two FADDs)
             const float2 xs = __fadd2_rn(make_float2(__uint_as_float(sr[c16][c8 * 8 + 2 * e]), __uint_as_float(sr[c16][c8 * 8 + 2 * e + 1])), nmb2);
-            const float p0 = ex2f(xs.x), p1 = ex2f(xs.y);
+            // MVSF_ATT_POLY_PAIRS of every 4 pairs take the FMA-pipe polynomial (11 issue slots per pair, all packed or ALU)
+            // instead of two MUFU.EX2 (2 issue slots but 16 XU cycles per warp): see ex2_poly2
+            float p0, p1;
+            if (e < MVSF_ATT_POLY_PAIRS) {
+              const float2 pp = ex2_poly2(xs);
+              p0 = pp.x; p1 = pp.y;
+            } else {
+              p0 = ex2f(xs.x); p1 = ex2f(xs.y);
+            }
             const __half2 hh = __floats2half2_rn(p0, p1);
             pw[c8 * 4 + e] = *reinterpret_cast<const uint32_t*>(&hh);
             if (PLO) {
@@ -307,7 +346,15 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
           }
         }
-        tmem_st16(tP + c16 * 16, pw);
+        if (!FOLD_LATE) tmem_st16(tP + c16 * 16, pw);
+      }
+      if (FOLD_LATE) {
+        // O_w(j-1) = P_w(j-1) V(j-1) is only needed here, a whole exponential phase after it was issued: the fold never
+        // waits for the tensor core; P_w(j) stays in registers until P_w(j-1) has been consumed
+        if (j > 0) fold(j - 1);
+        corr_prev = corr;
+        tmem_st16(tP, pw2[0]);
+        tmem_st16(tP + 16, pw2[1]);
       }
       tmem_st_wait();
       if (PLO) fence_proxy_async();
