@@ -54,7 +54,16 @@ __device__ __forceinline__ void mma_ts(uint32_t el, uint32_t d, uint32_t ta, uin
       : "memory");
 }
 __device__ __forceinline__ void commit_e(uint32_t el, uint32_t bar) { commit_el(el, bar); }
-
+// Measured dead ends of round 2 (in-kernel clock trace, MVSF_ATT_TRACE; one CTA, 27 648 tokens, clk per 128-key tile):
+//   softmax warp: wait S 270, TMEM->registers 100, row max + exchange 650, 64 exponentials 1180, fold + P store 340  = 2600
+//   MMA warp:     six mbarrier waits of 240-580 clk each (a wait on an ALREADY COMPLETED mbarrier costs 120 clk on an idle SM,
+//                 tools/mbar_microbench.cu, and 230-260 clk in here), 22 MMAs issued in ~480 clk
+//   without exponentials, row max and fold (MVSF_ATT_DBG = 7) the tile still takes 2410 clk: the handshake chain
+//   MMA -> commit -> softmax wake-up -> tcgen05.ld -> arrive -> MMA-warp wake-up is as long as the softmax work itself.
+// Tried on top, all slower or equal (ms per launch incl. operand tiling, baseline 0.955): S-free / P-full signals as
+// shared-memory counters (release add per warp + polling LDS: 0.999, the release fence and the polls cost more than the
+// mbarrier), one mbarrier per K+V stage (0.964), pair-wise 64-thread named barriers + 4 independent max chains (1.03 with
+// one-lane polling), one-lane polling in the softmax warps (1.11 traced), exp2 polynomial on the FMA pipe (below).
 // 2^x for a pair of scores on the FMA pipe (packed fp32x2 instructions): round-to-nearest split x = n + f, f in [-0.5, 0.5],
 // degree-4 minimax polynomial (relative error 2.7e-6, a hundredth of the fp16 rounding P gets next), n added into the
 // exponent field.  x <= 14 by construction (running max); the clamp keeps n + 127 >= 1.
@@ -65,6 +74,12 @@ __device__ __forceinline__ void commit_e(uint32_t el, uint32_t bar) { commit_el(
 // scheduler the softmax warps are bound by issue + dependency latency around the exponentials, not by the XU alone.
 #ifndef MVSF_ATT_FOLD_LATE
 #define MVSF_ATT_FOLD_LATE 1   // fold O(j-1) after the exponentials of tile j (0.956 -> 0.940 ms): see the softmax loop
+#endif
+#ifndef MVSF_ATT_TRACE
+#define MVSF_ATT_TRACE 0   // instrumented build: clock() sums per phase of the MMA warp and of four softmax warps, printed by one CTA
+#endif
+#ifndef MVSF_ATT_DBG
+#define MVSF_ATT_DBG 0   // TIMING-ONLY decomposition (results are wrong): 1 no row max / exchange / barrier, 2 no MUFU, 4 no fold, 8 one P*V MMA instead of 8, 16 one S MMA instead of 3
 #endif
 #ifndef MVSF_ATT_POLY_PAIRS
 #define MVSF_ATT_POLY_PAIRS 0   // of every 4 score pairs, how many go through the polynomial
@@ -203,9 +218,13 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       tc_fence_after_sync();
       const uint32_t kh = k0 + (uint32_t)(t % NKV) * (2 * TILE >> 4), kl = kh + (TILE >> 4);
       const uint32_t tS = tmem_base + col_s(w);
+#if MVSF_ATT_DBG & 16
+      mma_ss(el, tS, q_hi[w], kh, idesc_s, 0u);
+#else
       mma_ss(el, tS, q_lo[w], kh, idesc_s, 0u);
       mma_ss(el, tS, q_hi[w], kl, idesc_s, 1u);
       mma_ss(el, tS, q_hi[w], kh, idesc_s, 1u);
+#endif
       commit_e(el, bar_sf + 8 * w);
     };
     auto issue_pv = [&](int w, int u) {          // O_w(u) = P_w(u) V(u)  (V(u) has landed, P_w(u) is complete)
@@ -215,7 +234,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       // two MMAs per 16 keys: P_hi (tensor memory) x [V_lo | V_hi | 1] (N = 48) -> columns [P_hi V_lo | P_hi V_hi | sum P_hi],
       // then P_lo (shared memory) x [V_hi | 1] (N = 32) accumulated onto columns 16..47.  An MMA costs ~50 clk whatever N <= 64.
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < ((MVSF_ATT_DBG & 8) ? 1 : 8); ++i) {
         mma_ts(el, tO, tP + i * 8, vv + i * (2 * LBO_V >> 4), idesc_o2, i > 0 ? 1u : 0u);
         if (PLO) mma_ss(el, tO + 16, p_lo[w] + i * (2 * LBO_P >> 4), vv + i * (2 * LBO_V >> 4) + (256 >> 4), idesc_o, 1u);
       }
@@ -223,29 +242,58 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
     };
     // Static schedule = the order in which the events arrive when the two warpgroups alternate (warpgroup 1 starts one
     // softmax phase after warpgroup 0): sfree0(t), pfull0(t), sfree1(t), pfull1(t), sfree0(t+1), ...
+#if MVSF_ATT_TRACE
+    uint32_t tr[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tc0 = clock();
+#define ATT_TR(i) { const uint32_t c_ = clock(); tr[i] += c_ - tc0; tc0 = c_; }
+#else
+#define ATT_TR(i)
+#endif
+    auto wait_sfree = [&](int w, int t) { wait1(bar_sfree + 8 * w, (uint32_t)(t & 1)); };   // S_w(t) is in registers
+    auto wait_pf = [&](int w, int t) { wait1(bar_pf + 8 * w, (uint32_t)(t & 1)); };         // P_w(t) complete
     wait1(bar_q, 0u);
     wait1(bar_kf, 0u);
     issue_s(0, 0);
+    ATT_TR(9)
     for (int t = 0; t < ntiles; ++t) {
       const int tn = t + 1;
       if (tn < ntiles) {
-        wait1(bar_sfree, (uint32_t)(t & 1));                                      // S_0(t) is in registers
+        wait_sfree(0, t);
+        ATT_TR(0)
         wait1(bar_kf + 8 * (tn % NKV), (uint32_t)((tn / NKV) & 1));
+        ATT_TR(1)
         issue_s(0, tn);
+        ATT_TR(2)
       }
-      wait1(bar_pf, (uint32_t)(t & 1));                                           // P_0(t) complete, O_0(t-1) folded
+      wait_pf(0, t);
+      ATT_TR(3)
       wait1(bar_vf + 8 * (t % NKV), (uint32_t)((t / NKV) & 1));
+      ATT_TR(4)
       issue_pv(0, t);
+      ATT_TR(5)
       if (t == 0) { issue_s(1, 0); commit_e(el, bar_ke); }                        // warpgroup 1 starts here
       if (tn < ntiles) {
-        wait1(bar_sfree + 8, (uint32_t)(t & 1));
+        wait_sfree(1, t);
+        ATT_TR(6)
         issue_s(1, tn);
         commit_e(el, bar_ke + 8 * (tn % NKV));                                    // K(t+1): both products issued
+        ATT_TR(2)
       }
-      wait1(bar_pf + 8, (uint32_t)(t & 1));
+      wait_pf(1, t);
+      ATT_TR(7)
+#if MVSF_ATT_TRACE
+      wait1(bar_q, 0u);   // a barrier that completed long ago: the fixed cost of one wait + one clock read
+      ATT_TR(8)
+#endif
       issue_pv(1, t);
       commit_e(el, bar_ve + 8 * (t % NKV));                                       // V(t): both products issued
+      ATT_TR(5)
     }
+#if MVSF_ATT_TRACE
+    if (lane == 0 && blockIdx.x == 3 && blockIdx.y == 1)
+      printf("MMA warp clk/tile: wait sfree0 %u, wait K %u, issue S (x2) %u, wait pf0 %u, wait V %u, issue PV (x2) %u, wait sfree1 %u, wait pf1 %u | total %u | a wait on a completed barrier %u\n",
+             tr[0] / ntiles, tr[1] / ntiles, tr[2] / ntiles, tr[3] / ntiles, tr[4] / ntiles, tr[5] / ntiles, tr[6] / ntiles, tr[7] / ntiles,
+             (tr[0] + tr[1] + tr[2] + tr[3] + tr[4] + tr[5] + tr[6] + tr[7]) / ntiles, tr[8] / ntiles);
+#endif
   } else {
     // ------------------------------------------------------------------------------------------ softmax warpgroups
     // 16 warps: query tile w = sw / 8, key-column half = (sw / 4) % 2, TMEM lane quarter = warp % 4.  The two threads of a
@@ -265,6 +313,9 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
     float m = -1e30f, l = 0.f, corr_prev = 1.0f;
     auto fold = [&](int t) {   // o = o * corr_prev + (three partial products of tile t)
       mbar_wait(bar_of + 8 * w, (uint32_t)(t & 1));
+#if MVSF_ATT_DBG & 4
+      return;
+#endif
       tc_fence_after_sync();
       uint32_t a0[8], a1[8], ls;
       tmem_ld8_nowait(tO, a0);                       // P_hi V_lo
@@ -275,8 +326,15 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       for (int d = 0; d < 8; ++d) o[d] = fmaf(o[d], corr_prev, __uint_as_float(a0[d]) + __uint_as_float(a1[d]));
       l = fmaf(l, corr_prev, __uint_as_float(ls));
     };
+#if MVSF_ATT_TRACE
+    uint32_t ts[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sc0 = clock();
+#define ATT_TS(i) { const uint32_t c_ = clock(); ts[i] += c_ - sc0; sc0 = c_; }
+#else
+#define ATT_TS(i)
+#endif
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(bar_sf + 8 * w, (uint32_t)(j & 1));
+      ATT_TS(0)
       tc_fence_after_sync();
       uint32_t sr[2][32];
       tmem_ld32_nowait(tS, sr[0]);
@@ -284,6 +342,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       tmem_ld_wait();
       tc_fence_before_sync();
       mbar_arrive(bar_sfree + 8 * w);          // S_w may be overwritten by the next tile's product
+      ATT_TS(1)
       if (j * 128 + 128 > N) {                 // last, partial tile only: keys >= N never win the max and get P = 0
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -291,6 +350,10 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
           for (int e = 0; e < 32; ++e)
             if (j * 128 + half * 64 + c * 32 + e >= N) sr[c][e] = 0xf149f2caU;  // -1e30f
       }
+#if MVSF_ATT_DBG & 1
+      const float mx = 20.0f, corr = 1.0f;
+      m = mx;
+#else
       float pmax = -1e30f;
 #pragma unroll
       for (int c = 0; c < 2; ++c)
@@ -302,6 +365,8 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       const float mx = fmaxf(m, fmaxf(pmax, xj[(half ^ 1) * 128 + row]));
       const float corr = ex2f(m - mx);
       m = mx;
+#endif
+      ATT_TS(2)
       // PLO: P_lo(j) goes to shared memory inside the loop below, so P_w(j-1) must have been consumed before it starts
       constexpr bool FOLD_LATE = MVSF_ATT_FOLD_LATE && !PLO;
       if (!FOLD_LATE) {
@@ -331,7 +396,11 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
               const float2 pp = ex2_poly2(xs);
               p0 = pp.x; p1 = pp.y;
             } else {
+#if MVSF_ATT_DBG & 2
+              p0 = xs.x; p1 = xs.y;
+#else
               p0 = ex2f(xs.x); p1 = ex2f(xs.y);
+#endif
             }
             const __half2 hh = __floats2half2_rn(p0, p1);
             pw[c8 * 4 + e] = *reinterpret_cast<const uint32_t*>(&hh);
@@ -348,6 +417,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
         }
         if (!FOLD_LATE) tmem_st16(tP + c16 * 16, pw);
       }
+      ATT_TS(3)
       if (FOLD_LATE) {
         // O_w(j-1) = P_w(j-1) V(j-1) is only needed here, a whole exponential phase after it was issued: the fold never
         // waits for the tensor core; P_w(j) stays in registers until P_w(j-1) has been consumed
@@ -356,11 +426,19 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
         tmem_st16(tP, pw2[0]);
         tmem_st16(tP + 16, pw2[1]);
       }
+      ATT_TS(4)
       tmem_st_wait();
       if (PLO) fence_proxy_async();
       tc_fence_before_sync();
       mbar_arrive(bar_pf + 8 * w);
+      ATT_TS(5)
     }
+#if MVSF_ATT_TRACE
+    if (lane == 0 && (quarter == 2) && blockIdx.x == 3 && blockIdx.y == 1)
+      printf("softmax warp %d (tile %d half %d) clk/tile: wait S %u, ld S %u, max+exchange %u, exps %u, fold+st %u, st wait+arrive %u | total %u\n",
+             warp, w, half, ts[0] / ntiles, ts[1] / ntiles, ts[2] / ntiles, ts[3] / ntiles, ts[4] / ntiles, ts[5] / ntiles,
+             (ts[0] + ts[1] + ts[2] + ts[3] + ts[4] + ts[5]) / ntiles);
+#endif
     fold(ntiles - 1);
     const int qt = qt0 + w;
     const int r = qt * 128 + row;
