@@ -81,10 +81,16 @@ int mvsf_position3d(const float* kinv_ref, const float* depth, const float* dept
 int mvsf_homo_warp(const float* src_nhwc, const float* hom, const float* depth, float* warped, uint8_t* mask, int C,
                    int D, int H, int W, mvsf_stream_t stream);
 
-/* ---- test hook: the cost-volume passes have two organisations computing the same function - L1 gathers from global
- * memory (warp_corr.cu, any C in 8/16/32/64) and TMA-staged shared-memory windows (warp_tile.cu, C = 8/16, even H).
- * enable = 1 (default): use the window kernels where they apply; 0: force the L1 organisation everywhere. */
-int mvsf_warp_corr_set_tile_path(int enable);
+/* ---- test / measurement hooks: the cost-volume passes have two organisations computing the same function - L1 gathers
+ * from global memory (warp_corr.cu, any C in 8/16/32/64) and TMA-staged shared-memory windows (warp_tile.cu, C = 8/16, even H).
+ * mode 0: force the L1 organisation everywhere; 1 (default): adaptive - the window kernels of the two-gather plan where they
+ * apply, and for mvsf_warp_corr_entropy_store at C = 8, D = 4 a per-call choice made ON THE DEVICE from the call's own
+ * geometry (share of sampled taps that miss the pipeline kernel's predicted windows <= max_window_miss per mille ->
+ * pipeline kernel, else L1 kernel; both are launched, the one not chosen returns at once); 2: force the window / pipeline
+ * kernels wherever they exist.  mvsf_warp_corr_last_selection reads the most recent decision back (synchronises). */
+int mvsf_warp_corr_set_tile_path(int mode);
+int mvsf_warp_corr_set_max_window_miss(int permille);
+int mvsf_warp_corr_last_selection(int* used_pipeline, int* miss_permille);
 
 /* ---- which of the two cost-volume plans to run for a stage shape: 1 = two gathers (mvsf_warp_corr_entropy, mvsf_vis_cnn,
  * mvsf_warp_corr_aggregate; no intermediate buffer), 0 = spill plan (mvsf_warp_corr_entropy_store, mvsf_vis_cnn,

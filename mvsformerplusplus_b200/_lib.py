@@ -22,6 +22,8 @@ SIGNATURES = {
     "mvsf_position3d": ([P, P, P, I, P, I, P, I, I, I, P], I),
     "mvsf_homo_warp": ([P, P, P, P, P, I, I, I, I, P], I),
     "mvsf_warp_corr_set_tile_path": ([I], I),
+    "mvsf_warp_corr_set_max_window_miss": ([I], I),
+    "mvsf_warp_corr_last_selection": ([ctypes.POINTER(I), ctypes.POINTER(I)], I),
     "mvsf_warp_corr_plan": ([I, I, I, I, I, I, Z], I),
     "mvsf_warp_corr_entropy": ([P, P, P, P, I, I, I, I, I, I, P], I),
     "mvsf_vis_cnn_set_precision": ([I], I),
@@ -64,8 +66,10 @@ def lib():
             L.mvsf_attention_set_precision(1)
         if os.environ.get("MVSF_VIS_XLO") in ("0", "1"):   # A-B measurements of the vis-CNN activation precision
             L.mvsf_vis_cnn_set_precision(int(os.environ["MVSF_VIS_XLO"]))
-        if os.environ.get("MVSF_WARP_TILE", "1") == "0":   # debugging / A-B measurements: force the L1-gather organisation
-            L.mvsf_warp_corr_set_tile_path(0)
+        if os.environ.get("MVSF_WARP_TILE", "1") in ("0", "2"):   # A-B measurements: 0 force the L1-gather kernels, 2 force the window kernels
+            L.mvsf_warp_corr_set_tile_path(int(os.environ["MVSF_WARP_TILE"]))
+        if os.environ.get("MVSF_WT_MAX_MISS"):
+            L.mvsf_warp_corr_set_max_window_miss(int(os.environ["MVSF_WT_MAX_MISS"]))
         _lib = L
     return _lib
 
@@ -95,7 +99,8 @@ class profile_calls:
         for name in SIGNATURES:
             if name.endswith("_workspace_bytes") or name in ("mvsf_abi_version", "mvsf_launch_count", "mvsf_ktimer_enable",
                                                              "mvsf_ktimer_read", "mvsf_warp_corr_plan",
-                                                             "mvsf_warp_corr_set_tile_path", "mvsf_attention_set_precision",
+                                                             "mvsf_warp_corr_set_tile_path", "mvsf_warp_corr_set_max_window_miss",
+                                                             "mvsf_warp_corr_last_selection", "mvsf_attention_set_precision",
                                                              "mvsf_vis_cnn_set_precision"):
                 continue
             fn = getattr(L, name)

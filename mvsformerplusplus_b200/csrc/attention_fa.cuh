@@ -20,7 +20,11 @@
 
 namespace fa6 {
 using namespace umma;
-constexpr int NSOFT = 512, THREADS = 64 + NSOFT, NKV = 3;   // two threads per query row: 4 softmax warps per scheduler
+#ifndef MVSF_ATT_MMA2
+#define MVSF_ATT_MMA2 1   // one MMA issuer warp per query tile (warps 1, 2) instead of one warp interleaving both tiles
+#endif
+constexpr int NSOFT = 512, NCTRL = MVSF_ATT_MMA2 ? 4 : 2;   // control warps: producer, MMA issuer(s), (one idle warp keeps warp % 4 = TMEM lane quarter)
+constexpr int THREADS = 32 * NCTRL + NSOFT, NKV = 3;        // two threads per query row: 4 softmax warps per scheduler
 constexpr uint32_t TILE = 4096;                 // one canonical 128 x 16 (Q, K) or 16 x 128 (V^T) fp16 tile
 constexpr uint32_t LBO_QK = 2048, LBO_V = 768;  // k-chunk strides: Q/K 128 rows; V^T 48 rows = V_lo dims | V_hi dims | ones row + 15 zero rows
 constexpr uint32_t V_TILE = 16 * LBO_V;         // 12 KB
@@ -74,6 +78,9 @@ __device__ __forceinline__ void commit_e(uint32_t el, uint32_t bar) { commit_el(
 // scheduler the softmax warps are bound by issue + dependency latency around the exponentials, not by the XU alone.
 #ifndef MVSF_ATT_FOLD_LATE
 #define MVSF_ATT_FOLD_LATE 1   // fold O(j-1) after the exponentials of tile j (0.956 -> 0.940 ms): see the softmax loop
+#endif
+#ifndef MVSF_ATT_PROBE
+#define MVSF_ATT_PROBE 1   // softmax warps probe their two mbarriers (S full, O full) a phase ahead of the point of use
 #endif
 #ifndef MVSF_ATT_TRACE
 #define MVSF_ATT_TRACE 0   // instrumented build: clock() sums per phase of the MMA warp and of four softmax warps, printed by one CTA
@@ -172,7 +179,8 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
 
   if (tid == 0) {
     mbar_init(bar_q, 1);
-    for (int i = 0; i < NKV; ++i) { mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, 1); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, 1); }
+    // a K / V stage is free once BOTH query tiles' products that read it are complete: one commit (MMA2: one per issuer warp)
+    for (int i = 0; i < NKV; ++i) { mbar_init(bar_kf + 8 * i, 1); mbar_init(bar_ke + 8 * i, MVSF_ATT_MMA2 ? 2 : 1); mbar_init(bar_vf + 8 * i, 1); mbar_init(bar_ve + 8 * i, MVSF_ATT_MMA2 ? 2 : 1); }
     for (int w = 0; w < 2; ++w) { mbar_init(bar_sf + 8 * w, 1); mbar_init(bar_sfree + 8 * w, 256); mbar_init(bar_pf + 8 * w, 256); mbar_init(bar_of + 8 * w, 1); }
     fence_barrier_init();
   }
@@ -203,7 +211,8 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
         bulk_load(sb + OFF_V + s * V_TILE, tiled + 4 * plane + ((size_t)h * ntiles + t) * 6144, V_TILE, bar_vf + 8 * s);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp < NCTRL) {
+    if (MVSF_ATT_MMA2 && warp == 3) goto done;   // idle filler warp
     // ------------------------------------------------------------------------------------------ MMA issuer (converged warp)
     const uint32_t idesc_s = make_idesc_f16(128, 128), idesc_o = make_idesc_f16(128, 32), idesc_o2 = make_idesc_f16(128, 48);
     const uint32_t el = elect_one();
@@ -250,6 +259,34 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
 #endif
     auto wait_sfree = [&](int w, int t) { wait1(bar_sfree + 8 * w, (uint32_t)(t & 1)); };   // S_w(t) is in registers
     auto wait_pf = [&](int w, int t) { wait1(bar_pf + 8 * w, (uint32_t)(t & 1)); };         // P_w(t) complete
+#if MVSF_ATT_MMA2
+    // this warp serves query tile mw alone: its chain S(t+1) <- S-free(t), P V(t) <- P-full(t) never waits for the other
+    // tile's events (a wait costs 230-260 clk even on a completed mbarrier; the single issuer went through six per tile)
+    const int mw = warp - 1;
+    wait1(bar_q, 0u);
+    wait1(bar_kf, 0u);
+    issue_s(mw, 0);
+    commit_e(el, bar_ke);
+    for (int t = 0; t < ntiles; ++t) {
+      const int tn = t + 1;
+      if (tn < ntiles) {
+        wait_sfree(mw, t);
+        ATT_TR(0)
+        wait1(bar_kf + 8 * (tn % NKV), (uint32_t)((tn / NKV) & 1));
+        ATT_TR(1)
+        issue_s(mw, tn);
+        commit_e(el, bar_ke + 8 * (tn % NKV));
+        ATT_TR(2)
+      }
+      wait_pf(mw, t);
+      ATT_TR(3)
+      wait1(bar_vf + 8 * (t % NKV), (uint32_t)((t / NKV) & 1));
+      ATT_TR(4)
+      issue_pv(mw, t);
+      commit_e(el, bar_ve + 8 * (t % NKV));
+      ATT_TR(5)
+    }
+#else
     wait1(bar_q, 0u);
     wait1(bar_kf, 0u);
     issue_s(0, 0);
@@ -288,6 +325,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       commit_e(el, bar_ve + 8 * (t % NKV));                                       // V(t): both products issued
       ATT_TR(5)
     }
+#endif
 #if MVSF_ATT_TRACE
     if (lane == 0 && blockIdx.x == 3 && blockIdx.y == 1)
       printf("MMA warp clk/tile: wait sfree0 %u, wait K %u, issue S (x2) %u, wait pf0 %u, wait V %u, issue PV (x2) %u, wait sfree1 %u, wait pf1 %u | total %u | a wait on a completed barrier %u\n",
@@ -299,7 +337,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
     // 16 warps: query tile w = sw / 8, key-column half = (sw / 4) % 2, TMEM lane quarter = warp % 4.  The two threads of a
     // row exchange their partial row maxima through shared memory (double buffered by tile parity) and meet at a named
     // barrier of their tile's 256 threads - the other tile's warps are not involved.
-    const int sw = warp - 2;
+    const int sw = warp - NCTRL;
     const int w = sw >> 3, half = (sw >> 2) & 1, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = ((uint32_t)(quarter * 32)) << 16;
@@ -311,8 +349,9 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
 #pragma unroll
     for (int d = 0; d < 8; ++d) o[d] = 0.f;
     float m = -1e30f, l = 0.f, corr_prev = 1.0f;
+    uint32_t s_ready = 0, o_ready = 0;   // answers of the early probes (mbar_test_wait)
     auto fold = [&](int t) {   // o = o * corr_prev + (three partial products of tile t)
-      mbar_wait(bar_of + 8 * w, (uint32_t)(t & 1));
+      if (!o_ready) mbar_wait(bar_of + 8 * w, (uint32_t)(t & 1));
 #if MVSF_ATT_DBG & 4
       return;
 #endif
@@ -333,7 +372,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
 #define ATT_TS(i)
 #endif
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(bar_sf + 8 * w, (uint32_t)(j & 1));
+      if (!s_ready) mbar_wait(bar_sf + 8 * w, (uint32_t)(j & 1));
       ATT_TS(0)
       tc_fence_after_sync();
       uint32_t sr[2][32];
@@ -359,9 +398,11 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int e = 0; e < 32; ++e) pmax = fmaxf(pmax, __uint_as_float(sr[c][e]));
+      ATT_TS(6)
       volatile float* xj = xchg + (j & 1) * 512;
       xj[half * 128 + row] = pmax;
       if (w == 0) named_bar_sync_c<1>(256); else named_bar_sync_c<2>(256);
+      ATT_TS(7)
       const float mx = fmaxf(m, fmaxf(pmax, xj[(half ^ 1) * 128 + row]));
       const float corr = ex2f(m - mx);
       m = mx;
@@ -378,6 +419,8 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       // normaliser for peaked rows.  The factor cancels in O / l.
       const float mb = m - 14.0f;
       const float2 nmb2 = make_float2(-mb, -mb);
+      // the answer is looked at after the exponentials: by then it has arrived, and O(j-1) is complete in all but rare cases
+      o_ready = (MVSF_ATT_PROBE && FOLD_LATE && j > 0) ? mbar_test_wait(bar_of + 8 * w, (uint32_t)((j - 1) & 1)) : 0u;
       uint32_t pw2[2][16];
 #pragma unroll
       for (int c16 = 0; c16 < 2; ++c16) {      // 32 keys: one tcgen05.st of 16 packed columns, four P_lo chunks of 8 keys
@@ -418,6 +461,8 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
         if (!FOLD_LATE) tmem_st16(tP + c16 * 16, pw);
       }
       ATT_TS(3)
+      // S(j+1) was issued right after this tile's scores were pulled out of tensor memory: normally long complete
+      s_ready = (MVSF_ATT_PROBE && j + 1 < ntiles) ? mbar_test_wait(bar_sf + 8 * w, (uint32_t)((j + 1) & 1)) : 0u;
       if (FOLD_LATE) {
         // O_w(j-1) = P_w(j-1) V(j-1) is only needed here, a whole exponential phase after it was issued: the fold never
         // waits for the tensor core; P_w(j) stays in registers until P_w(j-1) has been consumed
@@ -435,10 +480,11 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
     }
 #if MVSF_ATT_TRACE
     if (lane == 0 && (quarter == 2) && blockIdx.x == 3 && blockIdx.y == 1)
-      printf("softmax warp %d (tile %d half %d) clk/tile: wait S %u, ld S %u, max+exchange %u, exps %u, fold+st %u, st wait+arrive %u | total %u\n",
-             warp, w, half, ts[0] / ntiles, ts[1] / ntiles, ts[2] / ntiles, ts[3] / ntiles, ts[4] / ntiles, ts[5] / ntiles,
-             (ts[0] + ts[1] + ts[2] + ts[3] + ts[4] + ts[5]) / ntiles);
+      printf("softmax warp %d (tile %d half %d) clk/tile: wait S %u, ld S %u, row max %u, exchange barrier %u, new max + corr %u, exps %u, fold+st %u, st wait+arrive %u | total %u\n",
+             warp, w, half, ts[0] / ntiles, ts[1] / ntiles, ts[6] / ntiles, ts[7] / ntiles, ts[2] / ntiles, ts[3] / ntiles, ts[4] / ntiles, ts[5] / ntiles,
+             (ts[0] + ts[1] + ts[2] + ts[3] + ts[4] + ts[5] + ts[6] + ts[7]) / ntiles);
 #endif
+    o_ready = 0;
     fold(ntiles - 1);
     const int qt = qt0 + w;
     const int r = qt * 128 + row;
@@ -455,6 +501,7 @@ attention_fa_kernel(const __half* __restrict__ tiled, float* __restrict__ out, _
       if (out2) split_store8(out2 + (size_t)r * 128 + col, out2 + (size_t)r * 128 + 64 + col, res);
     }
   }
+done:
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);

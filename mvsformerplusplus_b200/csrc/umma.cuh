@@ -36,6 +36,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe.  An mbarrier query has a latency of 120-260 clk even when the phase completed long ago
+// (tools/mbar_microbench.cu): issue the probe EARLY, do independent work, look at the answer later.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 // bounded wait: a mis-programmed pipeline traps (sticky CUDA error) instead of hanging the device
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t it = 0; it < (1u << 26); ++it)

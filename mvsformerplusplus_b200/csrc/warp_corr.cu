@@ -15,6 +15,9 @@
 // (cost_volume.py:89-93); recomputing the gather is cheaper than spilling (V-1) x G x D x H x W floats.
 #include <float.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace mvsf {
@@ -27,7 +30,7 @@ int warp_tile_aggregate(const float* feat, const float* homs, const float* depth
                         int D, int H, int W, cudaStream_t s);
 bool warp_stream_store_supported(const float* feat, const float* corr, int C, int G, int D, int H, int W);
 int warp_stream_entropy_store(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
-                              int C, int D, int H, int W, cudaStream_t s);
+                              int C, int D, int H, int W, int* select, int max_miss_permille, cudaStream_t s);
 
 constexpr int kMaxGenericD = 512;
 
@@ -106,8 +109,9 @@ template <int C, bool GENERIC, int CPGS>
 __global__ void __launch_bounds__(256)
 warp_corr_entropy_kernel(const float* __restrict__ feat, const float* __restrict__ homs,
                          const float* __restrict__ depth, float* __restrict__ entropy, float* __restrict__ corr, int G,
-                         int D, int H, int W) {
+                         int D, int H, int W, const int* __restrict__ skip_if) {
   constexpr int LPP = WC<C>::LPP, P = WC<C>::P, DCH = WC<C>::DCH;
+  if (skip_if && *skip_if != 0) return;   // the pipeline kernel (warp_tile.cu) served this call
   constexpr int SPL = DCH / LPP;  // complete sims per lane per chunk (= 2)
   constexpr int MAXCH = GENERIC ? (kMaxGenericD + DCH - 1) / DCH : 1;
   __shared__ TapTable tables[8];
@@ -322,18 +326,18 @@ __global__ void homo_warp_kernel(const float* __restrict__ src, const float* __r
 
 template <int C>
 static int launch_entropy(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V, int G,
-                          int D, int H, int W, cudaStream_t s) {
+                          int D, int H, int W, cudaStream_t s, const int* skip_if = nullptr) {
   constexpr int P = WC<C>::P;
   dim3 grid(cdiv((long long)H * W, 8 * P), V - 1);
   if (corr) {   // G == 8 (checked by the caller)
     if (D == WC<C>::DCH)
-      warp_corr_entropy_kernel<C, false, C / 8><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, corr, G, D, H, W);
+      warp_corr_entropy_kernel<C, false, C / 8><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, corr, G, D, H, W, skip_if);
     else
-      warp_corr_entropy_kernel<C, true, C / 8><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, corr, G, D, H, W);
+      warp_corr_entropy_kernel<C, true, C / 8><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, corr, G, D, H, W, skip_if);
   } else if (D == WC<C>::DCH) {
-    warp_corr_entropy_kernel<C, false, 0><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, nullptr, G, D, H, W);
+    warp_corr_entropy_kernel<C, false, 0><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, nullptr, G, D, H, W, skip_if);
   } else {
-    warp_corr_entropy_kernel<C, true, 0><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, nullptr, G, D, H, W);
+    warp_corr_entropy_kernel<C, true, 0><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, nullptr, G, D, H, W, skip_if);
   }
   return 0;
 }
@@ -375,12 +379,51 @@ using namespace mvsf;
 
 // test hook: 0 forces the L1-gather organisation (warp_corr.cu) for every shape, 1 (default) lets C = 8 / 16 stages use
 // the TMA-staged window kernels (warp_tile.cu).  Both compute the same function; tests compare them.
-static int g_use_tile = 1;
+static int g_use_tile = 1;            // 0: L1-gather kernels everywhere, 1: adaptive (default), 2: window / pipeline kernels wherever they exist
+static int g_max_miss_permille = 60;  // adaptive choice: the pipeline kernel serves a call when <= this share of the sampled taps miss its window
+
+// Selection slots of the adaptive pass-A choice: 8 ints per call (decision, miss share, 3 scratch counters), a ring per device so that calls in
+// flight on different streams do not share a slot.  Allocated on the first call (like the kernels' attribute set-up).
+constexpr int kSelectSlots = 256;
+static int* g_select[16] = {};
+static std::atomic<unsigned> g_select_next{0};
+static std::atomic<int*> g_select_last{nullptr};
+static std::mutex g_select_mu;
+static int* select_slot() {
+  const int dev = current_device();
+  if (dev < 0 || dev >= 16) return nullptr;
+  if (!g_select[dev]) {
+    std::lock_guard<std::mutex> lock(g_select_mu);
+    if (!g_select[dev]) {
+      int* p = nullptr;
+      if (cudaMalloc(&p, sizeof(int) * 8 * kSelectSlots) != cudaSuccess) return nullptr;
+      cudaMemset(p, 0, sizeof(int) * 8 * kSelectSlots);
+      g_select[dev] = p;
+    }
+  }
+  int* slot = g_select[dev] + 8 * (g_select_next.fetch_add(1) % kSelectSlots);
+  g_select_last.store(slot);
+  return slot;
+}
 
 extern "C" {
 
 int mvsf_warp_corr_set_tile_path(int enable) {
-  g_use_tile = enable != 0;
+  g_use_tile = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+  return MVSF_OK;
+}
+int mvsf_warp_corr_set_max_window_miss(int permille) {
+  MVSF_REQUIRE(permille >= 0 && permille <= 1000, "warp_corr_set_max_window_miss: 0..1000");
+  g_max_miss_permille = permille;
+  return MVSF_OK;
+}
+int mvsf_warp_corr_last_selection(int* used_pipeline, int* miss_permille) {
+  int* slot = g_select_last.load();
+  MVSF_REQUIRE(slot && used_pipeline && miss_permille, "warp_corr_last_selection: no adaptive call has been made yet");
+  int h[2] = {0, 0};
+  MVSF_CUDA_OK(cudaMemcpy(h, slot, sizeof(h), cudaMemcpyDeviceToHost));   // synchronises: diagnostics / tests only
+  *used_pipeline = h[0];
+  *miss_permille = h[1];
   return MVSF_OK;
 }
 
@@ -425,11 +468,23 @@ static int warp_corr_entropy_impl(const float* feat, const float* homs, const fl
   MVSF_REQUIRE(D <= kMaxGenericD, "warp_corr_entropy: D <= %d", kMaxGenericD);
   cudaStream_t s = (cudaStream_t)stream;
   if (corr && g_use_tile && warp_stream_store_supported(feat, corr, C, G, D, H, W)) {
-    // fine stages of the cascade (C = 8, D = 4 and C = 16, D = 8): persistent TMA producer / consumer pipeline
-    int rc = warp_stream_entropy_store(feat, homs, depth, entropy, corr, V, C, D, H, W, s);
-    if (rc) return rc;
-    MVSF_LAUNCH_CHECK("warp_stream_entropy_store");
-    return MVSF_OK;
+    // finest stage of the cascade (C = 8, D = 4): persistent TMA producer / consumer pipeline kernel, as long as the taps of
+    // this call fit its windows (decided on the device, per call: see warp_stream_select_kernel).  The C = 16, D = 8
+    // instance is not faster than the L1 kernel on either workload (DTU 0.345 vs 0.336 ms, T&T 1.88 vs 0.94 ms) and only
+    // runs when forced (mvsf_warp_corr_set_tile_path(2)).
+    const bool forced = g_use_tile == 2;
+    if (forced || C == 8) {
+      int* select = forced ? nullptr : select_slot();
+      if (forced || select) {
+        int rc = warp_stream_entropy_store(feat, homs, depth, entropy, corr, V, C, D, H, W, select, g_max_miss_permille, s);
+        if (rc) return rc;
+        MVSF_LAUNCH_CHECK("warp_stream_entropy_store");
+        if (forced) return MVSF_OK;
+        launch_entropy<8>(feat, homs, depth, entropy, corr, V, G, D, H, W, s, select);   // returns at once unless select[0] == 0
+        MVSF_LAUNCH_CHECK("warp_corr_entropy");
+        return MVSF_OK;
+      }
+    }
   }
   if (!corr && g_use_tile && warp_tile_supported(feat, C, G, D, H, W)) {
     int rc = warp_tile_entropy(feat, homs, depth, entropy, V, C, D, H, W, s);

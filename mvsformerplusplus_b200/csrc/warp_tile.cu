@@ -462,11 +462,13 @@ template <int C, int D, int NBUF>
 __global__ void __launch_bounds__(PsCfg<C>::THREADS, (C == 8) ? MVSF_PS_BLOCKS8 : 1)
 warp_stream_entropy_store_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ feat,
                                  const float* __restrict__ homs, const float* __restrict__ depth, float* __restrict__ entropy,
-                                 float* __restrict__ corr, int V, int H, int W, int tiles_x, int ntiles, int dbg) {
+                                 float* __restrict__ corr, int V, int H, int W, int tiles_x, int ntiles, int dbg,
+                                 const int* __restrict__ select) {
   using K = Cfg<C>;
   using P = PsCfg<C>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ PsShared<NBUF> sh;
+  if (select && *select == 0) return;   // warp_stream_select_kernel chose the L1-gather kernel for this call (launched next)
   const uint32_t win0 = (smem_u32(smem_raw) + 127u) & ~127u;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int HW = H * W;
@@ -622,6 +624,82 @@ warp_stream_entropy_store_kernel(const __grid_constant__ CUtensorMap map, const 
   }
 }
 
+
+// Which pass-A kernel should serve this call?  The pipeline kernel wins as long as nearly every tap lies in the 64 x 16 texel
+// window its producer predicts (DTU stage 4: 28 misses per 1000 taps, 0.36 vs 0.51 ms); a tap outside goes through a divergent
+// global gather, and with wide baselines + noisy hypotheses (Tanks&Temples, 9 source views: 287 per 1000, 1.57 vs 1.43 ms)
+// the L1-gather kernel is faster.  CTA b replays the producer's prediction for sample tile b (one warp per source view) and
+// counts, for the tile's 32 sample pixels, the hypotheses whose tap misses the window; the last CTA to finish turns the
+// totals into the decision and clears the scratch counters for the slot's next use.
+//   select[0] = 1: pipeline kernel, 0: L1 kernel;  select[1] = misses per 1000 in-bound taps (diagnostics);
+//   select[2..4] = scratch: taps, misses, finished CTAs (zero between calls).
+// Both kernels are launched behind it; the one not chosen returns at once.
+template <int C, int D>
+__global__ void __launch_bounds__(1024)
+warp_stream_select_kernel(const float* __restrict__ homs, const float* __restrict__ depth, int V, int H, int W, int tiles_x,
+                          int ntiles, int max_miss_permille, int* __restrict__ select) {
+  using K = Cfg<C>;
+  using P = PsCfg<C>;
+  const int lane = threadIdx.x & 31, HW = H * W;
+  const CoordConst cc = make_coord_const(W, H);
+  const int sr = (lane >> 3) * 2 + 1, sc = (lane & 7) * 4 + 1;   // the producer's sample pixels
+  const int tile = (int)(((long long)blockIdx.x * ntiles) / gridDim.x);
+  const int px = min((tile % tiles_x) * TW + sc, W - 1), py = min((tile / tiles_x) * P::TROWS + sr, H - 1);
+  const int p = py * W + px;
+  const float fxp = (float)px, fyp = (float)py;
+  float dv[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) dv[k] = __ldg(depth + (size_t)k * HW + p);
+  unsigned int tot = 0u, miss = 0u;
+  for (int v = threadIdx.x >> 5; v < V - 1; v += blockDim.x >> 5) {
+    const Hom m = load_hom(homs + (size_t)v * 12);
+    const float rx = __fadd_rn(fmaf(m.r01, fyp, __fmul_rn(m.r00, fxp)), m.r02);
+    const float ry = __fadd_rn(fmaf(m.r11, fyp, __fmul_rn(m.r10, fxp)), m.r12);
+    const float rz = __fadd_rn(fmaf(m.r21, fyp, __fmul_rn(m.r20, fxp)), m.r22);
+    TapCoord tc[D];
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      float ix, iy;
+      warp_coord_lean(rx, ry, rz, m, dv[k], cc, ix, iy);
+      tc[k] = split_coord(ix, iy, W, H);
+      if ((k == 0 || k == D - 1) && tc[k].inb) { mnx = min(mnx, tc[k].x0); mxx = max(mxx, tc[k].x0); mny = min(mny, tc[k].y0); mxy = max(mxy, tc[k].y0); }
+    }
+    mnx = __reduce_min_sync(0xffffffffu, mnx);
+    mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mny = __reduce_min_sync(0xffffffffu, mny);
+    mxy = __reduce_max_sync(0xffffffffu, mxy);
+    int ox = 0, oy = 0;
+    if (mnx <= mxx) {
+      const int slack_x = K::WX - (mxx + 2 - mnx), slack_y = K::WY - (mxy + 2 - mny);
+      ox = mnx - (slack_x > 0 ? slack_x / 2 : 0);
+      oy = (mny - (slack_y > 0 ? slack_y / 2 : 0)) & ~1;
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      if (!tc[k].inb) continue;
+      ++tot;
+      const int lx = tc[k].x0 - ox, ly = tc[k].y0 - oy;
+      if (!((unsigned)lx <= (unsigned)(K::WX - 2) && (unsigned)ly <= (unsigned)(K::WY - 2))) ++miss;
+    }
+  }
+  tot = __reduce_add_sync(0xffffffffu, tot);
+  miss = __reduce_add_sync(0xffffffffu, miss);
+  if (lane == 0) { atomicAdd(select + 2, (int)tot); atomicAdd(select + 3, (int)miss); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(select + 4, 1) == (int)gridDim.x - 1) {   // last CTA: every other CTA's counts are visible
+      __threadfence();
+      const unsigned int t = (unsigned int)atomicExch(select + 2, 0), ms = (unsigned int)atomicExch(select + 3, 0);
+      const unsigned int permille = t ? (unsigned int)(((unsigned long long)ms * 1000ull) / t) : 0u;
+      select[1] = (int)permille;
+      select[0] = permille <= (unsigned int)max_miss_permille ? 1 : 0;
+      atomicExch(select + 4, 0);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -693,7 +771,7 @@ static int dispatch(int mode, const float* feat, const float* homs, const float*
 
 template <int C, int D, int NBUF>
 static int launch_stream_store(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
-                               int H, int W, cudaStream_t s) {
+                               int H, int W, int* select, int max_miss_permille, cudaStream_t s) {
   using K = Cfg<C>;
   auto kern = warp_stream_entropy_store_kernel<C, D, NBUF>;
   static DeviceOnce once;
@@ -710,7 +788,11 @@ static int launch_stream_store(const float* feat, const float* homs, const float
   const int per_sm = (C == 8) ? MVSF_PS_BLOCKS8 : 1;
   const int cap = device_sm_count(dev) * per_sm;
   static const int dbg = getenv("MVSF_WT_DEBUG") ? atoi(getenv("MVSF_WT_DEBUG")) : 0;   // measurement knobs (1: no staging, 2: no
-  kern<<<ntiles < cap ? ntiles : cap, PsCfg<C>::THREADS, smem, s>>>(map, feat, homs, depth, entropy, corr, V, H, W, tiles_x, ntiles, dbg);   // window gather, 4: no fallback, 8: no store)
+  if (select) {
+    const int nsample = ntiles < 96 ? ntiles : 96, warps = V - 1 < 32 ? V - 1 : 32;
+    warp_stream_select_kernel<C, D><<<nsample, 32 * warps, 0, s>>>(homs, depth, V, H, W, tiles_x, ntiles, max_miss_permille, select);
+  }
+  kern<<<ntiles < cap ? ntiles : cap, PsCfg<C>::THREADS, smem, s>>>(map, feat, homs, depth, entropy, corr, V, H, W, tiles_x, ntiles, dbg, select);   // window gather, 4: no fallback, 8: no store)
   return MVSF_OK;
 }
 
@@ -739,10 +821,12 @@ int warp_tile_aggregate(const float* feat, const float* homs, const float* depth
 bool warp_stream_store_supported(const float* feat, const float* corr, int C, int G, int D, int H, int W) {
   return warp_tile_supported(feat, C, G, D, H, W) && ((C == 8 && D == 4) || (C == 16 && D == 8)) && ((uintptr_t)corr & 15) == 0;
 }
+// select != nullptr: five device ints (decision, miss share, three zeroed scratch counters); a small kernel decides from the geometry of THIS call whether the pipeline kernel runs
+// (select[0] = 1) or leaves the call to the L1-gather kernel the caller launches next (select[0] = 0)
 int warp_stream_entropy_store(const float* feat, const float* homs, const float* depth, float* entropy, float* corr, int V,
-                              int C, int D, int H, int W, cudaStream_t s) {
-  if (C == 8) return wt::launch_stream_store<8, 4, MVSF_PS_NBUF8>(feat, homs, depth, entropy, corr, V, H, W, s);
-  return wt::launch_stream_store<16, 8, 3>(feat, homs, depth, entropy, corr, V, H, W, s);
+                              int C, int D, int H, int W, int* select, int max_miss_permille, cudaStream_t s) {
+  if (C == 8) return wt::launch_stream_store<8, 4, MVSF_PS_NBUF8>(feat, homs, depth, entropy, corr, V, H, W, select, max_miss_permille, s);
+  return wt::launch_stream_store<16, 8, 3>(feat, homs, depth, entropy, corr, V, H, W, select, max_miss_permille, s);
 }
 
 }  // namespace mvsf

@@ -216,18 +216,31 @@ def test_cost_volume_kernels(dev, L, C, D, H, W, V, th, jit):
         ent_t, vis_t, vol_t = run_two_gathers()
         e_tile = dict(tile_vs_l1_entropy=max_abs(ent_t.cpu(), ent.cpu()), tile_vs_l1_volume=max_abs(vol_t.cpu(), vol_s.cpu()))
         assert e_tile["tile_vs_l1_entropy"] < 2e-5 and e_tile["tile_vs_l1_volume"] < 1e-5 * vol_scale, e_tile
-        # ... and the spill plan as hotpath.py runs it (C = 8, D = 4 / C = 16, D = 8: the persistent TMA pipeline kernel)
-        ent_p = torch.empty(V - 1, H, W, device=dev)
-        corr_p = torch.full((V - 1, D, H, W, 8), float("nan"), device=dev)
-        vol_p = torch.empty(D, H, W, 8, device=dev)
-        ck(L.mvsf_warp_corr_entropy_store(P(f), P(homs), P(dd), P(ent_p), P(corr_p), V, C, 8, D, H, W, S()), "warp_corr_entropy_store")
-        vis_p = torch.empty(V - 1, H, W, device=dev)
-        ck(L.mvsf_vis_cnn(P(ent_p), P(wts), P(vis_p), V - 1, H, W, S()), "vis_cnn")
-        ck(L.mvsf_corr_aggregate(P(corr_p), P(vis_p), P(vol_p), V, 8, D, H, W, S()), "corr_aggregate")
-        e_tile.update(pipe_vs_l1_entropy=max_abs(ent_p.cpu(), ent.cpu()), pipe_vs_l1_corr=max_abs(corr_p.cpu(), corr.cpu()),
-                      pipe_vs_l1_volume=max_abs(vol_p.cpu(), vol_s.cpu()))
-        assert bool(torch.isfinite(corr_p).all())
-        assert e_tile["pipe_vs_l1_entropy"] < 2e-5 and e_tile["pipe_vs_l1_corr"] < 1e-5 * vol_scale * 8 and e_tile["pipe_vs_l1_volume"] < 1e-5 * vol_scale, e_tile
+        # ... and the spill plan: forced through the persistent TMA pipeline kernel where it exists (C = 8, D = 4 and C = 16,
+        # D = 8; mode 2), then as hotpath.py runs it (mode 1: at C = 8, D = 4 the device picks pipeline or L1 kernel per call)
+        for mode in (2, 1):
+            ck(L.mvsf_warp_corr_set_tile_path(mode), "set_tile_path")
+            try:
+                ent_p = torch.empty(V - 1, H, W, device=dev)
+                corr_p = torch.full((V - 1, D, H, W, 8), float("nan"), device=dev)
+                vol_p = torch.empty(D, H, W, 8, device=dev)
+                ck(L.mvsf_warp_corr_entropy_store(P(f), P(homs), P(dd), P(ent_p), P(corr_p), V, C, 8, D, H, W, S()), "warp_corr_entropy_store")
+            finally:
+                ck(L.mvsf_warp_corr_set_tile_path(1), "set_tile_path")
+            vis_p = torch.empty(V - 1, H, W, device=dev)
+            ck(L.mvsf_vis_cnn(P(ent_p), P(wts), P(vis_p), V - 1, H, W, S()), "vis_cnn")
+            ck(L.mvsf_corr_aggregate(P(corr_p), P(vis_p), P(vol_p), V, 8, D, H, W, S()), "corr_aggregate")
+            tag = "pipe" if mode == 2 else "adaptive"
+            e_tile.update({f"{tag}_vs_l1_entropy": max_abs(ent_p.cpu(), ent.cpu()), f"{tag}_vs_l1_corr": max_abs(corr_p.cpu(), corr.cpu()),
+                           f"{tag}_vs_l1_volume": max_abs(vol_p.cpu(), vol_s.cpu())})
+            assert bool(torch.isfinite(corr_p).all())
+            assert e_tile[f"{tag}_vs_l1_entropy"] < 2e-5 and e_tile[f"{tag}_vs_l1_corr"] < 1e-5 * vol_scale * 8 and e_tile[f"{tag}_vs_l1_volume"] < 1e-5 * vol_scale, e_tile
+            if mode == 1 and C == 8 and D == 4:
+                used, miss = ctypes.c_int(-1), ctypes.c_int(-1)
+                ck(L.mvsf_warp_corr_last_selection(ctypes.byref(used), ctypes.byref(miss)), "last_selection")
+                e_tile.update(adaptive_used_pipeline=used.value, adaptive_window_miss_permille=miss.value)
+                assert used.value in (0, 1) and 0 <= miss.value <= 1000
+                assert used.value == (1 if miss.value <= 60 else 0)   # wide baseline (theta 0.6): 193 per mille -> L1 kernel
         ent, vis, vol_s = ent_p, vis_p, vol_p
     vol = vol_s
     e_ent = max_abs(ent.cpu(), want["entropy"][0])

@@ -27,6 +27,10 @@ d = dv.to(dev)
 for _ in range(a.iters):
     net.forward_features(f, p, d, bench.TMP)
 torch.cuda.synchronize()
+import ctypes  # noqa: E402
+used, miss = ctypes.c_int(-1), ctypes.c_int(-1)
+if _lib.lib().mvsf_warp_corr_last_selection(ctypes.byref(used), ctypes.byref(miss)) == 0:
+    print(f"finest stage, pass A: pipeline kernel chosen = {used.value}, sampled window misses = {miss.value} per mille")
 if a.breakdown:
     with _lib.profile_calls() as prof:
         for _ in range(3):
