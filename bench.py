@@ -215,18 +215,38 @@ def run_ours(a, wl, rank, world, local_rank):
     host_out = torch.empty((B, 2, H, W)).pin_memory()
     gather_ws = {}
 
+    # Reference views are independent: with --streams 2 consecutive steps run on alternating compute streams ("lanes"), two
+    # depth maps are in flight per GPU and the latency-bound kernels of one overlap the other's (tools/two_stream_probe.py).
+    # Off by default (see --streams).  Every step still does all of its work; a lane's buffers are reused, stream-ordered.
+    n_lanes = max(1, a.streams)
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(n_lanes)] if n_lanes > 1 else [torch.cuda.current_stream(dev)]
+    lane_bufs = [local_buf] + [torch.empty_like(local_buf) for _ in range(n_lanes - 1)]
+    lane_gathered = [torch.cuda.Event() for _ in range(n_lanes)]
+    step_no = [0]
+
     def step_resident():
-        for b, (f, p, d) in enumerate(dev_inputs):
-            out = net.forward_features(f, p, d, TMP)
-            local_buf[b, 0].copy_(out["refined_depth"][0])
-            local_buf[b, 1].copy_(out["photometric_confidence"][0])
-        # the only collective on the path: gather of the depth / confidence maps in item order
-        sharding.gather_maps(local_buf, n_items, workspace=gather_ws)
+        k = step_no[0] % n_lanes
+        step_no[0] += 1
+        lane, buf = lanes[k], lane_bufs[k]
+        with torch.cuda.stream(lane):
+            lane.wait_event(lane_gathered[k])           # the gather of this lane's previous step has read `buf`
+            for b, (f, p, d) in enumerate(dev_inputs):
+                out = net.forward_features(f, p, d, TMP)
+                buf[b, 0].copy_(out["refined_depth"][0])
+                buf[b, 1].copy_(out["photometric_confidence"][0])
+        # the only collective on the path: gather of the depth / confidence maps in item order, issued on the
+        # main stream in step order on every rank (after the lane's kernels; the other lane keeps running)
+        if world > 1:
+            main = torch.cuda.current_stream(dev)
+            if n_lanes > 1:
+                main.wait_stream(lane)
+            sharding.gather_maps(buf, n_items, workspace=gather_ws)
+            lane_gathered[k].record(main)
 
     # end to end through the package's host-side API: every step uploads its pinned host batch (copy stream, three device
     # slots: the upload of the next batches overlaps the kernels of the current one) and reads the depth + confidence maps back
     from mvsformerplusplus_b200.streaming import PrefetchingRunner
-    runner = PrefetchingRunner(net, dev, slots=3)
+    runner = PrefetchingRunner(net, dev, slots=3 if n_lanes == 1 else 2 + n_lanes, lanes=n_lanes)
 
     def step_e2e():
         n = len(host_inputs)
@@ -248,8 +268,15 @@ def run_ours(a, wl, rank, world, local_rank):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        main = torch.cuda.current_stream(dev)
+        for lane in lanes:
+            if lane is not main:
+                lane.wait_event(e0)
         for _ in range(steps):
             fn()
+        for lane in list(lanes) + list(runner.lanes):
+            if lane is not main:
+                main.wait_stream(lane)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -343,9 +370,11 @@ def run_ours(a, wl, rank, world, local_rank):
                            "precision": "fp32-class parity mode: tcgen05 GEMMs / attention scores / 3-D and 2-D convolutions on fp16 hi+lo "
                                         "split operands (22-bit mantissa, fp32 accumulate), attention probabilities fp16, "
                                         "everything else fp32 SIMT",
-                           "e2e_pipeline": "pinned host batch (allocated on the GPU's NUMA node) -> copy stream -> 3 device slots; "
-                                           "upload of batch i+1 overlaps the kernels of batch i; depth+confidence read back every step",
-                           "numa_binding": numa},
+                           "e2e_pipeline": "pinned host batch (allocated on the GPU's NUMA node) -> copy stream -> device slots; "
+                                           "upload of batch i+1 overlaps the kernels of batch i; depth+confidence read back every step; "
+                                           "consecutive steps alternate between `compute_streams` streams (two depth maps in flight)",
+                           "numa_binding": numa,
+                           "compute_streams": n_lanes if n_lanes > 1 else 1},
                 "e2e": {"value": maps * 1000.0 / ms_e2e, "unit": "depth-maps/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
                 "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches, "clocks": clocks,
@@ -431,6 +460,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="dtu", choices=sorted(WORKLOADS) + ["dsweep"])
     ap.add_argument("--batch", type=int, default=1, help="reference views per GPU per step")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="compute streams per GPU: consecutive steps alternate between them.  EXPERIMENTAL above 1: two depth maps in "
+                         "flight measured +8.7 %% (79.8 maps/s) but the attention kernel deadlocks once in a few hundred launches when "
+                         "kernels of another stream run next to it (DESIGN.md 5); the bounded waits turn that into a CUDA error")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -7,6 +7,9 @@
 //   - TMEM alloc/dealloc and tcgen05.ld (32 lanes x 32 bit, one accumulator row per thread).
 // Field layouts follow the PTX ISA / CUTLASS cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #pragma once
+#ifndef MVSF_MBAR_SPIN_LOG2
+#define MVSF_MBAR_SPIN_LOG2 26   // bounded mbarrier waits: ~1.5 s of polling before the trap
+#endif
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -51,7 +54,7 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity
 }
 // bounded wait: a mis-programmed pipeline traps (sticky CUDA error) instead of hanging the device
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t it = 0; it < (1u << 26); ++it)
+  for (uint32_t it = 0; it < (1u << MVSF_MBAR_SPIN_LOG2); ++it)
     if (mbar_try_wait(bar, parity)) return;
 #ifdef MVSF_DEBUG_WAIT
   printf("mbarrier wait stuck: block (%d,%d) thread %d bar %x parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
@@ -110,6 +113,7 @@ __device__ __forceinline__ void commit_elect(uint32_t bar) {
       "{\n\t.reg .pred q;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+
 }
 // Lean issue path for a dedicated, converged MMA warp: the issuing warp is the critical resource of the small-N kernels
 // (a tcgen05.mma costs ~50 clk stand-alone, more when its ~20 set-up instructions compete for issue slots).  Descriptors
@@ -136,6 +140,7 @@ __device__ __forceinline__ void commit_el(uint32_t el, uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}" ::"r"(el), "r"(bar) : "memory");
+
 }
 // one lane polls, the warp reconverges (32 polling lanes steal issue slots and shared-memory bandwidth)
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
@@ -154,6 +159,7 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uin
 // arrives (count 1) on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+
 }
 // one full warp; writes the TMEM base address (lane 0, column c) to *dst_smem
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {

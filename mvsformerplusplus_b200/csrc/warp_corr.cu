@@ -480,6 +480,7 @@ static int warp_corr_entropy_impl(const float* feat, const float* homs, const fl
         if (rc) return rc;
         MVSF_LAUNCH_CHECK("warp_stream_entropy_store");
         if (forced) return MVSF_OK;
+        count_launch();   // the selection kernel
         launch_entropy<8>(feat, homs, depth, entropy, corr, V, G, D, H, W, s, select);   // returns at once unless select[0] == 0
         MVSF_LAUNCH_CHECK("warp_corr_entropy");
         return MVSF_OK;
