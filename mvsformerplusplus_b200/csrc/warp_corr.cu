@@ -105,7 +105,7 @@ struct ReduceScatter {
 // CPGS > 0: also store the per-view GROUP correlations corr[v][d][pixel][g] (G = C / CPGS = 8 groups) so that the view
 // aggregation becomes a streaming pass (corr_aggregate_kernel) instead of a second gather: the gather is bound by L1
 // requests, the extra 4 * G * D * HW * (V-1) bytes of HBM traffic each way are cheaper.
-template <int C, bool GENERIC, int CPGS>
+template <int C, bool GENERIC, int CPGS, bool STRIDED = false>
 __global__ void __launch_bounds__(256)
 warp_corr_entropy_kernel(const float* __restrict__ feat, const float* __restrict__ homs,
                          const float* __restrict__ depth, float* __restrict__ entropy, float* __restrict__ corr, int G,
@@ -119,8 +119,13 @@ warp_corr_entropy_kernel(const float* __restrict__ feat, const float* __restrict
   TapTable& tb = tables[warp];
   const int HW = H * W;
   const int v = blockIdx.y;
-  const int pix0 = (blockIdx.x * 8 + warp) * P;
-  if (pix0 >= HW) return;  // whole warp exits together
+  // STRIDED (the adaptive launch behind the selection kernel, C = 8): a capped grid strides over the 8-warp pixel blocks, so
+  // that the launch that finds skip_if set costs microseconds instead of 55 000 exiting CTAs (and the kernel itself is
+  // faster at C = 8, T&T 1.43 -> 1.24 ms; at C = 16..64 the loop costs registers - 143 at C = 64 - and is not used)
+  int bx = blockIdx.x;
+  do {
+  const int pix0 = (bx * 8 + warp) * P;
+  if (pix0 >= HW) return;  // whole warp exits together (later blocks lie further out still)
   // phase-1 pixel (lane % P) and phase-2 pixel (lane / LPP)
   const int p1 = min(pix0 + lane % P, HW - 1);
   const int p2raw = pix0 + lane / LPP;
@@ -195,6 +200,8 @@ warp_corr_entropy_kernel(const float* __restrict__ feat, const float* __restrict
 #pragma unroll
   for (int o = LPP / 2; o > 0; o >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, o);
   if (active && lip == 0) entropy[(size_t)v * HW + p2] = ent;
+  if (STRIDED) __syncwarp();   // the warp's tap table is rewritten by the next trip
+  } while (STRIDED && (bx += (int)gridDim.x) * 8 * P < HW);
 }
 
 // ---------------------------------------------------------------------------------------------- pass B
@@ -329,6 +336,15 @@ static int launch_entropy(const float* feat, const float* homs, const float* dep
                           int D, int H, int W, cudaStream_t s, const int* skip_if = nullptr) {
   constexpr int P = WC<C>::P;
   dim3 grid(cdiv((long long)H * W, 8 * P), V - 1);
+  if (skip_if) {   // adaptive launch (may find nothing to do): a capped, grid-strided grid
+    const int cap = device_sm_count(current_device()) * 16;
+    if ((int)grid.x > cap) grid.x = cap;
+    if (corr && D == WC<C>::DCH) {
+      warp_corr_entropy_kernel<C, false, C / 8, true><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, corr, G, D, H, W, skip_if);
+      return 0;
+    }
+    return -1;   // only the spill plan's fixed-D instance is launched this way
+  }
   if (corr) {   // G == 8 (checked by the caller)
     if (D == WC<C>::DCH)
       warp_corr_entropy_kernel<C, false, C / 8><<<grid, 256, 0, s>>>(feat, homs, depth, entropy, corr, G, D, H, W, skip_if);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence of the kernels as shipped: CSV exports only (the .ncu-rep files stay on the box)
 mkdir -p gpurun_out
-bash tools/ncu_capture.sh r2_ncu_costvolume "warp_|corr_aggregate|vis_cnn" 12 -- python tools/profile_forward.py --iters 1
+bash tools/ncu_capture.sh r2_ncu_costvolume "warp_|corr_aggregate|vis_cnn" 16 -- python tools/profile_forward.py --iters 1
 bash tools/ncu_capture.sh r2_ncu_fmt "fmt_smooth|reduce1x1|linattn|kv_partial|layernorm64" 12 -- python tools/profile_forward.py --iters 1
 bash tools/ncu_capture.sh r2_ncu_linear "linear_tc" 10 -s 20 -- python tools/profile_forward.py --iters 1
 bash tools/ncu_capture.sh r2_ncu_conv3d "conv3d" 27 -- python tools/profile_forward.py --iters 1
