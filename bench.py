@@ -330,7 +330,8 @@ def run_ours(a, wl, rank, world, local_rank):
                                   "traffic": traffic, "peak_source": tf_which, "algorithmic_flops_per_launch": att_flops,
                                   "launch_ms": att_launch_ms, "launches_per_depth_map": att_n // reps,
                                   "share_of_step": att_ms / reps / ms_step if ms_step > 0 else None,
-                                  "note": "bound by the XU pipe (ncu: 81.7 % busy): 3.06e9 exp2 per launch at 16 / clk / SM = 0.66 ms; "
+                                  "note": "bound by the XU pipe (ncu: 83.7 % busy): 3.06e9 exp2 per launch at 16 / clk / SM = 0.66 ms, plus the "
+                                          "mbarrier handshake latency between the MMA and softmax warps (DESIGN.md 4); "
                                           "Q/K/V are fp16 hi+lo (3 products for the scores), the probabilities fp16"}
         # the fused warp + group-correlation kernels are the HBM-roofline kernels of the path (8 launches / depth map)
         t_wc = sum(per_map.get(k, 0.0) for k in ("mvsf_warp_corr_entropy", "mvsf_warp_corr_aggregate",
@@ -345,9 +346,10 @@ def run_ours(a, wl, rank, world, local_rank):
                                       "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                                       "traffic": traffic_wc, "peak_source": which, "algorithmic_bytes_per_depth_map": sum(alg),
                                       "kernel_ms_per_depth_map": t_wc,
-                                      "note": "algorithmic bytes = features + hypotheses + volume; traffic = measured DRAM bytes of the 8 "
-                                              "launches (profiles/r2_ncu_traffic.json): the per-view group correlations spilled between "
-                                              "the two passes are implementation traffic.  The 4-corner fp32 gather is bound by the SM "
+                                      "note": "algorithmic bytes = features + hypotheses + volume; traffic = measured DRAM bytes of the pass-A / "
+                                              "pass-B launches of one depth map (profiles/r2_ncu_traffic.json; stage 4 pass A = selection kernel + "
+                                              "TMA pipeline kernel + the L1 kernel's skipped launch): the per-view group correlations spilled "
+                                              "between the two passes are implementation traffic.  The 4-corner fp32 gather is bound by the SM "
                                               "load path (3.6 GB per stage and pass at 128 B/clk/SM): ceiling ~0.22 of the HBM roofline"}
         line_extra["kernel_ms_per_depth_map"] = {k.replace("mvsf_", ""): round(v, 4) for k, v in sorted(per_map.items())}
 
