@@ -92,6 +92,10 @@ int mvsf_warp_corr_set_tile_path(int mode);
 int mvsf_warp_corr_set_max_window_miss(int permille);
 int mvsf_warp_corr_last_selection(int* used_pipeline, int* miss_permille);
 
+/* ---- measurement hook: 1 = prefer the largest shared-memory carve-out for every kernel of the context (cudaDeviceSetCacheConfig),
+ * 0 = driver default.  Used to test whether carve-out switches play a part in the two-stream deadlock. */
+int mvsf_set_prefer_shared_carveout(int on);
+
 /* ---- which of the two cost-volume plans to run for a stage shape: 1 = two gathers (mvsf_warp_corr_entropy, mvsf_vis_cnn,
  * mvsf_warp_corr_aggregate; no intermediate buffer), 0 = spill plan (mvsf_warp_corr_entropy_store, mvsf_vis_cnn,
  * mvsf_corr_aggregate; needs a [(V-1)][D][H][W][8] fp32 buffer; the faster one on B200).  Both give the same volume. */

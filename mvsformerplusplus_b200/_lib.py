@@ -23,6 +23,7 @@ SIGNATURES = {
     "mvsf_homo_warp": ([P, P, P, P, P, I, I, I, I, P], I),
     "mvsf_warp_corr_set_tile_path": ([I], I),
     "mvsf_warp_corr_set_max_window_miss": ([I], I),
+    "mvsf_set_prefer_shared_carveout": ([I], I),
     "mvsf_warp_corr_last_selection": ([ctypes.POINTER(I), ctypes.POINTER(I)], I),
     "mvsf_warp_corr_plan": ([I, I, I, I, I, I, Z], I),
     "mvsf_warp_corr_entropy": ([P, P, P, P, I, I, I, I, I, I, P], I),
@@ -68,6 +69,8 @@ def lib():
             L.mvsf_vis_cnn_set_precision(int(os.environ["MVSF_VIS_XLO"]))
         if os.environ.get("MVSF_WARP_TILE", "1") in ("0", "2"):   # A-B measurements: 0 force the L1-gather kernels, 2 force the window kernels
             L.mvsf_warp_corr_set_tile_path(int(os.environ["MVSF_WARP_TILE"]))
+        if os.environ.get("MVSF_PREFER_SHARED") in ("0", "1"):   # measurement: one shared-memory carve-out for every kernel
+            L.mvsf_set_prefer_shared_carveout(int(os.environ["MVSF_PREFER_SHARED"]))
         if os.environ.get("MVSF_WT_MAX_MISS"):
             L.mvsf_warp_corr_set_max_window_miss(int(os.environ["MVSF_WT_MAX_MISS"]))
         _lib = L
@@ -99,7 +102,7 @@ class profile_calls:
         for name in SIGNATURES:
             if name.endswith("_workspace_bytes") or name in ("mvsf_abi_version", "mvsf_launch_count", "mvsf_ktimer_enable",
                                                              "mvsf_ktimer_read", "mvsf_warp_corr_plan",
-                                                             "mvsf_warp_corr_set_tile_path", "mvsf_warp_corr_set_max_window_miss",
+                                                             "mvsf_warp_corr_set_tile_path", "mvsf_warp_corr_set_max_window_miss", "mvsf_set_prefer_shared_carveout",
                                                              "mvsf_warp_corr_last_selection", "mvsf_attention_set_precision",
                                                              "mvsf_vis_cnn_set_precision"):
                 continue
